@@ -1,0 +1,246 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures by running the REFERENCE's own code on seeded synthetic inputs.
+
+Run in the authoring container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference modules are imported unmodified from ``/root/reference``; the two packages they import
+that are not installable here are replaced by stubs *before* import:
+
+* ``sentence_transformers`` — only the name ``SentenceTransformer`` is needed at import (SDAG.py:7,
+  dense.py:8, malicious_selection.py:7); the ranker object passed in is ``tests/synth.HashRanker``.
+* ``faiss`` — ``dense.py:6`` imports it; the index object passed in is ``oracle.flat_ip.FlatIPOracle``
+  (so the search arithmetic itself stays "parity unpinned", see oracle/__init__.py).
+
+Outputs (all small): masks.npz, attention.npz, generation.json, knn.json, selector.json, retrieval.json,
+ranked_list.json.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, "/root/reference")
+
+sys.modules.setdefault("sentence_transformers", types.SimpleNamespace(SentenceTransformer=object))
+sys.modules.setdefault("faiss", types.SimpleNamespace(read_index=None))
+
+import synth  # noqa: E402
+from oracle.flat_ip import FlatIPOracle  # noqa: E402
+from oracle.sdag_mask import synthetic_layout  # noqa: E402
+from src.pipeline.attack import malicious_selection as ref_sel  # noqa: E402
+from src.pipeline.retrieval import dense as ref_dense  # noqa: E402
+from src.pipeline.sparse_attention_RAG import SDAG as ref_sdag  # noqa: E402
+from src.pipeline.utils import ranked_list as ref_rl  # noqa: E402
+from src.pipeline.utils.prompts import SYSTEM_PROMPT_RAG, USER_RAG_PROMPT  # noqa: E402
+
+
+def mask_cases():
+    """(name, L, S, spans, qa_start, neighbours) — layouts incl. the quirks of SURVEY.md Appendix A."""
+    cases = []
+    L, S, spans, qa = synthetic_layout(5, 3, 7, 2, 6)
+    cases.append(("strict_small", L, S, spans, qa, None))
+    cases.append(("nbrs_directed", L, S, spans, qa, [[2], [0, 2], []]))
+    cases.append(("nbrs_len_mismatch_off", L, S, spans, qa, [[1], [0]]))
+    cases.append(("nbrs_oob_self_dup", L, S, spans, qa, [[0, 0, 5, -1], [1, 2, 2], [7]]))
+    cases.append(("ragged", 61, 9, [(9, 12), (14, 33), (33, 40), (45, 46)], 50, [[3], [], [1, 0], [2]]))
+    cases.append(("no_docs", 20, 8, [], 12, None))
+    cases.append(("no_qa", 30, 4, [(4, 14), (16, 28)], 30, None))
+    cases.append(("no_gaps", 5 + 3 * 8 + 4, 5, [(5, 13), (13, 21), (21, 29)], 29, [[1], [2], [0]]))
+    cases.append(("empty_neighbour_lists", L, S, spans, qa, [[], [], []]))
+    L, S, spans, qa = synthetic_layout(48, 5, 256, 1, 24)
+    cases.append(("cfg1_k5x256", L, S, spans, qa, None))
+    L, S, spans, qa = synthetic_layout(48, 10, 256, 1, 24)
+    cases.append(("cfg2_k10x256", L, S, spans, qa, None))
+    L, S, spans, qa = synthetic_layout(48, 10, 256, 0, 24)
+    cases.append(("cfg2_nogap", L, S, spans, qa, None))
+    L, S, spans, qa = synthetic_layout(130, 6, 200, 2, 40)
+    rng = np.random.default_rng(42)
+    emb = rng.standard_normal((6, 32)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    sims = emb @ emb.T
+    nb = [[int(j) for j in np.argsort(-sims[r]) if j != r][:2] for r in range(6)]
+    cases.append(("mid_k6x200_K2", L, S, spans, qa, nb))
+    return cases
+
+
+def gen_masks():
+    small, meta = {}, []
+    for name, L, S, spans, qa, nb in mask_cases():
+        m = ref_sdag.build_blocked_causal_mask_full(
+            base_seq_len=L, max_new_tokens=500, sys_user_len=S, doc_token_spans=spans, qa_start=qa,
+            device="cpu", doc_neighbors=nb,
+        ).numpy()
+        packed = np.packbits(m, axis=1)
+        entry = dict(name=name, L=L, S=S, spans=[list(s) for s in spans], qa_start=qa, neighbors=nb,
+                     pairs=int(m.sum()), gap_rows=int((~m.any(axis=1)).sum()),
+                     sha256=hashlib.sha256(packed.tobytes()).hexdigest())
+        meta.append(entry)
+        if L <= 256:
+            small[name] = packed
+    # config 5 (L = 32 122): count only (the bool mask is ~1 GiB)
+    L, S, spans, qa = synthetic_layout(48, 50, 640, 1, 24)
+    rng = np.random.default_rng(42)
+    emb = rng.standard_normal((50, 64)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    sims = emb @ emb.T
+    nb = [[int(j) for j in np.argsort(-sims[r]) if j != r][:2] for r in range(50)]
+    for name, nbrs in (("cfg5_k50x640_strict", None), ("cfg5_k50x640_K2", nb)):
+        m = ref_sdag.build_blocked_causal_mask_full(L, 500, S, spans, qa, "cpu", nbrs)
+        meta.append(dict(name=name, L=L, S=S, spans=[list(s) for s in spans], qa_start=qa, neighbors=nbrs,
+                         pairs=int(m.sum()), gap_rows=int((~m.any(dim=1)).sum()), sha256=None))
+        del m
+    np.savez_compressed(os.path.join(HERE, "masks.npz"), **small)
+    with open(os.path.join(HERE, "masks.json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("masks:", [(e["name"], e["pairs"]) for e in meta])
+
+
+def gen_attention():
+    """HF eager attention fed exactly as SDAG.py:161-176 feeds it (additive finfo.min bias), fp32."""
+    from transformers.models.llama.modeling_llama import eager_attention_forward
+
+    out = {}
+    for name, L, S, spans, qa, nb in mask_cases():
+        if L > 256:
+            continue
+        H, Hkv, D = 4, 2, 16
+        g = torch.Generator().manual_seed(abs(hash(name)) % (2**31))
+        g = torch.Generator().manual_seed(int(hashlib.sha256(name.encode()).hexdigest()[:8], 16))
+        q = torch.randn(1, H, L, D, generator=g)
+        k = torch.randn(1, Hkv, L, D, generator=g)
+        v = torch.randn(1, Hkv, L, D, generator=g)
+        mask = ref_sdag.build_blocked_causal_mask_full(L, 500, S, spans, qa, "cpu", nb)
+        neg = torch.finfo(torch.float32).min
+        attn = torch.zeros_like(mask, dtype=torch.float32).masked_fill(~mask, neg).unsqueeze(0).unsqueeze(1)
+        module = types.SimpleNamespace(num_key_value_groups=H // Hkv, training=False)
+        o, _ = eager_attention_forward(module, q, k, v, attn, scaling=D ** -0.5)
+        out[name + "/q"] = q[0].numpy()
+        out[name + "/k"] = k[0].numpy()
+        out[name + "/v"] = v[0].numpy()
+        out[name + "/out"] = o[0].numpy()  # [L, H, D]
+    np.savez_compressed(os.path.join(HERE, "attention.npz"), **out)
+    print("attention cases:", len(out) // 4)
+
+
+def gen_generation():
+    ref_sdag.TEMPERATURE = 0  # greedy (module-level import-time copy)
+    tok = synth.make_tokenizer()
+    model = synth.tiny_llama(len(tok))
+    ranker = synth.HashRanker()
+    docs = [d for d in synth.SAMPLE_DOCS]
+    records = []
+    for case, retrieved, mal, rank, nbr_k in (
+        ("strict_rank1", docs[:5], synth.SAMPLE_MAL[:1], 1, 0),
+        ("nbrs2_rank2_no_empty", [d for d in docs if d.strip()][:5], synth.SAMPLE_MAL[:2], 2, 2),
+        ("nbrs2_with_empty_doc_disables", docs[:5], synth.SAMPLE_MAL[:1], 1, 2),
+        ("no_attack", docs[3:6], [], 0, 0),
+    ):
+        chat, S, spans, qa, ranked = ref_sdag.build_rag_chat_and_spans(
+            tok, SYSTEM_PROMPT_RAG, USER_RAG_PROMPT, synth.SAMPLE_QUERY, mal, retrieved, rank)
+        seen = {}
+        orig_decode = tok.decode
+
+        def spy(ids, **kw):
+            seen["ids"] = [int(x) for x in ids]
+            return orig_decode(ids, **kw)
+
+        tok.decode = spy
+        ans = ref_sdag.run_rag_with_doc_isolation(
+            model=model, tokenizer=tok, query=synth.SAMPLE_QUERY, malicious_docs=mal, retrieved_docs=retrieved,
+            max_new_tokens=6, device="cpu", add_attack_in_rank=rank, ranker=ranker, doc_neighbors_k=nbr_k)
+        tok.decode = orig_decode
+        nbrs = ref_sdag.compute_doc_knn_for_docs(ranker, ranked, nbr_k) if nbr_k > 0 else None
+        L = len(tok(chat, return_tensors="pt").input_ids[0])
+        records.append(dict(case=case, retrieved=retrieved, malicious=mal, rank=rank, doc_neighbors_k=nbr_k,
+                            chat_sha256=hashlib.sha256(chat.encode()).hexdigest(), L=L, S=S,
+                            spans=[list(s) for s in spans], qa_start=qa, ranked_docs=ranked, neighbors=nbrs,
+                            new_token_ids=seen["ids"], answer=ans))
+    with open(os.path.join(HERE, "generation.json"), "w") as f:
+        json.dump(records, f, indent=1)
+    print("generation:", [(r["case"], r["L"], r["new_token_ids"]) for r in records])
+
+
+def gen_knn():
+    ranker = synth.HashRanker()
+    recs = []
+    for docs, k in ((synth.SAMPLE_DOCS, 2), ([d for d in synth.SAMPLE_DOCS if d.strip()], 3),
+                    (synth.SAMPLE_DOCS[:1], 2), (synth.SAMPLE_DOCS, 0), (["  ", "x"], 1)):
+        recs.append(dict(docs=docs, k=k, neighbors=ref_sdag.compute_doc_knn_for_docs(ranker, docs, k)))
+    with open(os.path.join(HERE, "knn.json"), "w") as f:
+        json.dump(recs, f, indent=1)
+
+
+def gen_selector():
+    ranker = synth.HashRanker()
+    retrieved = [[d for d in synth.SAMPLE_DOCS], synth.SAMPLE_DOCS[3:6], [" ", ""], synth.SAMPLE_DOCS[:2]]
+    cands = [synth.SAMPLE_MAL, synth.SAMPLE_MAL[:3], synth.SAMPLE_MAL[:2], []]
+    recs = []
+    for strategy in ("closest_to_centroid", "furthest_from_centroid"):
+        for max_docs in (1, 3, None, -1, 99):
+            random.seed(1234)
+            chosen = ref_sel.select_malicious_docs_for_batch(ranker, retrieved, cands, strategy, max_docs)
+            recs.append(dict(strategy=strategy, max_docs=max_docs, chosen=chosen))
+    for strategy in ("random", "something_else"):
+        for max_docs in (1, 2):
+            random.seed(1234)
+            chosen = ref_sel.select_malicious_docs_for_batch(ranker, retrieved, cands, strategy, max_docs)
+            recs.append(dict(strategy=strategy, max_docs=max_docs, chosen=chosen, seed=1234))
+    with open(os.path.join(HERE, "selector.json"), "w") as f:
+        json.dump(dict(retrieved=retrieved, candidates=cands, records=recs), f, indent=1)
+
+
+def gen_retrieval():
+    ranker = synth.HashRanker()
+    corpus = [f"document number {i} about topic {i % 7}" for i in range(40)]
+    meta = [dict(id=f"doc{i}", text=t) for i, t in enumerate(corpus)]
+    meta[5] = dict(text="no id here")  # id missing -> 'NA' (dense.py:120)
+    emb = np.stack([synth.text_embedding("passage: " + t) for t in corpus])
+    recs = []
+    for n_rows, k in ((40, 6), (4, 6)):
+        index = FlatIPOracle(emb.shape[1])
+        index.add(emb[:n_rows])
+        retr = ref_dense.DenseRetriever(ranker, index, meta[:n_rows])
+        queries = ["topic 3 documents", "document number 17", synth.SAMPLE_QUERY]
+        rb = retr.retrieve_batch(queries, max_k_needed=k, embed_batch_size=2)
+        recs.append(dict(n_rows=n_rows, k=k, queries=queries, docs_texts_full=rb.docs_texts_full,
+                         ids_full=rb.ids_full, scores_full=rb.scores_full,
+                         q_embs=[np.asarray(e).tolist() for e in rb.q_embs]))
+    with open(os.path.join(HERE, "retrieval.json"), "w") as f:
+        json.dump(dict(corpus=corpus, meta=meta, records=recs), f, indent=1)
+
+
+def gen_ranked_list():
+    base = ["a", "b", "c", "d"]
+    recs = []
+    for mal, pos in ((["M1"], 1), (["M1", "M2"], 2), (["M1"], 99), (["M1"], 0), ([], 3), (["M1", "M2"], [3, 1]),
+                     (["M1", "M2", "M3"], [2]), (["M1"], -1), (["M1", "M2"], [None, 2]), (["M1"], -5)):
+        random.seed(7)
+        recs.append(dict(base=base, malicious=mal, pos=pos, seed=7,
+                         out=ref_rl.inject_malicious_docs_into_ranked_list(base, mal, pos)))
+    with open(os.path.join(HERE, "ranked_list.json"), "w") as f:
+        json.dump(recs, f, indent=1)
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    gen_masks()
+    gen_attention()
+    gen_generation()
+    gen_knn()
+    gen_selector()
+    gen_retrieval()
+    gen_ranked_list()
+    print("golden fixtures written to", HERE)
