@@ -1,0 +1,161 @@
+/*
+ * sdag_b200 — C ABI of the B200 (sm_100a) library behind the two hot paths of
+ * sagie-dekel/Sparse-Document-Attention-RAG-.
+ *
+ * The reference is pure Python and has no FFI of its own; each entry point below names the
+ * reference function (file:line under /root/reference) whose arithmetic it replaces.  The Python
+ * package binds these with ctypes (see INTEGRATION.md for the stubs a maintainer of the reference
+ * would add).
+ *
+ * Conventions: raw device pointers, explicit sizes / strides (in ELEMENTS unless a name says
+ * bytes), a cudaStream_t passed as void*; return 0 on success, a cudaError_t value (< 1000) or one
+ * of the SDAG_ERR_* codes otherwise.  No call allocates device memory, throws, or synchronises the
+ * stream except where documented; workspaces are caller-owned and sized by the *_bytes queries.
+ * All functions are re-entrant per stream.
+ */
+#ifndef SDAG_B200_H_
+#define SDAG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDAG_OK 0
+#define SDAG_ERR_INVALID 1001     /* bad argument (null pointer, negative size, misaligned stride) */
+#define SDAG_ERR_UNSUPPORTED 1002 /* shape outside what the kernels implement (head_dim, nbr_k, ...) */
+#define SDAG_ERR_WORKSPACE 1003   /* caller workspace too small */
+#define SDAG_ERR_DRIVER 1004      /* tensor-map encoding unavailable / failed */
+
+#define SDAG_TILE 128             /* query rows and key columns per attention tile */
+#define SDAG_BLOCKMAP_HEADER 16   /* int32 words */
+#define SDAG_LAYOUT_HEADER 8      /* int32 words */
+#define SDAG_MAX_NBR_K 16
+#define SDAG_MAX_DOCS 512
+
+int sdag_b200_version(void);
+const char* sdag_b200_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path A — SDAG mask / block map.
+ *
+ * A prompt layout is an int32 record  [L, S, qa_start, n_docs, use_nbrs, 0, 0, 0,
+ *   spans[max_docs][2], nbrs[max_docs][nbr_k] (-1 padded)]   (stride = sdag_layout_ints()).
+ * It carries exactly the arguments of build_blocked_causal_mask_full (SDAG.py:68-76):
+ * base_seq_len, sys_user_len, doc_token_spans, qa_start, doc_neighbors (use_nbrs = the
+ * `len(doc_neighbors) == num_docs` test of SDAG.py:111).
+ * ---------------------------------------------------------------------------------------------- */
+int sdag_layout_ints(int max_docs, int nbr_k);
+
+/* Dense bool mask [L, L] (1 byte per entry) — the 1:1 replacement of
+ * build_blocked_causal_mask_full, SDAG.py:68-127, including its slice-clipping behaviour on odd
+ * inputs.  Only used at that seam and by tests; the attention path never materialises it. */
+int sdag_build_mask(const int32_t* layout_dev, int max_docs, int nbr_k, uint8_t* mask_dev, int L,
+                    void* stream);
+
+/* Block map computed from the document token offsets (replaces SDAG.py:68-127 + the bool->additive
+ * conversion of SDAG.py:164-173 on the attention path).  One map per prompt:
+ *   header[16] = {n_qtiles, n_kvtiles, status, n_gap_rows, L, cap_qtiles, cap_kvtiles,
+ *                 bit_words_per_row, pairs_lo, pairs_hi, bits_offset_ints, ...}
+ *   qtiles[cap_qtiles]   = {q0, nrows, kv_off, kv_cnt}   sorted by kv_cnt descending
+ *   kvtiles[cap_kvtiles] = {k0, ncols, doff, flags}      allowed(r,c) = c < ncols && c <= r + doff
+ * status: 0 ok; 1 layout not in canonical order (S <= s_0, spans sorted and disjoint,
+ * e_last <= qa_start) -> caller must use sdag_blockmap_from_mask; 2 capacity exceeded. */
+size_t sdag_blockmap_bytes(int L, int n_docs, int nbr_k);
+int sdag_build_blockmap(const int32_t* layouts_dev, int n_prompts, int max_docs, int nbr_k, int max_L,
+                        int32_t* blockmaps_dev, size_t blockmap_stride_bytes, void* stream);
+
+/* General path: block map of an arbitrary dense bool mask [Lq = L, L] (what
+ * generate_with_custom_mask accepts, SDAG.py:130-136).  Tiles are globally aligned; non-empty tiles
+ * carry a bit-packed copy of the mask stored inside the map buffer. */
+size_t sdag_maskmap_bytes(int L);
+int sdag_blockmap_from_mask(const uint8_t* mask_dev, int64_t row_stride, int L, int32_t* blockmap_dev,
+                            size_t blockmap_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path A — attention.  Replaces the HF attention call the reference's mask reaches:
+ * LlamaAttention.forward -> sdpa/eager  softmax(Q K^T * scaling + bias) V
+ * (transformers models/llama/modeling_llama.py:199-221, integrations/sdpa_attention.py:40-104),
+ * reached from SDAG.py:176 (prefill) and SDAG.py:193-197 (decode).
+ * bf16 in / bf16 out, fp32 softmax and accumulation; GQA: q head h reads kv head h / (H / Hkv).
+ * Rows with no allowed key produce mean_j V[j] over all Skv keys (uniform softmax over finfo.min
+ * logits — SURVEY.md Appendix A2).
+ * ---------------------------------------------------------------------------------------------- */
+size_t sdag_prefill_workspace_bytes(int B, int Hkv, int D);
+
+/* q [B,H,Lq,D] / k,v [B,Hkv,Skv,D] / out [B,Lq,H,D] addressed through element strides (innermost
+ * stride 1, others multiples of 8).  blockmaps: one per batch entry (stride in bytes, 0 = shared).
+ * D in {64, 128}. */
+int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l,
+                     const void* k, int64_t sk_b, int64_t sk_h, int64_t sk_l,
+                     const void* v, int64_t sv_b, int64_t sv_h, int64_t sv_l,
+                     void* out, int64_t so_b, int64_t so_l, int64_t so_h,
+                     int B, int H, int Hkv, int Lq, int Skv, int D, float scaling,
+                     const int32_t* blockmaps_dev, size_t blockmap_stride_bytes, int cap_qtiles,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* One decode step, dense over the cache (SDAG.py:193-197 passes no mask): q [B,H,D] (stride sq_b,
+ * sq_h), k/v cache [B,Hkv,S_cap,D], kv_len valid positions, out [B,H,D] contiguous. */
+size_t sdag_decode_workspace_bytes(int B, int H, int D, int kv_len);
+int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h,
+                    const void* k, int64_t sk_b, int64_t sk_h, int64_t sk_l,
+                    const void* v, int64_t sv_b, int64_t sv_h, int64_t sv_l,
+                    void* out, int B, int H, int Hkv, int kv_len, int D, float scaling,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path B — exact max-inner-product top-k.  Replaces faiss IndexFlatIP.search as called by
+ * search_index, src/pipeline/retrieval/dense.py:68-84.
+ *
+ * Stage 1 (ip_topk_fwd): bf16 tcgen05 GEMM over the HBM-resident bf16 shadow of the corpus, fused
+ * with a per-query threshold filter; survivors (bf16 score, row id) are appended to per-query
+ * candidate lists.  Thresholds are provable lower bounds of the final k-th exact score minus the
+ * bf16 error bound, so the true top-k is always among the candidates.
+ * Stage 2 (ip_rescore_topk): exact fp32 re-scoring of the candidates against the fp32 corpus and
+ * final ordering (score descending, id ascending) -> (D float32[Q,k], I int64[Q,k]), -1 / -FLT_MAX
+ * padding when fewer than k rows exist (dense.py:118-125 relies on that).
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 rows -> bf16 shadow rows; also max row L2 norm (atomicMax on *max_norm_dev, caller zeroes). */
+int ip_cast_rows_bf16(const float* x, void* x_bf16, float* max_norm_dev, int64_t n, int d, void* stream);
+
+typedef struct {
+  int cand_cap;     /* candidate slots per query */
+  int sample_rows;  /* rows of the first (dump) epoch */
+} ip_search_config_t;
+
+size_t ip_search_workspace_bytes(int Q, int d, int k, int cand_cap);
+/* Full single-shard search.  xq fp32 [Q,d] (device), corpus fp32 [N,d] + bf16 shadow [N,d],
+ * id_offset added to row numbers (corpus sharding), max_norm = max corpus row norm (device scalar).
+ * Outputs on device: scores float32 [Q,k], ids int64 [Q,k]; stats int32[4] =
+ * {overflowed queries (re-run exactly inside), total candidates, epochs, reserved}. */
+int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpus_bf16, int64_t N, int d,
+              int64_t id_offset, const float* max_norm_dev, int k, float* out_scores, int64_t* out_ids,
+              int32_t* stats_dev, void* workspace, size_t workspace_bytes, int cand_cap, void* stream);
+
+/* Merge G per-shard results [G,Q,k] (e.g. after ncclAllGather) into the global top-k, same order. */
+int topk_merge(const float* scores, const int64_t* ids, int G, int Q, int k, float* out_scores,
+               int64_t* out_ids, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Path B — selector.  Replaces the numeric core of _select_malicious_docs_for_query,
+ * src/pipeline/attack/malicious_selection.py:81-128: centroid = mean of retrieved embeddings (not
+ * re-normalised), sims = cand . centroid, order by sims (descending for near, ascending for far;
+ * ties -> lower index first, as np.argmax / np.argmin).  Batched over queries:
+ * retrieved [nq, R_max, d] with r_count[nq] valid rows, cand [nq, C_max, d] with c_count[nq].
+ * Outputs: sims float32 [nq, C_max], order int32 [nq, C_max] (-1 past c_count).
+ * ---------------------------------------------------------------------------------------------- */
+int centroid_select(const float* retrieved, const int32_t* r_count, int R_max, const float* cand,
+                    const int32_t* c_count, int C_max, int nq, int d, int furthest, float* sims_out,
+                    int32_t* order_out, void* stream);
+
+/* Directed kNN among the k prompt documents (compute_doc_knn_for_docs, SDAG.py:50-63): sims = E E^T
+ * fp32, per row the k_neighbors most similar other rows, most similar first. emb [n,d] -> nbrs
+ * int32 [n, k_neighbors] (-1 when fewer exist). */
+int doc_knn(const float* emb, int n, int d, int k_neighbors, int32_t* nbrs_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDAG_B200_H_ */

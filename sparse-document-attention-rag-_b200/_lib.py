@@ -1,0 +1,87 @@
+"""ctypes binding of libsdag_b200.so (the C ABI declared in include/sdag_b200.h).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdag_b200.so")
+
+SDAG_TILE = 128
+BLOCKMAP_HEADER = 16
+LAYOUT_HEADER = 8
+MAX_NBR_K = 16
+MAX_DOCS = 512
+
+
+class SdagB200Error(RuntimeError):
+    pass
+
+
+_i32, _i64, _f32, _sz, _vp = C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_void_p
+
+# name -> (restype, argtypes); every symbol include/sdag_b200.h declares
+SIGNATURES = {
+    "sdag_b200_version": (_i32, []),
+    "sdag_b200_error_string": (C.c_char_p, [_i32]),
+    "sdag_layout_ints": (_i32, [_i32, _i32]),
+    "sdag_build_mask": (_i32, [_vp, _i32, _i32, _vp, _i32, _vp]),
+    "sdag_blockmap_bytes": (_sz, [_i32, _i32, _i32]),
+    "sdag_build_blockmap": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
+    "sdag_maskmap_bytes": (_sz, [_i32]),
+    "sdag_blockmap_from_mask": (_i32, [_vp, _i64, _i32, _vp, _sz, _vp]),
+    "sdag_prefill_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "sdag_prefill_fwd": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
+                                _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32,
+                                _vp, _sz, _i32, _vp, _sz, _vp]),
+    "sdag_decode_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "sdag_decode_fwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp,
+                               _i32, _i32, _i32, _i32, _i32, _f32, _vp, _sz, _vp]),
+    "ip_cast_rows_bf16": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
+    "ip_search_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "ip_search": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "topk_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "centroid_select": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "doc_knn": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SdagB200Error(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py build` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI and the header drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = load().sdag_b200_error_string(code).decode()
+        raise SdagB200Error(f"{what} failed: {msg} (code {code})")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> 0)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
