@@ -1,0 +1,633 @@
+// Exact max-inner-product top-k for sm_100a (path B2): replaces faiss IndexFlatIP.search as called from
+// search_index, src/pipeline/retrieval/dense.py:68-84.
+//
+// faiss computes Q x N fp32 scores with blocked sgemm and keeps a k-heap per query.  Here the Q x N score
+// matrix never exists:
+//   1. a bf16 tcgen05 GEMM streams the bf16 shadow of the corpus (HBM-resident, read once per batch) against
+//      the bf16 queries; its epilogue compares every score with a per-query threshold while it is still in
+//      TMEM and appends the rare survivors (score, row) to a small per-query candidate list;
+//   2. the corpus is swept in epochs of doubling size; after each epoch a "tighten" kernel raises every
+//      query's threshold to (k-th best bf16 score so far) - 2e, where e >= |bf16 score - exact score| is a
+//      rigorous bound (Cauchy-Schwarz on the rounding errors).  Any row whose exact score reaches the final
+//      exact k-th best therefore always survives: the candidate list is a superset of the true top-k;
+//   3. candidates are re-scored exactly in fp32 against the fp32 corpus and ordered (score descending, row
+//      ascending) — so ids and scores are those of an exact fp32 search, up to fp32 summation order.
+// A query whose list overflows is re-done by an exact fp32 scan (counted in stats).
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int TM = 128;      // queries per tile (UMMA M)
+constexpr int TN = 256;      // corpus rows per tile (UMMA N)
+constexpr int KB = 64;       // k-block (one 128-byte swizzle row of bf16)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TM * KB * 2;
+constexpr int B_BYTES = TN * KB * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024;
+constexpr int SORT_MAX = 2048;
+constexpr int SCAN_SLICES = 32;
+// |bf16(x).bf16(q) - x.q| <= (2u + u^2) |x||q| with u = 2^-8, plus fp32 accumulation slack
+constexpr float ERR_COEF = 0.0078125f + 0.00048828125f;
+
+struct Cand {
+  float score;
+  int32_t row;
+};
+
+struct SearchState {   // device arrays, all indexed by query
+  float* thr;          // current emission threshold (bf16-score domain)
+  int32_t* cnt;        // candidates appended (may exceed cap -> overflow)
+  int32_t* overflow;   // sticky flag
+  float* qnorm;        // |q|
+  Cand* cand;          // [Q][cap]
+  int cap;
+};
+
+__device__ __forceinline__ uint32_t orderable(float f) {  // monotone float -> uint
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unorderable(uint32_t k) {
+  const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 rows -> bf16 rows (+ row norms).  One warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cast_rows_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, float* __restrict__ max_norm,
+                 float* __restrict__ row_norm, long long n, long long n_pad, int d) {
+  const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_pad) return;
+  float ss = 0.f;
+  for (int j = lane * 4; j < d; j += 128) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n) v = *reinterpret_cast<const float4*>(x + row * d + j);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&lo);
+    w.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(y + row * d + j) = w;
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0 && row < n) {
+    const float nr = sqrtf(ss) * 1.0000002f;  // round up: the bound must not be under-estimated
+    if (row_norm) row_norm[row] = nr;
+    if (max_norm) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nr));  // nr >= 0: int order == float order
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM + threshold filter
+// ------------------------------------------------------------------------------------------------
+struct GemmParams {
+  SearchState st;
+  int Q, n_qt;           // queries, query tiles
+  long long row_begin;   // first corpus row of this epoch (multiple of TN)
+  long long row_end;     // one past the last
+  int n_ct;              // corpus tiles in this epoch
+  int kblocks;           // d / 64
+  int dump;              // 1: positional dump of every score (first epoch)
+};
+
+__global__ void __launch_bounds__(192, 1)
+ip_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 128);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const long long n_units = static_cast<long long>(p.n_ct) * p.n_qt;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int ct = static_cast<int>(u / p.n_qt), qt = static_cast<int>(u % p.n_qt);
+        const int row0 = static_cast<int>(p.row_begin + static_cast<long long>(ct) * TN);
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          tma_load_2d(sa, &tmA, &full[s], kb * KB, qt * TM);
+          tma_load_2d(sa + A_BYTES, &tmB, &full[s], kb * KB, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc = umma_idesc_bf16_f32(TM, TN, 0, 0);
+    uint32_t it = 0, ui = 0;
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      const uint32_t a = ui & 1;
+      mbar_wait(&acc_empty[a], ((ui >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < KB / 16; ++kk)
+            umma_ss(tmem + a * TN, umma_smem_desc_sw128(sa + kk * 32, 16, 1024),
+                    umma_smem_desc_sw128(sa + A_BYTES + kk * 32, 16, 1024), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&empty[s]);
+          if (kb == p.kblocks - 1) umma_commit(&acc_full[a]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ======================= epilogue: threshold filter (warps 2..5) =======================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t ui = 0;
+    uint32_t r[32];
+    for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+      const int ct = static_cast<int>(u / p.n_qt), qt = static_cast<int>(u % p.n_qt);
+      const uint32_t a = ui & 1;
+      const int q = qt * TM + row;
+      const bool q_ok = q < p.Q;
+      const float thr = q_ok ? p.st.thr[q] : INFINITY;
+      const long long col0 = p.row_begin + static_cast<long long>(ct) * TN;
+      Cand* cq = p.st.cand + static_cast<long long>(q_ok ? q : 0) * p.st.cap;
+      mbar_wait(&acc_full[a], (ui >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < TN / 32; ++c) {
+        tmem_ld_32x32b_x32(tmem + lane_addr + a * TN + c * 32, r);
+        tmem_ld_wait();
+        const long long cb = col0 + c * 32;
+        if (p.dump) {
+          if (q_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const long long rr = cb + i;
+              if (rr < p.row_end) cq[rr - p.row_begin] = Cand{__uint_as_float(r[i]), static_cast<int32_t>(rr)};
+            }
+          }
+        } else {
+          float mx = __uint_as_float(r[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          if (mx >= thr) {  // rare: fully unrolled so r[] stays in registers
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float s = __uint_as_float(r[i]);
+              if (s >= thr && cb + i < p.row_end) {
+                const int slot = atomicAdd(&p.st.cnt[q], 1);
+                if (slot < p.st.cap) cq[slot] = Cand{s, static_cast<int32_t>(cb + i)};
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[a]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bitonic sort of 64-bit keys in shared memory, descending; n_pow2 <= SORT_MAX, blockDim = 256
+// ------------------------------------------------------------------------------------------------
+__device__ void bitonic_sort_desc(unsigned long long* keys, int n_pow2) {
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int pow2_at_least(int n) {
+  int p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// After an epoch: raise thr[q] to (k-th best bf16 score) - 2e and drop candidates below it.
+__global__ void __launch_bounds__(256)
+tighten_kernel(SearchState st, int k, int force_cnt, const float* __restrict__ max_norm) {
+  __shared__ unsigned long long keys[SORT_MAX];
+  __shared__ int n_keep_s;
+  const int q = blockIdx.x;
+  int n = force_cnt >= 0 ? force_cnt : st.cnt[q];
+  if (n > st.cap) {
+    if (threadIdx.x == 0) st.overflow[q] = 1;
+    n = st.cap;
+  }
+  Cand* cq = st.cand + static_cast<long long>(q) * st.cap;
+  const int P = pow2_at_least(n < 1 ? 1 : n);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    unsigned long long key = 0;
+    if (i < n) {
+      const Cand c = cq[i];
+      key = (static_cast<unsigned long long>(orderable(c.score)) << 32) | static_cast<uint32_t>(c.row);
+    }
+    keys[i] = key;
+  }
+  if (threadIdx.x == 0) n_keep_s = 0;
+  __syncthreads();
+  bitonic_sort_desc(keys, P);
+  float thr = st.thr[q];
+  if (n >= k) {
+    const float kth = unorderable(static_cast<uint32_t>(keys[k - 1] >> 32));
+    const float e = ERR_COEF * st.qnorm[q] * (*max_norm);
+    thr = fmaxf(thr, kth - 2.f * e);
+  }
+  int keep = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float s = unorderable(static_cast<uint32_t>(keys[i] >> 32));
+    if (s >= thr) {
+      cq[i] = Cand{s, static_cast<int32_t>(keys[i] & 0xffffffffu)};
+      ++keep;
+    }
+  }
+  if (keep) atomicAdd(&n_keep_s, keep);  // sorted descending: the kept entries form a prefix
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st.thr[q] = thr;
+    st.cnt[q] = n_keep_s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact fp32 dot of one corpus row with the query held in shared memory (one warp)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_dot_f32(const float* __restrict__ row, const float* sq, int d, int lane) {
+  float s = 0.f;
+  for (int j = lane * 4; j < d; j += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(row + j);
+    const float4 b = *reinterpret_cast<const float4*>(sq + j);
+    s = fmaf(a.x, b.x, s);
+    s = fmaf(a.y, b.y, s);
+    s = fmaf(a.z, b.z, s);
+    s = fmaf(a.w, b.w, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+__device__ __forceinline__ float warp_dot_bf16(const __nv_bfloat16* __restrict__ row, const float* sq, int d, int lane) {
+  float s = 0.f;
+  for (int j = lane * 4; j < d; j += 128) {
+    const uint2 w = *reinterpret_cast<const uint2*>(row + j);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+    const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+    const float4 b = *reinterpret_cast<const float4*>(sq + j);
+    s = fmaf(a.x, b.x, s);
+    s = fmaf(a.y, b.y, s);
+    s = fmaf(c.x, b.z, s);
+    s = fmaf(c.y, b.w, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// Overflowed queries only: exact scan of a slice of the corpus, slice-local top-k -> cand[q][slice*k ..].
+__global__ void __launch_bounds__(256)
+exact_scan_kernel(SearchState st, const float* __restrict__ xq, const float* __restrict__ corpus_f32,
+                  const __nv_bfloat16* __restrict__ corpus_bf16, long long N, int d, int k) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  float* sq = reinterpret_cast<float*>(dyn);  // [d]
+  __shared__ unsigned long long keys[SORT_MAX];
+  __shared__ int fill_s;
+  __shared__ float thr_s;
+  const int q = blockIdx.x, slice = blockIdx.y;
+  if (!st.overflow[q]) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int j = tid; j < d; j += blockDim.x) sq[j] = xq[static_cast<long long>(q) * d + j];
+  if (tid == 0) {
+    fill_s = 0;
+    thr_s = -INFINITY;
+  }
+  __syncthreads();
+  const long long per = (N + SCAN_SLICES - 1) / SCAN_SLICES;
+  const long long lo = slice * per, hi = (lo + per < N) ? lo + per : N;
+  constexpr int BATCH = 8 * 64;  // rows per round (64 per warp)
+  for (long long base = lo; base < hi; base += BATCH) {
+    for (int t = 0; t < 64; ++t) {
+      const long long rr = base + warp * 64 + t;
+      if (rr < hi) {
+        const float s = corpus_f32 ? warp_dot_f32(corpus_f32 + rr * d, sq, d, lane)
+                                   : warp_dot_bf16(corpus_bf16 + rr * d, sq, d, lane);
+        if (lane == 0 && s >= thr_s) {
+          const int slot = atomicAdd(&fill_s, 1);  // <= 512 new entries per round + k kept: fits SORT_MAX
+          keys[slot] = (static_cast<unsigned long long>(orderable(s)) << 32) | (0xffffffffu - static_cast<uint32_t>(rr));
+        }
+      }
+    }
+    __syncthreads();
+    const int n = fill_s;
+    if (n > k) {
+      const int P = pow2_at_least(n);
+      for (int i = n + tid; i < P; i += blockDim.x) keys[i] = 0;
+      __syncthreads();
+      bitonic_sort_desc(keys, P);
+      if (tid == 0) {
+        fill_s = k;
+        thr_s = unorderable(static_cast<uint32_t>(keys[k - 1] >> 32));
+      }
+    }
+    __syncthreads();
+  }
+  // slice result: exact scores, rows recovered from the key
+  const int n = fill_s < k ? fill_s : k;
+  if (fill_s <= k) {  // not sorted yet (fewer than k rows in the slice) — order is irrelevant here
+  }
+  Cand* out = st.cand + static_cast<long long>(q) * st.cap + slice * k;
+  for (int i = tid; i < k; i += blockDim.x) {
+    if (i < n)
+      out[i] = Cand{unorderable(static_cast<uint32_t>(keys[i] >> 32)),
+                    static_cast<int32_t>(0xffffffffu - static_cast<uint32_t>(keys[i] & 0xffffffffu))};
+    else
+      out[i] = Cand{-FLT_MAX, -1};
+  }
+  if (tid == 0 && slice == 0) st.cnt[q] = SCAN_SLICES * k;
+}
+
+// Exact re-scoring of the candidates and the final ordered top-k.
+__global__ void __launch_bounds__(256)
+rescore_topk_kernel(SearchState st, const float* __restrict__ xq, const float* __restrict__ corpus_f32,
+                    const __nv_bfloat16* __restrict__ corpus_bf16, int d, int k, long long id_offset,
+                    float* __restrict__ out_scores, long long* __restrict__ out_ids, int32_t* __restrict__ stats) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  float* sq = reinterpret_cast<float*>(dyn);
+  __shared__ unsigned long long keys[SORT_MAX];
+  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int j = tid; j < d; j += blockDim.x) sq[j] = xq[static_cast<long long>(q) * d + j];
+  int n = st.cnt[q];
+  if (n > st.cap) n = st.cap;
+  const int P = pow2_at_least(n < 1 ? 1 : n);
+  for (int i = n + tid; i < P; i += blockDim.x) keys[i] = 0;
+  __syncthreads();
+  const Cand* cq = st.cand + static_cast<long long>(q) * st.cap;
+  for (int i = warp; i < n; i += blockDim.x / 32) {
+    const int row = cq[i].row;
+    unsigned long long key = 0;
+    if (row >= 0) {
+      const float s = corpus_f32 ? warp_dot_f32(corpus_f32 + static_cast<long long>(row) * d, sq, d, lane)
+                                 : warp_dot_bf16(corpus_bf16 + static_cast<long long>(row) * d, sq, d, lane);
+      // descending key order = score descending, then row ascending
+      key = (static_cast<unsigned long long>(orderable(s)) << 32) | (0xffffffffu - static_cast<uint32_t>(row));
+    }
+    if (lane == 0) keys[i] = key;
+  }
+  __syncthreads();
+  bitonic_sort_desc(keys, P);
+  for (int i = tid; i < k; i += blockDim.x) {
+    float s = -FLT_MAX;
+    long long id = -1;
+    if (i < n && keys[i] != 0) {
+      s = unorderable(static_cast<uint32_t>(keys[i] >> 32));
+      id = static_cast<long long>(0xffffffffu - static_cast<uint32_t>(keys[i] & 0xffffffffu)) + id_offset;
+    }
+    out_scores[static_cast<long long>(q) * k + i] = s;
+    out_ids[static_cast<long long>(q) * k + i] = id;
+  }
+  if (stats && tid == 0) {
+    atomicAdd(&stats[1], n);
+    if (st.overflow[q]) atomicAdd(&stats[0], 1);
+  }
+}
+
+__global__ void init_state_kernel(SearchState st, int Q, int32_t* stats) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) {
+    st.thr[q] = -INFINITY;
+    st.cnt[q] = 0;
+    st.overflow[q] = 0;
+  }
+  if (q < 4 && stats) stats[q] = 0;
+}
+
+// merge of per-shard top-k lists: order (score desc, id asc), id < 0 (padding) last
+__global__ void __launch_bounds__(128)
+topk_merge_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, int G, int Q, int k,
+                  float* __restrict__ out_scores, long long* __restrict__ out_ids) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  const int n = G * k;
+  float* s = reinterpret_cast<float*>(dyn);
+  long long* id = reinterpret_cast<long long*>(dyn + ((n * 4 + 15) & ~15));
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int g = i / k, j = i % k;
+    s[i] = scores[(static_cast<long long>(g) * Q + q) * k + j];
+    id[i] = ids[(static_cast<long long>(g) * Q + q) * k + j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float si = s[i];
+    const long long ii = id[i];
+    const bool pad_i = ii < 0;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float sj = s[j];
+      const long long ij = id[j];
+      const bool pad_j = ij < 0;
+      bool better;
+      if (pad_i != pad_j)
+        better = pad_i;  // real entries before padding
+      else if (sj != si)
+        better = sj > si;
+      else if (ij != ii)
+        better = ij < ii;
+      else
+        better = j < i;
+      rank += better;
+    }
+    if (rank < k) {
+      out_scores[static_cast<long long>(q) * k + rank] = pad_i ? -FLT_MAX : si;
+      out_ids[static_cast<long long>(q) * k + rank] = pad_i ? -1 : ii;
+    }
+  }
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WorkspaceLayout {
+  size_t xq_bf16, qnorm, thr, cnt, overflow, cand, total;
+  int q_pad;
+};
+inline WorkspaceLayout plan_workspace(int Q, int d, int cap) {
+  WorkspaceLayout w;
+  w.q_pad = (Q + TM - 1) / TM * TM;
+  size_t off = 0;
+  w.xq_bf16 = off, off = align_up(off + static_cast<size_t>(w.q_pad) * d * 2, 256);
+  w.qnorm = off, off = align_up(off + static_cast<size_t>(w.q_pad) * 4, 256);
+  w.thr = off, off = align_up(off + static_cast<size_t>(Q) * 4, 256);
+  w.cnt = off, off = align_up(off + static_cast<size_t>(Q) * 4, 256);
+  w.overflow = off, off = align_up(off + static_cast<size_t>(Q) * 4, 256);
+  w.cand = off, off = align_up(off + static_cast<size_t>(Q) * cap * sizeof(Cand), 256);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ip_cast_rows_bf16(const float* x, void* x_bf16, float* max_norm_dev, int64_t n, int d, void* stream) {
+  if (!x || !x_bf16 || n < 0 || d <= 0 || (d % 4)) return SDAG_ERR_INVALID;
+  if (n == 0) return SDAG_OK;
+  const long long blocks = (n * 32 + 255) / 256;
+  cast_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(x_bf16), max_norm_dev, nullptr, n, n, d);
+  return static_cast<int>(cudaGetLastError());
+}
+
+size_t ip_search_workspace_bytes(int Q, int d, int k, int cand_cap) {
+  if (Q <= 0 || d <= 0 || k <= 0 || cand_cap <= 0) return 0;
+  return plan_workspace(Q, d, cand_cap).total;
+}
+
+int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpus_bf16, int64_t N, int d,
+              int64_t id_offset, const float* max_norm_dev, int k, float* out_scores, int64_t* out_ids,
+              int32_t* stats_dev, void* workspace, size_t workspace_bytes, int cand_cap, void* stream) {
+  if (!xq || !corpus_bf16 || !max_norm_dev || !out_scores || !out_ids || !workspace) return SDAG_ERR_INVALID;
+  if (Q <= 0 || N < 0 || d <= 0 || k <= 0) return SDAG_ERR_INVALID;
+  if (d % KB || d > 8192) return SDAG_ERR_UNSUPPORTED;       // whole 128-byte swizzle rows; query fits in smem
+  if (cand_cap > SORT_MAX || cand_cap < 256 || (cand_cap & (cand_cap - 1))) return SDAG_ERR_INVALID;
+  if (k > cand_cap / SCAN_SLICES || N > 0x7fffff00ll) return SDAG_ERR_UNSUPPORTED;
+  const WorkspaceLayout w = plan_workspace(Q, d, cand_cap);
+  if (workspace_bytes < w.total) return SDAG_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  SearchState state;
+  state.thr = reinterpret_cast<float*>(ws + w.thr);
+  state.cnt = reinterpret_cast<int32_t*>(ws + w.cnt);
+  state.overflow = reinterpret_cast<int32_t*>(ws + w.overflow);
+  state.qnorm = reinterpret_cast<float*>(ws + w.qnorm);
+  state.cand = reinterpret_cast<Cand*>(ws + w.cand);
+  state.cap = cand_cap;
+  __nv_bfloat16* xq_bf16 = reinterpret_cast<__nv_bfloat16*>(ws + w.xq_bf16);
+
+  init_state_kernel<<<(Q + 255) / 256, 256, 0, st>>>(state, Q, stats_dev);
+  {
+    const long long blocks = (static_cast<long long>(w.q_pad) * 32 + 255) / 256;
+    cast_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(xq, xq_bf16, nullptr, state.qnorm, Q, w.q_pad, d);
+  }
+  SDAG_CUDA_TRY(cudaGetLastError());
+
+  if (N > 0) {
+    CUtensorMap tmA, tmB;
+    {
+      uint64_t dims[2] = {static_cast<uint64_t>(d), static_cast<uint64_t>(w.q_pad)};
+      uint64_t str[1] = {static_cast<uint64_t>(d) * 2};
+      uint32_t box[2] = {KB, TM};
+      if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xq_bf16, dims, str, box)) return SDAG_ERR_DRIVER;
+    }
+    {
+      uint64_t dims[2] = {static_cast<uint64_t>(d), static_cast<uint64_t>(N)};
+      uint64_t str[1] = {static_cast<uint64_t>(d) * 2};
+      uint32_t box[2] = {KB, TN};
+      if (make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, corpus_bf16, dims, str, box)) return SDAG_ERR_DRIVER;
+    }
+    static bool configured = false;
+    static int n_sm = 148;
+    if (!configured) {
+      SDAG_CUDA_TRY(cudaFuncSetAttribute(ip_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+      int dev = 0;
+      SDAG_CUDA_TRY(cudaGetDevice(&dev));
+      SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+      configured = true;
+    }
+    GemmParams gp;
+    gp.st = state;
+    gp.Q = Q;
+    gp.n_qt = w.q_pad / TM;
+    gp.kblocks = d / KB;
+    // first epoch: positional dump of up to cap/2 rows (multiple of TN), then doubling spans
+    long long begin = 0;
+    long long span = cand_cap / 2 / TN * TN;
+    if (span < TN) span = TN;
+    bool first = true;
+    int epochs = 0;
+    while (begin < N) {
+      long long end = begin + span < N ? begin + span : N;
+      gp.row_begin = begin;
+      gp.row_end = end;
+      gp.n_ct = static_cast<int>((end - begin + TN - 1) / TN);
+      gp.dump = first ? 1 : 0;
+      const long long units = static_cast<long long>(gp.n_ct) * gp.n_qt;
+      const int grid = static_cast<int>(units < n_sm ? units : n_sm);
+      ip_gemm_filter_kernel<<<grid, 192, GEMM_SMEM, st>>>(tmA, tmB, gp);
+      tighten_kernel<<<Q, 256, 0, st>>>(state, k, first ? static_cast<int>(end - begin) : -1, max_norm_dev);
+      SDAG_CUDA_TRY(cudaGetLastError());
+      if (!first) span *= 2;
+      first = false;
+      begin = end;
+      ++epochs;
+    }
+    (void)epochs;
+    exact_scan_kernel<<<dim3(Q, SCAN_SLICES), 256, static_cast<size_t>(d) * 4, st>>>(
+        state, xq, corpus_f32, static_cast<const __nv_bfloat16*>(corpus_bf16), N, d, k);
+  }
+  rescore_topk_kernel<<<Q, 256, static_cast<size_t>(d) * 4, st>>>(state, xq, corpus_f32,
+                                                                 static_cast<const __nv_bfloat16*>(corpus_bf16), d, k,
+                                                                 id_offset, out_scores, reinterpret_cast<long long*>(out_ids),
+                                                                 stats_dev);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int topk_merge(const float* scores, const int64_t* ids, int G, int Q, int k, float* out_scores, int64_t* out_ids,
+               void* stream) {
+  if (!scores || !ids || !out_scores || !out_ids || G <= 0 || Q <= 0 || k <= 0) return SDAG_ERR_INVALID;
+  const size_t n = static_cast<size_t>(G) * k;
+  const size_t smem = ((n * 4 + 15) & ~size_t(15)) + n * 8;
+  if (smem > 48 * 1024) return SDAG_ERR_UNSUPPORTED;
+  topk_merge_kernel<<<Q, 128, smem, static_cast<cudaStream_t>(stream)>>>(scores, reinterpret_cast<const long long*>(ids), G,
+                                                                        Q, k, out_scores, reinterpret_cast<long long*>(out_ids));
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // extern "C"

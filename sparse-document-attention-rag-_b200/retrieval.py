@@ -1,0 +1,318 @@
+"""Dense retrieval (hot path B) — host side.
+
+Mirrors ``src/pipeline/retrieval/dense.py`` / ``retriever.py`` of the reference:
+
+========================================  ==========================================================
+reference                                 here
+========================================  ==========================================================
+``Retriever`` ABC        retriever.py:9   ``Retriever`` (same abstract method)
+``load_faiss_index_and_meta``  dense:15   same name; reads a faiss ``IndexFlatIP`` file into HBM
+``embed_queries``              dense:44   same name / semantics ("query: " prefix iff e5)
+``search_index``               dense:68   same name; returns ``(indices, scores)``
+``materialize_dense_hits``     dense:87   same name; out-of-range index -> ``""`` / ``"NA"``
+``DenseRetriever``             dense:133  same name (``B200DenseRetriever`` is an alias)
+``faiss.IndexFlatIP``          (3rd pty)  ``FlatIPIndex`` — ``.d .ntotal .add(x) .search(x, k)``
+========================================  ==========================================================
+
+``FlatIPIndex`` keeps the corpus resident in HBM (fp32 rows for exact re-scoring + a bf16 shadow for the
+tensor-core pass) and runs ``ip_search`` from ``libsdag_b200.so``; ``ShardedFlatIPIndex`` partitions the
+rows over the ranks of a ``torch.distributed`` group and merges local results after one all-gather.
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+from abc import ABC, abstractmethod
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import config as _config
+from .datamodels import RetrievalBatch
+
+RANKER_MODEL_NAME = _config.RANKER_MODEL_NAME  # patchable, like the reference's import-time copy (dense.py:10)
+NEG_FLT_MAX = -3.4028234663852886e38
+DEFAULT_CAND_CAP = 2048
+MAX_QUERY_BATCH = 4096
+
+
+class Retriever(ABC):
+    """Retriever plug point (reference ``retrieval/retriever.py:9-19``)."""
+
+    @abstractmethod
+    def retrieve_batch(self, queries: Sequence[str], max_k_needed: int, embed_batch_size: int) -> RetrievalBatch:
+        raise NotImplementedError
+
+
+class FlatIPIndex:
+    """Exact inner-product index with the faiss ``IndexFlatIP`` surface the reference touches
+    (``dense.py:36, 83``): ``d``, ``ntotal``, ``add``, ``search``.
+
+    ``corpus_dtype="bf16"`` stores bf16 rows only; search is then exact over ``float32(bf16(corpus))``.
+    """
+
+    def __init__(self, d: int, device="cuda", corpus_dtype: str = "fp32", id_offset: int = 0,
+                 cand_cap: int = DEFAULT_CAND_CAP):
+        if corpus_dtype not in ("fp32", "bf16"):
+            raise ValueError("corpus_dtype must be 'fp32' or 'bf16'")
+        self.d = int(d)
+        self.device = torch.device(device)
+        self.corpus_dtype = corpus_dtype
+        self.id_offset = int(id_offset)
+        self.cand_cap = int(cand_cap)
+        self.ntotal = 0
+        self._f32: Optional[torch.Tensor] = None   # [cap_rows, d] fp32 (None for bf16 corpora)
+        self._bf16: Optional[torch.Tensor] = None  # [cap_rows, d] bf16 shadow
+        self._max_norm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._ws: Optional[torch.Tensor] = None
+        self.last_stats: Optional[torch.Tensor] = None
+
+    # -- construction ---------------------------------------------------------------------------------
+    @classmethod
+    def from_device(cls, corpus: torch.Tensor, **kw) -> "FlatIPIndex":
+        """Adopt a device-resident ``[N, d]`` tensor without copying it (fp32, or bf16 with corpus_dtype='bf16')."""
+        idx = cls(corpus.shape[1], device=corpus.device, **kw)
+        idx._adopt(corpus)
+        return idx
+
+    def _adopt(self, x: torch.Tensor) -> None:
+        lib = _lib.load()
+        x = x.contiguous()
+        n = x.shape[0]
+        if self.corpus_dtype == "fp32":
+            if x.dtype != torch.float32:
+                raise TypeError("fp32 corpus expected")
+            self._f32 = x
+            self._bf16 = torch.empty((n, self.d), dtype=torch.bfloat16, device=self.device)
+            _lib.check(lib.ip_cast_rows_bf16(x.data_ptr(), self._bf16.data_ptr(), self._max_norm.data_ptr(), n, self.d,
+                                             _lib.stream_ptr(self.device)), "ip_cast_rows_bf16")
+        else:
+            self._bf16 = x.to(torch.bfloat16)
+            # row norms of the stored (bf16) rows, conservatively rounded up
+            nr = torch.linalg.vector_norm(self._bf16.float(), dim=1).max() * 1.000001 if n else torch.zeros((), device=self.device)
+            self._max_norm = torch.maximum(self._max_norm, nr.reshape(1).float())
+        self.ntotal = n
+
+    def add(self, x) -> None:
+        """Append rows (numpy float32 ``[n, d]`` like faiss, or a torch tensor on any device)."""
+        t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)) if not torch.is_tensor(x) else x
+        if t.dim() != 2 or t.shape[1] != self.d:
+            raise ValueError(f"expected [n, {self.d}] rows")
+        t = t.to(self.device, dtype=torch.float32 if self.corpus_dtype == "fp32" else torch.bfloat16)
+        if self.ntotal == 0:
+            self._adopt(t)
+            return
+        old = self._f32 if self.corpus_dtype == "fp32" else self._bf16
+        self._max_norm.zero_()
+        self._adopt(torch.cat([old[: self.ntotal], t.to(old.dtype)], dim=0))
+
+    # -- search ---------------------------------------------------------------------------------------
+    def search_device(self, xq: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """xq fp32 ``[Q, d]`` on the index's device -> (scores fp32 ``[Q,k]``, ids int64 ``[Q,k]``) on device.
+        Rows sorted by descending score, ties by ascending id; ``-FLT_MAX`` / ``-1`` padding when ntotal < k."""
+        lib = _lib.load()
+        k = int(k)
+        if xq.dim() != 2 or xq.shape[1] != self.d:
+            raise ValueError(f"expected [Q, {self.d}] queries")
+        if k <= 0:
+            raise ValueError("k must be positive")
+        if k > self.cand_cap // 32:
+            raise _lib.SdagB200Error(f"k={k} exceeds the supported maximum {self.cand_cap // 32}")
+        xq = xq.to(self.device, dtype=torch.float32).contiguous()
+        Q = xq.shape[0]
+        scores = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((Q, k), dtype=torch.int64, device=self.device)
+        if Q == 0:
+            return scores, ids
+        if self._bf16 is None:  # empty index
+            self._bf16 = torch.zeros((1, self.d), dtype=torch.bfloat16, device=self.device)
+        stats = torch.zeros(4, dtype=torch.int32, device=self.device)
+        for q0 in range(0, Q, MAX_QUERY_BATCH):
+            q1 = min(Q, q0 + MAX_QUERY_BATCH)
+            nq = q1 - q0
+            need = int(lib.ip_search_workspace_bytes(nq, self.d, k, self.cand_cap))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            part_stats = torch.zeros(4, dtype=torch.int32, device=self.device)
+            _lib.check(
+                lib.ip_search(
+                    xq[q0:q1].data_ptr(), nq,
+                    _lib.ptr(self._f32) if self.corpus_dtype == "fp32" else 0,
+                    self._bf16.data_ptr(), self.ntotal, self.d, self.id_offset, self._max_norm.data_ptr(), k,
+                    scores[q0:q1].data_ptr(), ids[q0:q1].data_ptr(), part_stats.data_ptr(),
+                    self._ws.data_ptr(), self._ws.numel(), self.cand_cap, _lib.stream_ptr(self.device)),
+                "ip_search",
+            )
+            stats += part_stats
+        self.last_stats = stats
+        return scores, ids
+
+    def search(self, x, k: int):
+        """faiss call shape: numpy float32 ``[Q, d]`` in, ``(D float32 [Q,k], I int64 [Q,k])`` numpy out."""
+        xq = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32))
+        if torch.cuda.is_available():
+            xq = xq.pin_memory()
+        scores, ids = self.search_device(xq.to(self.device, non_blocking=True), k)
+        return scores.cpu().numpy(), ids.cpu().numpy()
+
+
+class ShardedFlatIPIndex:
+    """Corpus rows block-partitioned over the ranks of a process group: every rank searches its
+    shard for all queries, one ``all_gather`` moves the local ``[Q,k]`` results, every rank merges ``G*k -> k``
+    with the same order rule.  Global id = shard row offset + local row."""
+
+    def __init__(self, local: FlatIPIndex, group=None):
+        import torch.distributed as dist
+
+        self.local = local
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.d = local.d
+        if self.world > 1:
+            n = torch.tensor([local.ntotal], dtype=torch.int64, device=local.device)
+            dist.all_reduce(n, group=group)
+            self.ntotal = int(n.item())
+        else:
+            self.ntotal = local.ntotal
+
+    def search_device(self, xq: torch.Tensor, k: int):
+        import torch.distributed as dist
+
+        s, i = self.local.search_device(xq, k)
+        if self.world == 1:
+            return s, i
+        Q = s.shape[0]
+        gs = torch.empty((self.world, Q, k), dtype=s.dtype, device=s.device)
+        gi = torch.empty((self.world, Q, k), dtype=i.dtype, device=i.device)
+        dist.all_gather_into_tensor(gs, s, group=self.group)
+        dist.all_gather_into_tensor(gi, i, group=self.group)
+        return merge_topk_device(gs, gi, k)
+
+    def search(self, x, k: int):
+        xq = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self.local.device)
+        s, i = self.search_device(xq, k)
+        return s.cpu().numpy(), i.cpu().numpy()
+
+
+def merge_topk_device(scores: torch.Tensor, ids: torch.Tensor, k: int):
+    """``[G,Q,k]`` per-shard results -> global ``[Q,k]`` (``topk_merge`` kernel)."""
+    lib = _lib.load()
+    G, Q, kk = scores.shape
+    out_s = torch.empty((Q, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((Q, k), dtype=torch.int64, device=scores.device)
+    if kk != k:
+        raise ValueError("shard results must hold k entries per query")
+    _lib.check(lib.topk_merge(scores.contiguous().data_ptr(), ids.contiguous().data_ptr(), G, Q, k, out_s.data_ptr(),
+                              out_i.data_ptr(), _lib.stream_ptr(scores.device)), "topk_merge")
+    return out_s, out_i
+
+
+# ------------------------------------------------------------------------------------------------------
+# faiss IndexFlatIP file format.  Layout restated from faiss' index_write.cpp (not
+# verifiable here — no faiss in the image): fourcc "IxFI", int32 d, int64 ntotal, 2 x int64 dummy,
+# uint8 is_trained, int32 metric_type (0 = inner product), uint64 n_floats, n_floats x float32.
+# ------------------------------------------------------------------------------------------------------
+def write_flat_ip_file(path: str, x: np.ndarray) -> None:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n, d = x.shape
+    with open(path, "wb") as f:
+        f.write(b"IxFI")
+        f.write(struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, 0))
+        f.write(struct.pack("<Q", n * d))
+        f.write(x.tobytes())
+
+
+def read_flat_ip_file(path: str, device="cuda", **kw) -> FlatIPIndex:
+    with open(path, "rb") as f:
+        fourcc = f.read(4)
+        if fourcc != b"IxFI":
+            raise ValueError(f"{path}: not a faiss IndexFlatIP file (fourcc {fourcc!r}); only flat inner-product "
+                             "indexes are supported")
+        d, n, _, _, _trained, metric = struct.unpack("<iqqqBi", f.read(4 + 8 * 3 + 1 + 4))
+        if metric != 0:
+            raise ValueError("metric_type is not inner product")
+        (count,) = struct.unpack("<Q", f.read(8))
+        if count != n * d:
+            raise ValueError("corrupt index file: vector size does not match header")
+        x = np.frombuffer(f.read(count * 4), dtype=np.float32).reshape(n, d)
+    idx = FlatIPIndex(d, device=device, **kw)
+    idx.add(x)
+    return idx
+
+
+def load_faiss_index_and_meta(index_path: str, meta_path: str, device="cuda") -> Tuple[Any, List[Dict[str, Any]]]:
+    """Same contract as the reference (``dense.py:15-41``): ``FileNotFoundError`` for a missing file, metadata
+    is one JSON object per line."""
+    if not os.path.exists(index_path):
+        raise FileNotFoundError(f"FAISS index not found at {index_path}")
+    if not os.path.exists(meta_path):
+        raise FileNotFoundError(f"Metadata jsonl not found at {meta_path}")
+    index = read_flat_ip_file(index_path, device=device)
+    with open(meta_path, "r", encoding="utf-8") as f:
+        meta = [json.loads(line) for line in f]
+    return index, meta
+
+
+def embed_queries(ranker, queries: List[str], batch_size: int) -> np.ndarray:
+    """Unit-norm query embeddings, ``"query: "`` prefix iff the ranker is an e5 model (``dense.py:44-65``)."""
+    use_prefix = "e5" in RANKER_MODEL_NAME.lower()
+    texts = [("query: " + q) if use_prefix else q for q in queries]
+    chunks = []
+    for i in range(0, len(texts), batch_size):
+        emb = ranker.encode(texts[i : i + batch_size], convert_to_tensor=True, batch_size=batch_size,
+                            normalize_embeddings=True)
+        chunks.append(emb.cpu().numpy())
+    return np.vstack(chunks)
+
+
+def search_index(index: Any, query_embeddings: np.ndarray, top_k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """``(indices, scores)`` — note the swap relative to ``index.search`` (``dense.py:82-84``)."""
+    scores, indices = index.search(query_embeddings.astype(np.float32), top_k)
+    return indices, scores
+
+
+def materialize_dense_hits(indices, scores, meta):
+    """ids -> (texts, ids, scores) lists; an index outside ``[0, len(meta))`` becomes ``""`` / ``"NA"`` with its
+    score kept (``dense.py:87-130``)."""
+    texts_b: List[List[str]] = []
+    ids_b: List[List[str]] = []
+    scores_b: List[List[float]] = []
+    n_meta = len(meta)
+    for row_idx, row_sc in zip(indices, scores):
+        texts, ids, scs = [], [], []
+        for idx, sc in zip(row_idx, row_sc):
+            idx = int(idx)
+            if 0 <= idx < n_meta:
+                m = meta[idx]
+                texts.append(m.get("text", ""))
+                ids.append(str(m.get("id", "NA")))
+            else:
+                texts.append("")
+                ids.append("NA")
+            scs.append(float(sc))
+        texts_b.append(texts)
+        ids_b.append(ids)
+        scores_b.append(scs)
+    return texts_b, ids_b, scores_b
+
+
+class DenseRetriever(Retriever):
+    """Drop-in for the reference's ``DenseRetriever`` (``dense.py:133-178``); ``index`` is any faiss-shaped object,
+    normally a ``FlatIPIndex`` / ``ShardedFlatIPIndex``."""
+
+    def __init__(self, ranker, index: Any, meta: List[Dict[str, Any]]) -> None:
+        self.ranker = ranker
+        self.index = index
+        self.meta = meta
+
+    def retrieve_batch(self, queries: Sequence[str], max_k_needed: int, embed_batch_size: int) -> RetrievalBatch:
+        q_embs = embed_queries(self.ranker, list(queries), batch_size=embed_batch_size)
+        indices, scores = search_index(self.index, q_embs, top_k=max_k_needed)
+        texts, ids, scs = materialize_dense_hits(indices, scores, self.meta)
+        return RetrievalBatch(q_embs=list(q_embs), docs_texts_full=texts, ids_full=ids, scores_full=scs)
+
+
+B200DenseRetriever = DenseRetriever

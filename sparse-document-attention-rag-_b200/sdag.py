@@ -270,3 +270,226 @@ def build_blocked_causal_mask_full(
     _lib.check(lib.sdag_build_mask(rec.data_ptr(), max_docs, lay.nbr_k, mask.data_ptr(), lay.L, _lib.stream_ptr(mask.device)),
                "sdag_build_mask")
     return mask.view(torch.bool)
+
+
+# ------------------------------------------------------------------------------------------------------
+# compute_doc_knn_for_docs — SDAG.py:14-65
+# ------------------------------------------------------------------------------------------------------
+def doc_knn_device(emb: torch.Tensor, k_neighbors: int) -> torch.Tensor:
+    """``emb [n, d]`` fp32 on the GPU -> int32 ``[n, k]`` neighbour rows, most similar first (-1 = none)."""
+    lib = _lib.load()
+    emb = emb.to(torch.float32).contiguous()
+    n, d = emb.shape
+    out = torch.empty((n, k_neighbors), dtype=torch.int32, device=emb.device)
+    _lib.check(lib.doc_knn(emb.data_ptr(), n, d, k_neighbors, out.data_ptr(), _lib.stream_ptr(emb.device)), "doc_knn")
+    return out
+
+
+def compute_doc_knn_for_docs(ranker, docs: List[str], k_neighbors: int, device="cuda") -> List[List[int]]:
+    """Directed kNN lists among the prompt documents (indices into ``docs``).  Same conventions as the
+    reference: empty / whitespace docs take no part and get ``[]``; the ``"passage: "`` prefix is unconditional
+    (SDAG.py:47); fewer than two usable docs or ``k_neighbors <= 0`` -> all lists empty."""
+    n = len(docs)
+    if k_neighbors <= 0 or n == 0:
+        return [[] for _ in range(n)]
+    usable = [i for i, d in enumerate(docs) if d and d.strip()]
+    if len(usable) <= 1:
+        return [[] for _ in range(n)]
+    emb = ranker.encode(["passage: " + docs[i] for i in usable], convert_to_tensor=True, normalize_embeddings=True)
+    emb = torch.as_tensor(emb).to(device=device, dtype=torch.float32)
+    local = doc_knn_device(emb, int(k_neighbors)).cpu().tolist()
+    out: List[List[int]] = [[] for _ in range(n)]
+    for row, i_full in enumerate(usable):
+        out[i_full] = [usable[j] for j in local[row] if j >= 0]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# Hugging Face attention hook
+# ------------------------------------------------------------------------------------------------------
+def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling: Optional[float] = None) -> torch.Tensor:
+    """One decode step, dense over the cache: q ``[B,H,1,D]``, k/v ``[B,Hkv,S,D]`` bf16 -> ``[B,1,H,D]``."""
+    lib = _lib.load()
+    B, H, _, D = q.shape
+    Hkv, S = k.shape[1], k.shape[2]
+    q2 = q.reshape(B, H, D)
+    if q2.stride(-1) != 1:
+        q2 = q2.contiguous()
+    k, v = _unit_inner(k), _unit_inner(v)
+    out = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=q.device)
+    ws_bytes = int(lib.sdag_decode_workspace_bytes(B, H, D, S))
+    ws = _workspace(q.device, ws_bytes)
+    scaling = float(D ** -0.5 if scaling is None else scaling)
+    _lib.check(
+        lib.sdag_decode_fwd(q2.data_ptr(), q2.stride(0), q2.stride(1),
+                            k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
+                            v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
+                            out.data_ptr(), B, H, Hkv, S, D, scaling, ws.data_ptr(), ws.numel(), _lib.stream_ptr(q.device)),
+        "sdag_decode_fwd",
+    )
+    return out
+
+
+def sdag_b200_attention(module, query, key, value, attention_mask=None, dropout: float = 0.0, scaling=None,
+                        sdag_meta: Optional[BlockMap] = None, **kwargs):
+    """``AttentionInterface`` function (same contract as HF ``sdpa_attention_forward``,
+    integrations/sdpa_attention.py:40-104): returns ``(attn_output [B,Lq,H,D], None)``.
+
+    * prefill (``Lq == S``): block-sparse attention under ``sdag_meta`` (a ``BlockMap``), or plain causal when
+      no metadata is given (the CARG path);
+    * decode (``Lq == 1``): dense over the cache, exactly what the reference does after the prefill
+      (SDAG.py:193-197 passes no mask).
+    """
+    if dropout:
+        raise NotImplementedError("sdag_b200 attention is inference-only (dropout must be 0)")
+    B, H, Lq, D = query.shape
+    S = key.shape[2]
+    orig = query.dtype
+    if orig != torch.bfloat16:
+        query, key, value = query.to(torch.bfloat16), key.to(torch.bfloat16), value.to(torch.bfloat16)
+    if Lq == 1:
+        out = sdag_decode_attention(query, key, value, scaling)
+    elif Lq == S:
+        bm = sdag_meta if sdag_meta is not None else causal_blockmap(Lq, query.device)
+        out = sdag_prefill_attention(query, key, value, bm, scaling)
+    else:
+        raise NotImplementedError("chunked prefill against an existing cache is not part of the reference path")
+    return (out if orig == torch.bfloat16 else out.to(orig)), None
+
+
+def register_attention() -> str:
+    """Register the hook with transformers (idempotent) and return its name."""
+    from transformers import AttentionInterface
+
+    AttentionInterface.register(ATTN_NAME, sdag_b200_attention)
+    return ATTN_NAME
+
+
+def prepare_model(model):
+    """Point a HF causal LM at the ``sdag_b200`` attention function."""
+    register_attention()
+    if getattr(model.config, "_attn_implementation", None) != ATTN_NAME:
+        try:
+            model.set_attn_implementation(ATTN_NAME)
+        except Exception:
+            model.config._attn_implementation = ATTN_NAME
+    return model
+
+
+# ------------------------------------------------------------------------------------------------------
+# generate_with_custom_mask — SDAG.py:130-213
+# ------------------------------------------------------------------------------------------------------
+def _pick(logits: torch.Tensor) -> torch.Tensor:
+    if TEMPERATURE > 0:  # SDAG.py:182-185 — global torch RNG, like the reference
+        probs = torch.softmax(logits / TEMPERATURE, dim=-1)
+        return torch.multinomial(probs, num_samples=1)
+    return torch.argmax(logits, dim=-1, keepdim=True)
+
+
+def _generate(model, tokenizer, input_ids: torch.Tensor, blockmap: BlockMap, max_new_tokens: int) -> str:
+    prepare_model(model)
+    eos = tokenizer.eos_token_id
+    greedy = not (TEMPERATURE > 0)
+    with torch.no_grad():
+        out = model(input_ids=input_ids, use_cache=True, sdag_meta=blockmap, logits_to_keep=1)
+        past = out.past_key_values
+        nxt = _pick(out.logits[:, -1, :])
+        new_tokens = [nxt]
+        # One token comes from the prefill, up to max_new_tokens more from the loop; EOS is only tested inside
+        # the loop (Appendix A7).  Greedy decoding keeps tokens on the device and polls for EOS every 16 steps;
+        # the tail after the first in-loop EOS is cut below, so the result equals a per-token check.
+        for step in range(max_new_tokens):
+            out = model(input_ids=nxt, past_key_values=past, use_cache=True)
+            past = out.past_key_values
+            nxt = _pick(out.logits[:, -1, :])
+            new_tokens.append(nxt)
+            if not greedy:
+                if nxt.item() == eos:
+                    break
+            elif eos is not None and (step % 16 == 15) and bool((torch.cat(new_tokens[1:], dim=1) == eos).any()):
+                break
+    ids = torch.cat(new_tokens, dim=1)[0].tolist()
+    if eos is not None:
+        for pos in range(1, len(ids)):
+            if ids[pos] == eos:
+                ids = ids[: pos + 1]
+                break
+    return tokenizer.decode(ids, skip_special_tokens=True).strip()
+
+
+def generate_with_custom_mask(model, tokenizer, input_ids: torch.Tensor, prompt_mask: torch.Tensor,
+                              max_new_tokens: int = 128) -> str:
+    """Prefill under an arbitrary ``[L, L]`` allow-mask (bool, or the additive {0, finfo.min} form), then dense
+    token-by-token decoding; returns the decoded new tokens (special tokens removed, stripped)."""
+    device = input_ids.device
+    if device.type != "cuda":
+        raise _lib.SdagB200Error("sdag_b200 runs on CUDA devices only (no CPU fallback)")
+    bm = build_blockmap_from_mask(prompt_mask.to(device))
+    return _generate(model, tokenizer, input_ids, bm, max_new_tokens)
+
+
+# ------------------------------------------------------------------------------------------------------
+# build_rag_chat_and_spans — SDAG.py:216-304
+# ------------------------------------------------------------------------------------------------------
+def _token_len(tokenizer, text: str) -> int:
+    return len(tokenizer(text, return_tensors="pt").input_ids[0])
+
+
+def build_rag_chat_and_spans(tokenizer, system_prompt: str, user_template: str, query: str, malicious_docs: List[str],
+                             retrieved_docs: list, add_attack_in_rank: int):
+    """Prompt string plus the token offsets the mask needs: ``(chat_str, sys_user_len, doc_token_spans, qa_start,
+    ranked_docs)``.  Offsets are counted by tokenising string prefixes, as the reference does (Appendix A10), so
+    they agree with it for any tokenizer; all prefixes go through the tokenizer in one batched call."""
+    ranked_docs = inject_malicious_docs_into_ranked_list(base_docs=retrieved_docs, malicious_docs=malicious_docs,
+                                                         attack_pos=add_attack_in_rank)
+    bullets = ["- " + d.strip() for d in ranked_docs if d and d.strip()]
+    user_content = user_template.format(query=query, docs_text="\n\n".join(bullets))
+    chat_str = tokenizer.apply_chat_template(
+        [{"role": "system", "content": system_prompt}, {"role": "user", "content": user_content}],
+        tokenize=False, add_generation_prompt=True)
+
+    starts, cursor = [], 0
+    for b in bullets:
+        at = chat_str.find(b, cursor)
+        if at < 0:
+            at = cursor
+        starts.append(at)
+        cursor = at + len(b)
+    q_at = chat_str.find(QUESTION_MARKER)
+    if q_at < 0:
+        q_at = len(chat_str)
+
+    cuts = [starts[0] if starts else q_at]
+    for b, at in zip(bullets, starts):
+        cuts += [at, at + len(b)]
+    cuts.append(q_at)
+    try:
+        lens = [len(ids) for ids in tokenizer([chat_str[:c] for c in cuts]).input_ids]
+    except Exception:  # tokenizers without batched __call__
+        lens = [_token_len(tokenizer, chat_str[:c]) for c in cuts]
+    sys_user_len = lens[0]
+    spans = [(lens[1 + 2 * i], lens[2 + 2 * i]) for i in range(len(bullets))]
+    qa_start = lens[-1]
+    return chat_str, sys_user_len, spans, qa_start, ranked_docs
+
+
+# ------------------------------------------------------------------------------------------------------
+# run_rag_with_doc_isolation — SDAG.py:307-375
+# ------------------------------------------------------------------------------------------------------
+def run_rag_with_doc_isolation(model, tokenizer, query: str, malicious_docs: List[str], retrieved_docs: list,
+                               max_new_tokens: int, device: str, add_attack_in_rank: int, ranker,
+                               doc_neighbors_k: int) -> str:
+    """SDAG answer for one query.  Same steps as the reference, except that the ``[L, L]`` mask is never built:
+    the token offsets go to the device and come back as a block map consumed by the attention kernel."""
+    if torch.device(device).type != "cuda":
+        raise _lib.SdagB200Error("sdag_b200 runs on CUDA devices only (no CPU fallback)")
+    chat_str, sys_user_len, spans, qa_start, ranked_docs = build_rag_chat_and_spans(
+        tokenizer=tokenizer, system_prompt=SYSTEM_PROMPT_RAG, user_template=USER_RAG_PROMPT, query=query,
+        malicious_docs=malicious_docs, retrieved_docs=retrieved_docs, add_attack_in_rank=add_attack_in_rank)
+    neighbors = None
+    if doc_neighbors_k and doc_neighbors_k > 0:
+        neighbors = compute_doc_knn_for_docs(ranker=ranker, docs=ranked_docs, k_neighbors=doc_neighbors_k, device=device)
+    input_ids = tokenizer(chat_str, return_tensors="pt").to(device)["input_ids"]
+    layout = SdagLayout(L=input_ids.size(1), S=sys_user_len, spans=spans, qa_start=qa_start, neighbors=neighbors)
+    bm = build_blockmap_checked(layout, device)
+    return _generate(model, tokenizer, input_ids, bm, max_new_tokens)

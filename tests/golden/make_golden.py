@@ -163,11 +163,20 @@ def gen_generation():
             max_new_tokens=6, device="cpu", add_attack_in_rank=rank, ranker=ranker, doc_neighbors_k=nbr_k)
         tok.decode = orig_decode
         nbrs = ref_sdag.compute_doc_knn_for_docs(ranker, ranked, nbr_k) if nbr_k > 0 else None
-        L = len(tok(chat, return_tensors="pt").input_ids[0])
+        ids = tok(chat, return_tensors="pt").input_ids
+        L = ids.shape[1]
+        # prefill logits of the last position, exactly as SDAG.py:161-181 obtains them
+        mask = ref_sdag.build_blocked_causal_mask_full(L, 500, S, spans, qa, "cpu", nbrs)
+        attn = torch.zeros_like(mask, dtype=torch.float32).masked_fill(~mask, torch.finfo(torch.float32).min)
+        with torch.no_grad():
+            logits = model(input_ids=ids, attention_mask=attn[None, None], use_cache=True).logits[0, -1]
+        top = torch.topk(logits, 8)
         records.append(dict(case=case, retrieved=retrieved, malicious=mal, rank=rank, doc_neighbors_k=nbr_k,
                             chat_sha256=hashlib.sha256(chat.encode()).hexdigest(), L=L, S=S,
                             spans=[list(s) for s in spans], qa_start=qa, ranked_docs=ranked, neighbors=nbrs,
-                            new_token_ids=seen["ids"], answer=ans))
+                            new_token_ids=seen["ids"], answer=ans,
+                            prefill_top_ids=top.indices.tolist(), prefill_top_logits=top.values.tolist(),
+                            prefill_logits_absmax=float(logits.abs().max())))
     with open(os.path.join(HERE, "generation.json"), "w") as f:
         json.dump(records, f, indent=1)
     print("generation:", [(r["case"], r["L"], r["new_token_ids"]) for r in records])

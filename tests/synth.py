@@ -69,7 +69,7 @@ class HashRanker:
 
 
 def tiny_llama(vocab_size: int, seed: int = 42, dtype=torch.float32, hidden=64, layers=2, heads=4, kv_heads=2,
-               head_dim=None, inter=128):
+               head_dim=64, inter=128, init_scale=10.0):
     from transformers import LlamaConfig, LlamaForCausalLM
 
     cfg = LlamaConfig(
@@ -85,11 +85,11 @@ def tiny_llama(vocab_size: int, seed: int = 42, dtype=torch.float32, hidden=64, 
     )
     torch.manual_seed(seed)
     model = LlamaForCausalLM(cfg)
-    # default init std 0.02 gives near-uniform logits; widen so greedy choices are not knife-edge
+    # default init std 0.02 gives a context-independent fixed point; widen so the output depends on the mask
     with torch.no_grad():
         for p in model.parameters():
             if p.dim() >= 2:
-                p.mul_(4.0)
+                p.mul_(init_scale)
     return model.to(dtype).eval()
 
 

@@ -1,0 +1,140 @@
+"""CPU tests: host-side logic of the package against the reference goldens, ABI symbol coverage, loud failure
+without a GPU.  No kernel is launched here."""
+import ctypes
+import json
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+
+def test_library_exports_every_declared_symbol():
+    import sdag_b200._lib as L
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "sdag_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|size_t|const char\*)\s+(\w+)\s*\(", header, flags=re.M))
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    if not os.path.exists(L.LIB_PATH):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.sdag_b200_version() >= 100
+    assert lib.sdag_b200_error_string(1001) == b"invalid argument"
+    # pure size queries work without a GPU
+    assert lib.sdag_layout_ints(10, 2) == 8 + 20 + 20
+    assert lib.sdag_blockmap_bytes(2642, 10, 0) % 16 == 0 and lib.sdag_blockmap_bytes(2642, 10, 0) > 0
+    assert lib.sdag_prefill_workspace_bytes(1, 8, 128) == 4 * 8 * 32 * 128
+    assert lib.ip_search_workspace_bytes(4096, 1024, 10, 2048) > 4096 * 2048 * 8
+
+
+def test_ranked_list_injection_matches_reference_golden(golden_dir):
+    from sdag_b200.ranked_list import inject_malicious_docs_into_ranked_list
+
+    with open(os.path.join(golden_dir, "ranked_list.json")) as f:
+        recs = json.load(f)
+    for r in recs:
+        random.seed(r["seed"])
+        assert inject_malicious_docs_into_ranked_list(r["base"], r["malicious"], r["pos"]) == r["out"], r
+
+
+def test_prompt_text_is_the_reference_text(golden_dir):
+    """chat_sha256 in the golden file was computed by the reference over its own prompt constants."""
+    import hashlib
+
+    import synth
+    from sdag_b200.prompts import SYSTEM_PROMPT_RAG, USER_RAG_PROMPT
+    from sdag_b200.sdag import build_rag_chat_and_spans
+
+    tok = synth.make_tokenizer()
+    with open(os.path.join(golden_dir, "generation.json")) as f:
+        recs = json.load(f)
+    for r in recs:
+        chat, S, spans, qa, ranked = build_rag_chat_and_spans(tok, SYSTEM_PROMPT_RAG, USER_RAG_PROMPT, synth.SAMPLE_QUERY,
+                                                              r["malicious"], r["retrieved"], r["rank"])
+        assert hashlib.sha256(chat.encode()).hexdigest() == r["chat_sha256"]
+        assert [list(s) for s in spans] == r["spans"] and S == r["S"] and qa == r["qa_start"]
+        assert ranked == r["ranked_docs"]
+
+
+def test_materialize_and_search_index_contract(golden_dir):
+    """search_index swaps (scores, ids) -> (ids, scores); materialisation of out-of-range ids (dense.py:118-125)."""
+    from oracle.flat_ip import FlatIPOracle
+    from sdag_b200.retrieval import DenseRetriever, materialize_dense_hits, search_index
+
+    import synth
+
+    with open(os.path.join(golden_dir, "retrieval.json")) as f:
+        blob = json.load(f)
+    emb = np.stack([synth.text_embedding("passage: " + t) for t in blob["corpus"]])
+    for rec in blob["records"]:
+        n = rec["n_rows"]
+        idx = FlatIPOracle(emb.shape[1])  # faiss-shaped stand-in: the host logic is index-agnostic
+        idx.add(emb[:n])
+        rb = DenseRetriever(synth.HashRanker(), idx, blob["meta"][:n]).retrieve_batch(rec["queries"], rec["k"], 2)
+        assert rb.ids_full == rec["ids_full"] and rb.docs_texts_full == rec["docs_texts_full"]
+        np.testing.assert_allclose(np.array(rb.scores_full), np.array(rec["scores_full"]), rtol=1e-6)
+    ids, sc = search_index(idx, emb[:2], 3)
+    assert ids.dtype == np.int64 and sc.dtype == np.float32
+    t, i, s = materialize_dense_hits([[0, -1, 99]], [[1.0, 2.0, 3.0]], [{"id": 7, "text": "x"}])
+    assert t == [["x", "", ""]] and i == [["7", "NA", "NA"]] and s == [[1.0, 2.0, 3.0]]
+
+
+def test_selector_random_paths_use_global_rng_like_reference(golden_dir):
+    from sdag_b200.selection import select_malicious_docs_for_batch
+
+    import synth
+
+    with open(os.path.join(golden_dir, "selector.json")) as f:
+        blob = json.load(f)
+    for rec in blob["records"]:
+        if rec["strategy"] != "random":
+            continue  # non-"random" strategies need the GPU when retrieved docs are non-empty
+        random.seed(rec["seed"])
+        got = select_malicious_docs_for_batch(synth.HashRanker(), blob["retrieved"], blob["candidates"], "random", rec["max_docs"])
+        assert got == rec["chosen"]
+
+
+def test_faiss_flat_file_round_trip(tmp_path):
+    import struct
+
+    from sdag_b200.retrieval import load_faiss_index_and_meta, write_flat_ip_file
+
+    x = np.random.default_rng(0).standard_normal((5, 8)).astype(np.float32)
+    p = tmp_path / "faiss.index"
+    write_flat_ip_file(str(p), x)
+    raw = p.read_bytes()
+    assert raw[:4] == b"IxFI" and struct.unpack("<i", raw[4:8])[0] == 8 and len(raw) == 4 + 4 + 24 + 1 + 4 + 8 + 5 * 8 * 4
+    with pytest.raises(FileNotFoundError):
+        load_faiss_index_and_meta(str(p), str(tmp_path / "missing.jsonl"))
+    with pytest.raises(FileNotFoundError):
+        load_faiss_index_and_meta(str(tmp_path / "missing.index"), str(p))
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sdag_b200.sdag as sdag
+    from sdag_b200._lib import SdagB200Error
+
+    with pytest.raises(SdagB200Error):
+        sdag.run_rag_with_doc_isolation(model=None, tokenizer=None, query="q", malicious_docs=[], retrieved_docs=[],
+                                        max_new_tokens=1, device="cpu", add_attack_in_rank=0, ranker=None, doc_neighbors_k=0)
+    with pytest.raises(SdagB200Error):
+        sdag.generate_with_custom_mask(None, None, torch.zeros(1, 3, dtype=torch.long), torch.ones(3, 3, dtype=torch.bool))
+
+
+def test_package_never_imports_the_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "sparse-document-attention-rag-_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn

@@ -1,0 +1,252 @@
+"""GPU parity: exact inner-product top-k, merge, selector and doc-kNN through the C ABI vs the oracle."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.flat_ip import FlatIPOracle, merge_topk_oracle
+from oracle.selector import centroid_sims_oracle, doc_knn_oracle, select_order_oracle
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit_rows(n, d, seed, device="cuda"):
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn(n, d, generator=g, device=device, dtype=torch.float32)
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def _check_against_oracle(x, q, k, ids, scores, rtol=1e-5):
+    """ids bit-exact except where the oracle's own fp32 scores are tied / within the fp32 summation envelope."""
+    oracle = FlatIPOracle(x.shape[1])
+    oracle.add(x)
+    D, I = oracle.search(q, k)
+    np.testing.assert_allclose(scores, D, rtol=rtol, atol=1e-6)
+    mism = ids != I
+    if mism.any():
+        # documented exception class: near-ties (|ds| <= 2e-6 relative) may swap
+        exact = (q.astype(np.float64) @ x.astype(np.float64).T)
+        for r, c in zip(*np.nonzero(mism)):
+            a, b = ids[r, c], I[r, c]
+            assert a >= 0 and b >= 0
+            assert abs(exact[r, a] - exact[r, b]) <= 2e-6 * max(1.0, abs(exact[r, b])), (r, c, a, b)
+    return int(mism.sum())
+
+
+@pytest.mark.parametrize("N,d,Q,k", [(5000, 128, 37, 10), (1300, 64, 130, 11), (70000, 256, 64, 51)])
+def test_flat_ip_search_matches_oracle(N, d, Q, k):
+    from sdag_b200.retrieval import FlatIPIndex
+
+    x = _unit_rows(N, d, 42)
+    q = _unit_rows(Q, d, 7)
+    idx = FlatIPIndex(d)
+    idx.add(x.cpu().numpy())
+    assert idx.ntotal == N and idx.d == d
+    D, I = idx.search(q.cpu().numpy(), k)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (Q, k)
+    assert (np.diff(D, axis=1) <= 0).all()
+    _check_against_oracle(x.cpu().numpy(), q.cpu().numpy(), k, I, D)
+    assert int(idx.last_stats[0]) == 0  # no overflow fallback on well-spread data
+
+
+def test_flat_ip_search_unnormalised_rows_and_incremental_add():
+    from sdag_b200.retrieval import FlatIPIndex
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(9000, 128, generator=g, device="cuda") * torch.rand(9000, 1, generator=g, device="cuda") * 3
+    q = torch.randn(20, 128, generator=g, device="cuda")
+    idx = FlatIPIndex(128)
+    idx.add(x[:4000].cpu().numpy())
+    idx.add(x[4000:])
+    D, I = idx.search(q.cpu().numpy(), 10)
+    _check_against_oracle(x.cpu().numpy(), q.cpu().numpy(), 10, I, D)
+
+
+def test_flat_ip_search_ties_lower_id_first():
+    """1 % duplicated rows at known indices: exactly equal scores keep the lower id first (faiss heap rule)."""
+    from sdag_b200.retrieval import FlatIPIndex
+
+    x = _unit_rows(20000, 128, 42)
+    rng = np.random.default_rng(0)
+    src = rng.choice(20000, 200, replace=False)
+    dst = rng.choice(20000, 200, replace=False)
+    x[torch.from_numpy(dst).cuda()] = x[torch.from_numpy(src).cuda()]
+    q = x[torch.from_numpy(src[:50]).cuda()].clone()  # each query's best hits are a duplicated pair
+    idx = FlatIPIndex.from_device(x)
+    s, i = idx.search_device(q, 10)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    exact_dupes = 0
+    for r in range(s.shape[0]):
+        for c in range(9):
+            if s[r, c] == s[r, c + 1]:
+                assert i[r, c] < i[r, c + 1]
+                exact_dupes += 1
+    assert exact_dupes >= 40
+    _check_against_oracle(x.cpu().numpy(), q.cpu().numpy(), 10, i, s)
+
+
+def test_flat_ip_search_fewer_rows_than_k_pads():
+    from sdag_b200.retrieval import FlatIPIndex, NEG_FLT_MAX
+
+    x = _unit_rows(3, 64, 1)
+    q = _unit_rows(2, 64, 2)
+    idx = FlatIPIndex(64)
+    idx.add(x.cpu().numpy())
+    D, I = idx.search(q.cpu().numpy(), 5)
+    assert (I[:, 3:] == -1).all() and (D[:, 3:] == np.float32(NEG_FLT_MAX)).all()
+    oracle = FlatIPOracle(64)
+    oracle.add(x.cpu().numpy())
+    Do, Io = oracle.search(q.cpu().numpy(), 5)
+    assert np.array_equal(I, Io)
+    np.testing.assert_allclose(D[:, :3], Do[:, :3], rtol=1e-5)
+    empty = FlatIPIndex(64)
+    De, Ie = empty.search(q.cpu().numpy(), 4)
+    assert (Ie == -1).all()
+
+
+def test_flat_ip_search_bf16_corpus_is_exact_over_rounded_rows():
+    from sdag_b200.retrieval import FlatIPIndex
+
+    x = _unit_rows(30000, 128, 5).to(torch.bfloat16)
+    q = _unit_rows(33, 128, 6)
+    idx = FlatIPIndex.from_device(x, corpus_dtype="bf16")
+    s, i = idx.search_device(q, 10)
+    _check_against_oracle(x.float().cpu().numpy(), q.cpu().numpy(), 10, i.cpu().numpy(), s.cpu().numpy())
+
+
+def test_flat_ip_search_clustered_corpus_overflow_fallback_still_exact():
+    """Thousands of near-identical rows defeat the threshold filter: the counted exact-scan fallback must kick in
+    and the answer must still be the exact one."""
+    from sdag_b200.retrieval import FlatIPIndex
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    base = _unit_rows(1, 64, 11)
+    x = base + 1e-4 * torch.randn(6000, 64, generator=g, device="cuda")
+    x = torch.cat([x, _unit_rows(4000, 64, 12)])
+    q = torch.cat([base, _unit_rows(3, 64, 13)])
+    idx = FlatIPIndex.from_device(x.contiguous(), cand_cap=512)
+    s, i = idx.search_device(q, 10)
+    assert int(idx.last_stats[0]) >= 1
+    _check_against_oracle(x.cpu().numpy(), q.cpu().numpy(), 10, i.cpu().numpy(), s.cpu().numpy())
+
+
+def test_flat_ip_round_trip_property_at_scale():
+    """Size-independent property at a size the oracle cannot finish quickly: every corpus row queried against the
+    index must return itself first with score |x|^2 (unit rows -> 1), and results must be sorted."""
+    from sdag_b200.retrieval import FlatIPIndex
+
+    N, d = 1_000_000, 256
+    x = _unit_rows(N, d, 42)
+    idx = FlatIPIndex.from_device(x)
+    rows = torch.arange(0, N, N // 1024, device="cuda")[:1024]
+    s, i = idx.search_device(x[rows], 10)
+    assert torch.equal(i[:, 0], rows)
+    torch.testing.assert_close(s[:, 0], torch.ones_like(s[:, 0]), atol=1e-5, rtol=1e-5)
+    assert (s[:, 1:] <= s[:, :-1]).all()
+    # spot-check 16 queries fully against a brute-force fp32 matmul
+    ref = x[rows[:16]] @ x.T
+    rs, ri = ref.topk(10, dim=1)
+    torch.testing.assert_close(s[:16], rs, atol=2e-6, rtol=1e-5)
+    assert (ri == i[:16]).float().mean() > 0.98
+
+
+def test_topk_merge_matches_oracle_and_sharded_equals_unsharded():
+    from sdag_b200.retrieval import FlatIPIndex, merge_topk_device
+
+    N, d, Q, k, G = 40000, 128, 50, 10, 4
+    x = _unit_rows(N, d, 42)
+    x[30000] = x[5]  # a cross-shard exact tie
+    q = torch.cat([_unit_rows(Q - 1, d, 7), x[5:6]])
+    full_s, full_i = FlatIPIndex.from_device(x).search_device(q, k)
+    per = N // G
+    ss, ii = [], []
+    for g in range(G):
+        shard = FlatIPIndex.from_device(x[g * per : (g + 1) * per].contiguous(), id_offset=g * per)
+        s, i = shard.search_device(q, k)
+        ss.append(s)
+        ii.append(i)
+    gs, gi = torch.stack(ss), torch.stack(ii)
+    ms, mi = merge_topk_device(gs, gi, k)
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+    os_, oi = merge_topk_oracle(gs.cpu().numpy(), gi.cpu().numpy(), k)
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(ms.cpu().numpy(), os_)
+    # padding (-1) sorts last
+    gi2 = gi.clone()
+    gs2 = gs.clone()
+    gi2[0, :, 5:] = -1
+    gs2[0, :, 5:] = -3.4028234663852886e38
+    ms2, mi2 = merge_topk_device(gs2, gi2, k)
+    os2, oi2 = merge_topk_oracle(gs2.cpu().numpy(), gi2.cpu().numpy(), k)
+    assert np.array_equal(mi2.cpu().numpy(), oi2)
+
+
+def test_dense_retriever_reproduces_reference_call_site_golden(golden_dir):
+    """DenseRetriever.retrieve_batch over FlatIPIndex == the reference's dense.py run on the oracle index."""
+    from sdag_b200.retrieval import DenseRetriever, FlatIPIndex
+
+    with open(os.path.join(golden_dir, "retrieval.json")) as f:
+        blob = json.load(f)
+    emb = np.stack([synth.text_embedding("passage: " + t) for t in blob["corpus"]])
+    for rec in blob["records"]:
+        n = rec["n_rows"]
+        idx = FlatIPIndex(emb.shape[1])
+        idx.add(emb[:n])
+        retr = DenseRetriever(synth.HashRanker(), idx, blob["meta"][:n])
+        rb = retr.retrieve_batch(rec["queries"], max_k_needed=rec["k"], embed_batch_size=2)
+        assert rb.ids_full == rec["ids_full"]
+        assert rb.docs_texts_full == rec["docs_texts_full"]
+        np.testing.assert_allclose(np.array(rb.scores_full), np.array(rec["scores_full"]), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(np.stack(rb.q_embs), np.array(rec["q_embs"]), rtol=0, atol=0)
+
+
+def test_selector_kernel_matches_oracle_and_golden(golden_dir):
+    from sdag_b200.selection import centroid_order_device, select_malicious_docs_for_batch
+
+    rng = np.random.default_rng(0)
+    nq, R, C, d = 9, 11, 5, 1024
+    r = rng.standard_normal((nq, R, d)).astype(np.float32)
+    c = rng.standard_normal((nq, C, d)).astype(np.float32)
+    r /= np.linalg.norm(r, axis=2, keepdims=True)
+    c /= np.linalg.norm(c, axis=2, keepdims=True)
+    r_cnt = np.array([11, 1, 5, 11, 7, 2, 11, 3, 9], dtype=np.int32)
+    c_cnt = np.array([5, 5, 3, 1, 5, 2, 4, 5, 5], dtype=np.int32)
+    c[0, 3] = c[0, 1]  # exact tie -> lower index first
+    for furthest in (False, True):
+        sims, order = centroid_order_device(torch.from_numpy(r).cuda(), torch.from_numpy(r_cnt).cuda(),
+                                            torch.from_numpy(c).cuda(), torch.from_numpy(c_cnt).cuda(), furthest)
+        sims, order = sims.cpu().numpy(), order.cpu().numpy()
+        for i in range(nq):
+            ref = centroid_sims_oracle(r[i, : r_cnt[i]], c[i, : c_cnt[i]])
+            np.testing.assert_allclose(sims[i, : c_cnt[i]], ref, rtol=1e-5, atol=1e-6)
+            key = ref if furthest else -ref
+            expect = np.argsort(key, kind="stable")
+            assert list(order[i, : c_cnt[i]]) == list(expect), (i, furthest)
+            assert (order[i, c_cnt[i]:] == -1).all()
+
+    with open(os.path.join(golden_dir, "selector.json")) as f:
+        blob = json.load(f)
+    for rec in blob["records"]:
+        random.seed(rec.get("seed", 1234))
+        got = select_malicious_docs_for_batch(synth.HashRanker(), blob["retrieved"], blob["candidates"], rec["strategy"],
+                                              rec["max_docs"])
+        assert got == rec["chosen"], rec
+
+
+def test_doc_knn_kernel_matches_oracle_and_reference_golden(golden_dir):
+    import sdag_b200.sdag as sdag
+
+    rng = np.random.default_rng(42)
+    emb = rng.standard_normal((50, 64)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    for k in (1, 2, 7):
+        got = sdag.doc_knn_device(torch.from_numpy(emb).cuda(), k).cpu().numpy()
+        assert [list(r) for r in got] == doc_knn_oracle(emb, k)
+    with open(os.path.join(golden_dir, "knn.json")) as f:
+        recs = json.load(f)
+    for r in recs:
+        assert sdag.compute_doc_knn_for_docs(synth.HashRanker(), r["docs"], r["k"]) == r["neighbors"]
