@@ -85,3 +85,12 @@ def stream_ptr(device=None) -> int:
     import torch
 
     return torch.cuda.current_stream(device).cuda_stream
+
+
+# kernels launched through this binding since import (bench.py reports it as "gpu_launches")
+launch_count = 0
+
+
+def count_launches(n: int) -> None:
+    global launch_count
+    launch_count += n

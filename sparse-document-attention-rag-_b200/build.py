@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
     "-Xcompiler", "-fPIC",
-]
+] + os.environ.get("SDAG_EXTRA_NVCC_FLAGS", "").split()
 SOURCES = ["sdag_blockmap.cu", "sdag_prefill.cu", "sdag_decode.cu", "ip_search.cu", "selector.cu", "abi.cu"]
 
 

@@ -29,7 +29,7 @@ struct PrefillParams {
   long long so_b, so_l, so_h;
   const int32_t* blockmaps;
   long long bm_stride_ints;
-  const float* vsum;  // [B][Hkv][VSUM_CHUNKS][D] partial column sums of V
+  const float* vsum;  // [B][Hkv][VSUM_CHUNKS][D] partial column sums of V, then [B][Hkv][D] mean of V
   int B, H, Hkv, Lq, Skv;
   float scale_log2;
 };
@@ -41,6 +41,12 @@ struct Smem {
   static constexpr int kV = BN * D * 2;
   static constexpr int kTotal = kQ + kK + kV + 1024;  // + alignment slack
 };
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -56,6 +62,23 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "memory");
 }
 
+#ifdef SDAG_DEBUG_TIMING
+__device__ unsigned long long* g_timing = nullptr;  // [grid][8] globaltimer stamps (bring-up only)
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define STAMP(slot)                                                                       \
+  do {                                                                                    \
+    if (g_timing && threadIdx.x == 64) g_timing[blockIdx.x * 8ull + (slot)] = gtime();    \
+  } while (0)
+#else
+#define STAMP(slot) \
+  do {              \
+  } while (0)
+#endif
+
 template <int D>
 __global__ void __launch_bounds__(192, 2)
 sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -67,11 +90,26 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int b = rem / p.H;
   const int h = rem - b * p.H;
   const int32_t* map = p.blockmaps + static_cast<long long>(b) * p.bm_stride_ints;
+  STAMP(0);
   if (t >= map[0] || map[2] != 0) return;  // uniform: before any barrier / allocation
   const int4 qt = reinterpret_cast<const int4*>(map + SDAG_BLOCKMAP_HEADER)[t];
   const int q0 = qt.x, nrows = qt.y, n_kv = qt.w;
   const int4* kvt = reinterpret_cast<const int4*>(map + SDAG_BLOCKMAP_HEADER) + map[5] + qt.z;
   const int hkv = h / (p.H / p.Hkv);
+
+  if (n_kv == 0) {
+    // Gap rows only (no allowed key): every row is the mean of V over all keys.  No tensor work, no TMEM.
+    const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(b) * p.Hkv + hkv) * D;
+    for (int i = threadIdx.x; i < nrows * (D / 8); i += blockDim.x) {
+      const int rr = i / (D / 8), ch = i % (D / 8);
+      const float4 a = *reinterpret_cast<const float4*>(vm + ch * 8);
+      const float4 c4 = *reinterpret_cast<const float4*>(vm + ch * 8 + 4);
+      __nv_bfloat16* orow = p.out + b * p.so_b + static_cast<long long>(q0 + rr) * p.so_l + h * p.so_h;
+      *reinterpret_cast<uint4*>(orow + ch * 8) =
+          make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(c4.x, c4.y), pack_bf16x2(c4.z, c4.w));
+    }
+    return;
+  }
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -105,6 +143,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  STAMP(1);
   const uint32_t tmem_S = tmem;        // fp32 scores; P (bf16x2) is written over its first 64 columns
   const uint32_t tmem_O = tmem + 128;  // fp32 output accumulator, D columns
 
@@ -167,16 +206,22 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     float m = -INFINITY, l = 0.f;
-    uint32_t r[32];
+    uint32_t r[32], r2[32];
 
     for (int j = 0; j < n_kv; ++j) {
       const int4 kt = kvt[j];
       const int ncols = kt.y;
       const bool bitmask = (kt.w & KV_FLAG_BITMASK) != 0;
       int lim = min(ncols - 1, row + kt.z);  // allowed columns of this row: c <= lim
+      // warp-uniform bounds of lim over the 32 rows of this warp: chunks at or below wlim_lo need no masking at
+      // all, chunks above wlim_hi hold no allowed column for any lane
+      int wlim_lo = min(ncols - 1, quarter * 32 + kt.z);
+      int wlim_hi = min(ncols - 1, quarter * 32 + 31 + kt.z);
       uint32_t bits[4] = {0, 0, 0, 0};
       if (bitmask) {
         lim = ncols - 1;
+        wlim_lo = -1;  // every chunk takes the masked path
+        wlim_hi = ncols - 1;
         if (q0 + row < p.Lq) {
           const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
                                                           static_cast<long long>(q0 + row) * map[7] + (kt.x >> 5));
@@ -186,60 +231,102 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int nchunks = (ncols + 31) >> 5;
       mbar_wait(&s_full, j & 1);
       tc_fence_after();
+      if (j == 0) STAMP(2);
 
-      // pass 1: row maximum over the allowed columns
-      float mx = -INFINITY;
-      for (int c = 0; c < nchunks; ++c) {
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        const uint32_t bw = bitmask ? bits[c] : 0xffffffffu;
-        const int rel = lim - c * 32;  // columns i <= rel are allowed
+      // Single pass over the scores (TMEM reads are the scarce resource): per 32-column chunk take the chunk
+      // maximum, keep the running reference maximum m unless it is exceeded by more than RESCALE_TAU, and write
+      // P = exp2(S*scale - m) straight back over the S columns already consumed.  When m does move, everything
+      // accumulated against the old reference — l, O, and the P chunks of this tile already written — is
+      // rescaled (rare after the first chunk of the first tile).
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      tmem_ld_32x32b_x32(tmem_S + lane_addr, r);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool ok = (i <= rel) && ((bw >> i) & 1u);
-          mx = fmaxf(mx, ok ? __uint_as_float(r[i]) : -INFINITY);
-        }
-      }
-      mx *= p.scale_log2;
-      const float m_new = fmaxf(m, mx);
-      const bool need = m_new > m + RESCALE_TAU;  // also the first finite maximum (m == -inf)
-      if (__any_sync(0xffffffffu, need)) {
-        const float alpha = need ? exp2f(m - m_new) : 1.f;
-        l *= alpha;
-        if (need) m = m_new;
-        if (j > 0) {  // O holds P_0 V_0 .. P_{j-1} V_{j-1}, all retired (s_full commit)
-          for (int c = 0; c < D / 32; ++c) {
-            tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, r);
-            tmem_ld_wait();
+      for (int c = 0; c < 4; ++c) {
+        uint32_t* cur = (c & 1) ? r2 : r;
+        uint32_t* nxt = (c & 1) ? r : r2;
+        if (c < nchunks) {
+          const bool full_chunk = wlim_lo >= c * 32 + 31;
+          const bool empty_chunk = wlim_hi < c * 32;
+          const uint32_t bw = bitmask ? bits[c] : 0xffffffffu;
+          const int rel = lim - c * 32;  // columns i <= rel are allowed (masked chunks)
+          uint32_t pk[16];
+          if (!empty_chunk) {
+            float mx = -INFINITY;
+            if (full_chunk) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_32x32b_x32(tmem_O + lane_addr + c * 32, r);
+              for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const bool ok = (i <= rel) && ((bw >> i) & 1u);
+                mx = fmaxf(mx, ok ? __uint_as_float(cur[i]) : -INFINITY);
+              }
+            }
+            mx *= p.scale_log2;
+            const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf)
+            if (__any_sync(0xffffffffu, need)) {
+              const float alpha = need ? exp2f(m - mx) : 1.f;
+              if (need) m = mx;
+              l *= alpha;
+              l0 *= alpha, l1 *= alpha, l2 *= alpha, l3 *= alpha;
+              if (j > 0) {  // O holds P_0 V_0 .. P_{j-1} V_{j-1}, all retired (s_full commit)
+                for (int oc = 0; oc < D / 32; ++oc) {
+                  tmem_ld_32x32b_x32(tmem_O + lane_addr + oc * 32, nxt);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) nxt[i] = __float_as_uint(__uint_as_float(nxt[i]) * alpha);
+                  tmem_st_32x32b_x32(tmem_O + lane_addr + oc * 32, nxt);
+                }
+              }
+              for (int pc = 0; pc < c; ++pc) {  // P chunks of this tile written against the old reference
+                tmem_ld_32x32b_x16(tmem_S + lane_addr + pc * 16, nxt);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&nxt[i]));
+                  nxt[i] = pack_bf16x2(f.x * alpha, f.y * alpha);
+                }
+                tmem_st_32x32b_x16(tmem_S + lane_addr + pc * 16, nxt);
+              }
+            }
           }
-        }
-      }
-      const float m_use = (m == -INFINITY) ? 0.f : m;
-
-      // pass 2: P = exp2(S * scale - m), row sum, P -> TMEM as bf16 pairs over the S columns already read
-      for (int c = 0; c < nchunks; ++c) {
-        tmem_ld_32x32b_x32(tmem_S + lane_addr + c * 32, r);
-        tmem_ld_wait();
-        const uint32_t bw = bitmask ? bits[c] : 0xffffffffu;
-        const int rel = lim - c * 32;
-        uint32_t pk[16];
+          if (c + 1 < nchunks) tmem_ld_32x32b_x32(tmem_S + lane_addr + (c + 1) * 32, nxt);
+          const float neg_m = (m == -INFINITY) ? 0.f : -m;
+          if (empty_chunk) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const bool ok0 = (i <= rel) && ((bw >> i) & 1u);
-          const bool ok1 = (i + 1 <= rel) && ((bw >> (i + 1)) & 1u);
-          const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_use)) : 0.f;
-          const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_use)) : 0.f;
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          } else if (full_chunk) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float p0 = exp2f(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m));
+              const float p1 = exp2f(fmaf(__uint_as_float(cur[i + 1]), p.scale_log2, neg_m));
+              const float p2 = exp2f(fmaf(__uint_as_float(cur[i + 2]), p.scale_log2, neg_m));
+              const float p3 = exp2f(fmaf(__uint_as_float(cur[i + 3]), p.scale_log2, neg_m));
+              l0 += p0, l1 += p1, l2 += p2, l3 += p3;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+              pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const bool ok0 = (i <= rel) && ((bw >> i) & 1u);
+              const bool ok1 = (i + 1 <= rel) && ((bw >> (i + 1)) & 1u);
+              const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m)) : 0.f;
+              const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(cur[i + 1]), p.scale_log2, neg_m)) : 0.f;
+              l0 += p0, l1 += p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+          }
+          if (c + 1 < nchunks) tmem_ld_wait();  // S chunk c+1 is in registers before P chunk c lands on S columns
+          tmem_st_32x32b_x16(tmem_S + lane_addr + c * 16, pk);
         }
-        tmem_st_32x32b_x16(tmem_S + lane_addr + c * 16, pk);
       }
+      l += (l0 + l1) + (l2 + l3);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full);
+      if (j == 0) STAMP(3);
     }
 
     // ---- epilogue ----
@@ -247,45 +334,59 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&o_full, 0);
       tc_fence_after();
     }
+    STAMP(4);
     const bool valid = row < nrows;
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* orow = p.out + b * p.so_b + static_cast<long long>(q0 + row) * p.so_l + h * p.so_h;
-    const float* vs = p.vsum + (static_cast<long long>(b) * p.Hkv + hkv) * VSUM_CHUNKS * D;
-    const float inv_s = 1.f / static_cast<float>(p.Skv);
-    for (int c = 0; c < D / 32; ++c) {
-      if (n_kv > 0) {
-        tmem_ld_32x32b_x32(tmem_O + lane_addr + c * 32, r);
-        tmem_ld_wait();
-      }
-      if (valid) {
-        uint32_t o[16];
-        if (l > 0.f) {
+    // Stage the bf16 row in shared memory (Q/K/V tiles are dead once o_full fired), then let the bulk-copy engine
+    // write each row as one contiguous D*2-byte burst: 32 rows per warp would otherwise mean 32 partial lines per
+    // store instruction.
+    constexpr int ROW_BYTES = D * 2 + 16;  // +16 B: conflict-free 16-byte stores at a row stride
+    uint8_t* srow = smem + row * ROW_BYTES;
+    const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(b) * p.Hkv + hkv) * D;
+    if (n_kv > 0) tmem_ld_32x32b_x32(tmem_O + lane_addr, r);
 #pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            o[i >> 1] = pack_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
-        } else {
-          // no allowed key in the whole row: uniform softmax over all Skv keys = mean of V
-          for (int i = 0; i < 32; i += 2) {
-            float a0 = 0.f, a1 = 0.f;
-            for (int ch = 0; ch < VSUM_CHUNKS; ++ch) {
-              a0 += vs[ch * D + c * 32 + i];
-              a1 += vs[ch * D + c * 32 + i + 1];
-            }
-            o[i >> 1] = pack_bf16x2(a0 * inv_s, a1 * inv_s);
-          }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t* cur = (c & 1) ? r2 : r;
+      uint32_t* nxt = (c & 1) ? r : r2;
+      if (n_kv > 0) {
+        tmem_ld_wait();
+        if (c + 1 < D / 32) tmem_ld_32x32b_x32(tmem_O + lane_addr + (c + 1) * 32, nxt);
       }
+      uint32_t o[16];
+      if (l > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          o[i >> 1] = pack_bf16x2(__uint_as_float(cur[i]) * inv, __uint_as_float(cur[i + 1]) * inv);
+      } else {
+        // no allowed key in the whole row: uniform softmax over all Skv keys = mean of V
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 f = valid ? *reinterpret_cast<const float4*>(vm + c * 32 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          o[i >> 1] = pack_bf16x2(f.x, f.y);
+          o[(i >> 1) + 1] = pack_bf16x2(f.z, f.w);
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(srow + c * 64);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+      dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
     }
+    fence_proxy_async_smem();
+    if (valid) {
+      __nv_bfloat16* orow = p.out + b * p.so_b + static_cast<long long>(q0 + row) * p.so_l + h * p.so_h;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(orow), "r"(smem_u32(srow)), "n"(D * 2)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be released once it has been read
   }
 
+  STAMP(5);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 256);
+  STAMP(6);
 }
 
 // Partial column sums of V over VSUM_CHUNKS row ranges: vsum[b][hkv][chunk][d] (fp32, deterministic).
@@ -323,6 +424,18 @@ __global__ void __launch_bounds__(256) v_colsum_kernel(const __nv_bfloat16* __re
   }
 }
 
+// vmean[b][hkv][d] = (sum of the chunk partials, fixed order) / Skv, stored after the partials.
+template <int D>
+__global__ void __launch_bounds__(D) v_mean_kernel(float* __restrict__ vsum, int B, int Hkv, int Skv,
+                                                   const int32_t* __restrict__ blockmaps, long long bm_stride_ints) {
+  const int hkv = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  if (blockmaps && blockmaps[static_cast<long long>(b) * bm_stride_ints + 3] == 0) return;
+  const float* part = vsum + (static_cast<long long>(b) * Hkv + hkv) * VSUM_CHUNKS * D;
+  float s = 0.f;
+  for (int ch = 0; ch < VSUM_CHUNKS; ++ch) s += part[ch * D + d];
+  vsum[(static_cast<long long>(B) * Hkv * VSUM_CHUNKS + static_cast<long long>(b) * Hkv + hkv) * D + d] = s / static_cast<float>(Skv);
+}
+
 int make_map_4d(CUtensorMap* m, const void* base, int D, int rows, int heads, int B, int64_t s_l, int64_t s_h,
                 int64_t s_b, int box_rows) {
   uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(rows), static_cast<uint64_t>(heads),
@@ -351,9 +464,15 @@ int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
 
 extern "C" {
 
+#ifdef SDAG_DEBUG_TIMING
+int sdag_debug_set_timing(unsigned long long* buf) {
+  return static_cast<int>(cudaMemcpyToSymbol(g_timing, &buf, sizeof(buf)));
+}
+#endif
+
 size_t sdag_prefill_workspace_bytes(int B, int Hkv, int D) {
   if (B <= 0 || Hkv <= 0 || D <= 0) return 0;
-  return sizeof(float) * static_cast<size_t>(B) * Hkv * VSUM_CHUNKS * D;
+  return sizeof(float) * static_cast<size_t>(B) * Hkv * (VSUM_CHUNKS + 1) * D;  // chunk partials + the mean
 }
 
 int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, const void* k, int64_t sk_b,
@@ -394,11 +513,13 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
   if (D == 128) {
     v_colsum_kernel<128><<<vgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(v), sv_b, sv_h, sv_l, Skv,
                                                 static_cast<float*>(workspace), blockmaps_dev, p.bm_stride_ints);
+    v_mean_kernel<128><<<dim3(Hkv, B), 128, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints);
     SDAG_CUDA_TRY(cudaGetLastError());
     return launch_prefill<128>(tq, tk, tv, p, cap_qtiles, st);
   }
   v_colsum_kernel<64><<<vgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(v), sv_b, sv_h, sv_l, Skv,
                                              static_cast<float*>(workspace), blockmaps_dev, p.bm_stride_ints);
+  v_mean_kernel<64><<<dim3(Hkv, B), 64, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints);
   SDAG_CUDA_TRY(cudaGetLastError());
   return launch_prefill<64>(tq, tk, tv, p, cap_qtiles, st);
 }

@@ -47,6 +47,19 @@ class Retriever(ABC):
         raise NotImplementedError
 
 
+def _n_epochs(n_rows: int, cand_cap: int) -> int:
+    """Number of (GEMM + tighten) epochs ip_search runs: first cap/2 rows, same again, then doubling."""
+    span = max(256, cand_cap // 2 // 256 * 256)
+    done, first, n = 0, True, 0
+    while done < n_rows:
+        done += span
+        if not first:
+            span *= 2
+        first = False
+        n += 1
+    return n
+
+
 class FlatIPIndex:
     """Exact inner-product index with the faiss ``IndexFlatIP`` surface the reference touches
     (``dense.py:36, 83``): ``d``, ``ntotal``, ``add``, ``search``.
@@ -137,6 +150,7 @@ class FlatIPIndex:
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             part_stats = torch.zeros(4, dtype=torch.int32, device=self.device)
+            _lib.count_launches(2 + 2 * _n_epochs(self.ntotal, self.cand_cap) + 2)  # init+cast, (gemm+tighten)*, scan+rescore
             _lib.check(
                 lib.ip_search(
                     xq[q0:q1].data_ptr(), nq,

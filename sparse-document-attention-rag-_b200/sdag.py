@@ -94,6 +94,7 @@ class BlockMap:
         self.n_prompts = n_prompts
         self.max_L = max_L
         self.kind = kind  # "spans" | "mask"
+        self.launch_qtiles = cap_qtiles  # grid extent in query tiles (>= the device-side count)
 
     def header(self, i: int = 0) -> dict:
         """Host copy of prompt i's header (synchronises; tests / benchmarks only)."""
@@ -114,6 +115,19 @@ class BlockMap:
         return q, kv, raw
 
 
+def _count_qtiles(lay: SdagLayout) -> int:
+    """Query-row tiles the device builder will emit for a canonical layout (an upper bound otherwise): one list
+    of <=128-row tiles per segment (system block, gaps, documents, question block)."""
+    T = _lib.SDAG_TILE
+    tiles = lambda n: (max(n, 0) + T - 1) // T  # noqa: E731
+    qa = min(lay.qa_start, lay.L)
+    n, pos = tiles(lay.S), lay.S
+    for s, e in lay.spans:
+        n += tiles(s - pos) + tiles(e - s)
+        pos = max(pos, e)
+    return n + tiles(qa - pos) + tiles(lay.L - qa) + 1
+
+
 def build_blockmap(layouts: Sequence[SdagLayout], device="cuda") -> BlockMap:
     """Block maps of a batch of prompts straight from their token offsets (``sdag_build_blockmap``).
 
@@ -130,6 +144,7 @@ def build_blockmap(layouts: Sequence[SdagLayout], device="cuda") -> BlockMap:
     rec = _to_device_i32(_pack_layouts(layouts, max_docs, nbr_k), device)
     stride_bytes = int(lib.sdag_blockmap_bytes(max_L, max_docs, nbr_k))
     buf = torch.empty((len(layouts), stride_bytes // 4), dtype=torch.int32, device=device)
+    _lib.count_launches(1)
     _lib.check(
         lib.sdag_build_blockmap(rec.data_ptr(), len(layouts), max_docs, nbr_k, max_L, buf.data_ptr(), stride_bytes,
                                 _lib.stream_ptr(buf.device)),
@@ -137,6 +152,7 @@ def build_blockmap(layouts: Sequence[SdagLayout], device="cuda") -> BlockMap:
     )
     cap_q = (max_L + _lib.SDAG_TILE - 1) // _lib.SDAG_TILE + 2 * max_docs + 3
     bm = BlockMap(buf, stride_bytes, cap_q, len(layouts), max_L, "spans")
+    bm.launch_qtiles = min(cap_q, max(_count_qtiles(l) for l in layouts))
     bm._layout_rec = rec  # keep alive until the kernel has run
     return bm
 
@@ -196,6 +212,7 @@ def causal_blockmap(L: int, device) -> BlockMap:
 # Attention calls
 # ------------------------------------------------------------------------------------------------------
 _workspaces = {}
+_profile_events = None  # set to a list to collect (start, end) CUDA events around each prefill attention call
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
@@ -224,6 +241,11 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
     ws_bytes = int(lib.sdag_prefill_workspace_bytes(B, Hkv, D))
     ws = _workspace(q.device, ws_bytes)
     scaling = float(D ** -0.5 if scaling is None else scaling)
+    ev = None
+    if _profile_events is not None:  # bench.py: CUDA-event timing of the attention launches, on their stream
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    _lib.count_launches(3)  # v_colsum + v_mean + sdag_prefill
     _lib.check(
         lib.sdag_prefill_fwd(
             q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
@@ -231,10 +253,13 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
             v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
             out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
             B, H, Hkv, L, S, D, scaling,
-            blockmap.buf.data_ptr(), blockmap.stride_bytes if blockmap.n_prompts > 1 else 0, blockmap.cap_qtiles,
+            blockmap.buf.data_ptr(), blockmap.stride_bytes if blockmap.n_prompts > 1 else 0, blockmap.launch_qtiles,
             ws.data_ptr(), ws.numel(), _lib.stream_ptr(q.device)),
         "sdag_prefill_fwd",
     )
+    if ev is not None:
+        ev[1].record()
+        _profile_events.append(ev)
     return out
 
 
@@ -320,6 +345,7 @@ def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sca
     ws_bytes = int(lib.sdag_decode_workspace_bytes(B, H, D, S))
     ws = _workspace(q.device, ws_bytes)
     scaling = float(D ** -0.5 if scaling is None else scaling)
+    _lib.count_launches(2)  # split + merge
     _lib.check(
         lib.sdag_decode_fwd(q2.data_ptr(), q2.stride(0), q2.stride(1),
                             k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
@@ -493,3 +519,20 @@ def run_rag_with_doc_isolation(model, tokenizer, query: str, malicious_docs: Lis
     layout = SdagLayout(L=input_ids.size(1), S=sys_user_len, spans=spans, qa_start=qa_start, neighbors=neighbors)
     bm = build_blockmap_checked(layout, device)
     return _generate(model, tokenizer, input_ids, bm, max_new_tokens)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Batched prefill (serving-side extension of the batch-of-1 reference loop, main.py:467-496)
+# ------------------------------------------------------------------------------------------------------
+def prefill_batch(model, input_ids_host: torch.Tensor, layouts: Sequence[SdagLayout], device="cuda"):
+    """First generated token of B prompts of equal length in one pass: ``input_ids_host`` int64 ``[B, L]`` in
+    (pinned) host memory, one ``SdagLayout`` per prompt.  Copies the ids to the device, builds the block maps
+    from the token offsets there, runs the SDAG prefill (last-position logits only) and returns
+    ``(first_tokens_host [B] int64, past_key_values)``.  Greedy or sampled exactly like ``_pick``."""
+    prepare_model(model)
+    ids = input_ids_host.to(device, non_blocking=True)
+    bm = build_blockmap(layouts, device)
+    with torch.no_grad():
+        out = model(input_ids=ids, use_cache=True, sdag_meta=bm, logits_to_keep=1)
+        nxt = _pick(out.logits[:, -1, :])
+    return nxt[:, 0].cpu(), out.past_key_values
