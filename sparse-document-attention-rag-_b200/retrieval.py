@@ -178,11 +178,13 @@ class ShardedFlatIPIndex:
     shard for all queries, one ``all_gather`` moves the local ``[Q,k]`` results, every rank merges ``G*k -> k``
     with the same order rule.  Global id = shard row offset + local row."""
 
-    def __init__(self, local: FlatIPIndex, group=None):
+    def __init__(self, local: FlatIPIndex, group=None, merge_fn=None):
         import torch.distributed as dist
 
         self.local = local
         self.group = group
+        # merge of the gathered [G,Q,k] lists; the CUDA kernel unless a test injects a checker for CPU (gloo) runs
+        self.merge_fn = merge_fn or merge_topk_device
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.d = local.d
         if self.world > 1:
@@ -199,11 +201,11 @@ class ShardedFlatIPIndex:
         if self.world == 1:
             return s, i
         Q = s.shape[0]
-        gs = torch.empty((self.world, Q, k), dtype=s.dtype, device=s.device)
-        gi = torch.empty((self.world, Q, k), dtype=i.dtype, device=i.device)
-        dist.all_gather_into_tensor(gs, s, group=self.group)
-        dist.all_gather_into_tensor(gi, i, group=self.group)
-        return merge_topk_device(gs, gi, k)
+        gs = torch.empty((self.world * Q, k), dtype=s.dtype, device=s.device)
+        gi = torch.empty((self.world * Q, k), dtype=i.dtype, device=i.device)
+        dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)  # rank-major concatenation
+        dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
+        return self.merge_fn(gs.view(self.world, Q, k), gi.view(self.world, Q, k), k)
 
     def search(self, x, k: int):
         xq = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self.local.device)
