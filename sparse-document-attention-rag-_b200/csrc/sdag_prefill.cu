@@ -30,6 +30,7 @@ struct PrefillParams {
   const int32_t* blockmaps;
   long long bm_stride_ints;
   const float* vsum;  // [B][Hkv][VSUM_CHUNKS][D] partial column sums of V, then [B][Hkv][D] mean of V
+  int* next_item;     // work-stealing counter (zeroed by v_mean_kernel before every launch)
   int B, H, Hkv, Lq, Skv;
   float scale_log2;
 };
@@ -62,67 +63,61 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "memory");
 }
 
-#ifdef SDAG_DEBUG_TIMING
-__device__ unsigned long long* g_timing = nullptr;  // [grid][8] globaltimer stamps (bring-up only)
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#define STAMP(slot)                                                                       \
-  do {                                                                                    \
-    if (g_timing && threadIdx.x == 64) g_timing[blockIdx.x * 8ull + (slot)] = gtime();    \
-  } while (0)
-#else
-#define STAMP(slot) \
-  do {              \
-  } while (0)
-#endif
+struct Item {
+  int q0, nrows, n_kv, h, b, hkv;
+  const int4* kvt;
+  const int32_t* map;
+  bool valid;
+};
 
-template <int D>
-__global__ void __launch_bounds__(192, 2)
-sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const PrefillParams p) {
-  // ---- which (query tile, head, prompt) ----
+// Work item i -> (query tile, head, prompt).  Tiles are the slow index so the longest tiles of every head run
+// first and the G heads of a kv group run side by side (K/V shared through L2).
+__device__ __forceinline__ Item fetch_item(const PrefillParams& p, long long i) {
+  Item it;
   const int per_tile = p.H * p.B;
-  const int t = blockIdx.x / per_tile;
-  const int rem = blockIdx.x - t * per_tile;
-  const int b = rem / p.H;
-  const int h = rem - b * p.H;
-  const int32_t* map = p.blockmaps + static_cast<long long>(b) * p.bm_stride_ints;
-  STAMP(0);
-  if (t >= map[0] || map[2] != 0) return;  // uniform: before any barrier / allocation
-  const int4 qt = reinterpret_cast<const int4*>(map + SDAG_BLOCKMAP_HEADER)[t];
-  const int q0 = qt.x, nrows = qt.y, n_kv = qt.w;
-  const int4* kvt = reinterpret_cast<const int4*>(map + SDAG_BLOCKMAP_HEADER) + map[5] + qt.z;
-  const int hkv = h / (p.H / p.Hkv);
-
-  if (n_kv == 0) {
-    // Gap rows only (no allowed key): every row is the mean of V over all keys.  No tensor work, no TMEM.
-    const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(b) * p.Hkv + hkv) * D;
-    for (int i = threadIdx.x; i < nrows * (D / 8); i += blockDim.x) {
-      const int rr = i / (D / 8), ch = i % (D / 8);
-      const float4 a = *reinterpret_cast<const float4*>(vm + ch * 8);
-      const float4 c4 = *reinterpret_cast<const float4*>(vm + ch * 8 + 4);
-      __nv_bfloat16* orow = p.out + b * p.so_b + static_cast<long long>(q0 + rr) * p.so_l + h * p.so_h;
-      *reinterpret_cast<uint4*>(orow + ch * 8) =
-          make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(c4.x, c4.y), pack_bf16x2(c4.z, c4.w));
-    }
-    return;
+  const int t = static_cast<int>(i / per_tile);
+  const int rem = static_cast<int>(i - static_cast<long long>(t) * per_tile);
+  it.b = rem / p.H;
+  it.h = rem - it.b * p.H;
+  it.hkv = it.h / (p.H / p.Hkv);
+  it.map = p.blockmaps + static_cast<long long>(it.b) * p.bm_stride_ints;
+  it.valid = t < it.map[0] && it.map[2] == 0;
+  it.q0 = it.nrows = it.n_kv = 0;
+  it.kvt = nullptr;
+  if (it.valid) {
+    const int4 qt = reinterpret_cast<const int4*>(it.map + SDAG_BLOCKMAP_HEADER)[t];
+    it.q0 = qt.x, it.nrows = qt.y, it.n_kv = qt.w;
+    it.kvt = reinterpret_cast<const int4*>(it.map + SDAG_BLOCKMAP_HEADER) + it.map[5] + qt.z;
   }
+  return it;
+}
 
+// Persistent: 2 CTAs per SM, each walks items blockIdx.x, blockIdx.x + gridDim.x, ...  Every role derives the same
+// item sequence on its own; mbarrier parities are tracked with per-role use counters.  The producer runs ahead
+// across item boundaries (Q after the item's last QK^T, K after each QK^T, V after each PV and after the previous
+// item's epilogue has drained its staging rows, which live in the V buffer), and the first QK^T of the next item is
+// issued while the softmax warps are still in the epilogue of the current one.
+// Threads: warps 0-3 = softmax / epilogue warpgroup (one query row per thread; grows to 200 registers), warp 4 = TMA
+// producer, warp 5 = MMA issuer (+ TMEM allocation), warps 6-7 idle; the second warpgroup shrinks to 56 registers.
+template <int D>
+__global__ void __launch_bounds__(256, 2)
+sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const PrefillParams p, const long long n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Smem<D>::kQ;
   uint8_t* sV = sK + Smem<D>::kK;
-  __shared__ uint64_t q_full, k_full, k_empty, v_full, v_empty, s_full, p_full, o_full;
+  __shared__ uint64_t q_full, q_empty, k_full, k_empty, v_full, v_empty, s_full, p_full, o_full, o_empty, stage_free;
+  __shared__ uint64_t sched_full[2], sched_empty[2];
+  __shared__ long long sched_item[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     mbar_init(&q_full, 1);
+    mbar_init(&q_empty, 1);
     mbar_init(&k_full, 1);
     mbar_init(&k_empty, 1);
     mbar_init(&v_full, 1);
@@ -130,12 +125,18 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(&s_full, 1);
     mbar_init(&p_full, 128);
     mbar_init(&o_full, 1);
+    mbar_init(&o_empty, 128);
+    mbar_init(&stage_free, 1);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&sched_full[x], 1);
+      mbar_init(&sched_empty[x], 32 + 128);  // every MMA-warp lane and softmax thread reads the slot
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 1) {
+  if (warp == 5) {
     tmem_alloc(&tmem_base_s, 256);
     tmem_relinquish();
   }
@@ -143,34 +144,62 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  STAMP(1);
   const uint32_t tmem_S = tmem;        // fp32 scores; P (bf16x2) is written over its first 64 columns
   const uint32_t tmem_O = tmem + 128;  // fp32 output accumulator, D columns
 
-  if (warp == 0) {
+  if (warp >= 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == 4) {
     // ======================= TMA producer =======================
-    if (lane == 0 && n_kv > 0) {
-      mbar_expect_tx(&q_full, Smem<D>::kQ);
-      for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sQ + dh * BM * 128, &tmQ, &q_full, dh * 64, q0, h, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int k0 = kvt[j].x;
-        mbar_wait(&k_empty, (j & 1) ^ 1);
-        mbar_expect_tx(&k_full, Smem<D>::kK);
-        for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sK + dh * BN * 128, &tmK, &k_full, dh * 64, k0, hkv, b);
-        mbar_wait(&v_empty, (j & 1) ^ 1);
-        mbar_expect_tx(&v_full, Smem<D>::kV);
-        for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sV + dh * BN * 128, &tmV, &v_full, dh * 64, k0, hkv, b);
+    if (lane == 0) {
+      uint32_t nq = 0, nk = 0, nv = 0;  // loads issued so far per buffer
+      // Dynamic longest-first scheduling: the first item is blockIdx.x, later ones come from a global counter; the
+      // producer publishes each item index to the other roles through a two-slot ring (so it can run one item ahead).
+      long long i = blockIdx.x;
+      for (uint32_t ns = 0;; ++ns) {
+        const uint32_t slot = ns & 1;
+        mbar_wait(&sched_empty[slot], ((ns >> 1) & 1) ^ 1);
+        sched_item[slot] = i < n_items ? i : -1;
+        mbar_arrive(&sched_full[slot]);
+        if (i >= n_items) break;
+        const Item it = fetch_item(p, i);
+        i = static_cast<long long>(gridDim.x) + atomicAdd(p.next_item, 1);
+        if (!it.valid || it.n_kv == 0) continue;
+        mbar_wait(&q_empty, (nq & 1) ^ 1);
+        mbar_expect_tx(&q_full, Smem<D>::kQ);
+        for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sQ + dh * BM * 128, &tmQ, &q_full, dh * 64, it.q0, it.h, it.b);
+        for (int j = 0; j < it.n_kv; ++j) {
+          const int k0 = it.kvt[j].x;
+          mbar_wait(&k_empty, (nk & 1) ^ 1);
+          mbar_expect_tx(&k_full, Smem<D>::kK);
+          for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sK + dh * BN * 128, &tmK, &k_full, dh * 64, k0, it.hkv, it.b);
+          ++nk;
+          mbar_wait(&v_empty, (nv & 1) ^ 1);
+          if (j == 0 && nq > 0) mbar_wait(&stage_free, (nq - 1) & 1);  // previous item's output rows have left sV
+          mbar_expect_tx(&v_full, Smem<D>::kV);
+          for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sV + dh * BN * 128, &tmV, &v_full, dh * 64, k0, it.hkv, it.b);
+          ++nv;
+        }
+        ++nq;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     // ======================= MMA issuer =======================
-    if (n_kv > 0) {
-      mbar_wait(&q_full, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int ncols = kvt[j].y;
+    uint32_t nq = 0, nt = 0;  // items and kv tiles processed so far
+    for (uint32_t ns = 0;; ++ns) {
+      const uint32_t slot = ns & 1;
+      mbar_wait(&sched_full[slot], (ns >> 1) & 1);
+      const long long i = sched_item[slot];
+      mbar_arrive(&sched_empty[slot]);
+      if (i < 0) break;
+      const Item it = fetch_item(p, i);
+      if (!it.valid || it.n_kv == 0) continue;
+      mbar_wait(&q_full, nq & 1);
+      for (int j = 0; j < it.n_kv; ++j, ++nt) {
+        const int ncols = it.kvt[j].y;
         const uint32_t n_eff = static_cast<uint32_t>((ncols + 15) & ~15);
         const int pv_steps = (ncols + 15) >> 4;
-        mbar_wait(&k_full, j & 1);
+        mbar_wait(&k_full, nt & 1);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t idesc = umma_idesc_bf16_f32(BM, n_eff, 0, 0);
@@ -181,12 +210,14 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_ss(tmem_S, umma_smem_desc_sw128(smem_u32(sQ) + off, 16, 1024),
                     umma_smem_desc_sw128(smem_u32(sK) + offk, 16, 1024), idesc, ks > 0);
           }
-          umma_commit(&k_empty);  // K tile consumed -> producer may load K_{j+1}
-          umma_commit(&s_full);   // scores ready (and every earlier MMA, incl. P_{j-1} V_{j-1}, retired)
+          umma_commit(&k_empty);                        // K tile consumed -> producer may load the next K
+          if (j == it.n_kv - 1) umma_commit(&q_empty);  // Q consumed -> producer may load the next item's Q
+          umma_commit(&s_full);  // scores ready (and every earlier MMA, incl. the previous P.V, retired)
         }
         __syncwarp();
-        mbar_wait(&p_full, j & 1);
-        mbar_wait(&v_full, j & 1);
+        mbar_wait(&p_full, nt & 1);
+        mbar_wait(&v_full, nt & 1);
+        if (j == 0 && nq > 0) mbar_wait(&o_empty, (nq - 1) & 1);  // previous item's epilogue has read O out of TMEM
         tc_fence_after();
         if (lane == 0) {
           const uint32_t idesc = umma_idesc_bf16_f32(BM, D, 0, 1);  // B = V, MN-major
@@ -195,198 +226,231 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     (j > 0 || ks > 0) ? 1u : 0u);
           }
           umma_commit(&v_empty);
-          if (j == n_kv - 1) umma_commit(&o_full);
+          if (j == it.n_kv - 1) umma_commit(&o_full);
         }
         __syncwarp();
       }
+      ++nq;
     }
+   }
   } else {
-    // ======================= softmax + epilogue (warps 2..5) =======================
-    const int quarter = warp & 3;  // TMEM lanes this warp may touch: [32*quarter, 32*quarter+32)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    // ======================= softmax + epilogue (warps 0..3) =======================
+    const int quarter = warp;  // TMEM lanes this warp may touch: [32*quarter, 32*quarter+32)
     const int row = quarter * 32 + lane;
+    const int stid = tid;      // 0..127 among the softmax threads
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    float m = -INFINITY, l = 0.f;
     uint32_t r[32], r2[32];
+    uint32_t nq = 0, nt = 0;
 
-    for (int j = 0; j < n_kv; ++j) {
-      const int4 kt = kvt[j];
-      const int ncols = kt.y;
-      const bool bitmask = (kt.w & KV_FLAG_BITMASK) != 0;
-      int lim = min(ncols - 1, row + kt.z);  // allowed columns of this row: c <= lim
-      // warp-uniform bounds of lim over the 32 rows of this warp: chunks at or below wlim_lo need no masking at
-      // all, chunks above wlim_hi hold no allowed column for any lane
-      int wlim_lo = min(ncols - 1, quarter * 32 + kt.z);
-      int wlim_hi = min(ncols - 1, quarter * 32 + 31 + kt.z);
-      uint32_t bits[4] = {0, 0, 0, 0};
-      if (bitmask) {
-        lim = ncols - 1;
-        wlim_lo = -1;  // every chunk takes the masked path
-        wlim_hi = ncols - 1;
-        if (q0 + row < p.Lq) {
-          const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
-                                                          static_cast<long long>(q0 + row) * map[7] + (kt.x >> 5));
-          bits[0] = w.x, bits[1] = w.y, bits[2] = w.z, bits[3] = w.w;
+    for (uint32_t ns = 0;; ++ns) {
+      const uint32_t slot = ns & 1;
+      mbar_wait(&sched_full[slot], (ns >> 1) & 1);
+      const long long i = sched_item[slot];
+      mbar_arrive(&sched_empty[slot]);
+      if (i < 0) break;
+      const Item it = fetch_item(p, i);
+      if (!it.valid) continue;
+      const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(it.b) * p.Hkv + it.hkv) * D;
+      if (it.n_kv == 0) {
+        // Gap rows only (no allowed key): every row is the mean of V over all keys.  No tensor work.
+        for (int e = stid; e < it.nrows * (D / 8); e += 128) {
+          const int rr = e / (D / 8), ch = e % (D / 8);
+          const float4 a = *reinterpret_cast<const float4*>(vm + ch * 8);
+          const float4 c4 = *reinterpret_cast<const float4*>(vm + ch * 8 + 4);
+          __nv_bfloat16* orow = p.out + it.b * p.so_b + static_cast<long long>(it.q0 + rr) * p.so_l + it.h * p.so_h;
+          *reinterpret_cast<uint4*>(orow + ch * 8) =
+              make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(c4.x, c4.y), pack_bf16x2(c4.z, c4.w));
         }
+        continue;
       }
-      const int nchunks = (ncols + 31) >> 5;
-      mbar_wait(&s_full, j & 1);
-      tc_fence_after();
-      if (j == 0) STAMP(2);
+      const int q0 = it.q0;
+      const int32_t* map = it.map;
+      float m = -INFINITY, l = 0.f;
 
-      // Single pass over the scores (TMEM reads are the scarce resource): per 32-column chunk take the chunk
-      // maximum, keep the running reference maximum m unless it is exceeded by more than RESCALE_TAU, and write
-      // P = exp2(S*scale - m) straight back over the S columns already consumed.  When m does move, everything
-      // accumulated against the old reference — l, O, and the P chunks of this tile already written — is
-      // rescaled (rare after the first chunk of the first tile).
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-      tmem_ld_32x32b_x32(tmem_S + lane_addr, r);
-      tmem_ld_wait();
+      for (int j = 0; j < it.n_kv; ++j, ++nt) {
+        const int4 kt = it.kvt[j];
+        const int ncols = kt.y;
+        const bool bitmask = (kt.w & KV_FLAG_BITMASK) != 0;
+        int lim = min(ncols - 1, row + kt.z);  // allowed columns of this row: c <= lim
+        // warp-uniform bounds of lim over the 32 rows of this warp: chunks at or below wlim_lo need no masking at
+        // all, chunks above wlim_hi hold no allowed column for any lane
+        int wlim_lo = min(ncols - 1, quarter * 32 + kt.z);
+        int wlim_hi = min(ncols - 1, quarter * 32 + 31 + kt.z);
+        uint32_t bits[4] = {0, 0, 0, 0};
+        if (bitmask) {
+          lim = ncols - 1;
+          wlim_lo = -1;  // every chunk takes the masked path
+          wlim_hi = ncols - 1;
+          if (q0 + row < p.Lq) {
+            const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
+                                                            static_cast<long long>(q0 + row) * map[7] + (kt.x >> 5));
+            bits[0] = w.x, bits[1] = w.y, bits[2] = w.z, bits[3] = w.w;
+          }
+        }
+        const int nchunks = (ncols + 31) >> 5;
+        mbar_wait(&s_full, nt & 1);
+        tc_fence_after();
+
+        // Single pass over the scores: per 32-column chunk take the chunk maximum, keep the running reference
+        // maximum m unless it is exceeded by more than RESCALE_TAU, and write P = exp2(S*scale - m) straight back
+        // over the S columns already consumed.  When m does move, everything accumulated against the old reference
+        // — l, O, and the P chunks of this tile already written — is rescaled (rare after the first chunk).
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        tmem_ld_32x32b_x32(tmem_S + lane_addr, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t* cur = (c & 1) ? r2 : r;
-        uint32_t* nxt = (c & 1) ? r : r2;
-        if (c < nchunks) {
-          const bool full_chunk = wlim_lo >= c * 32 + 31;
-          const bool empty_chunk = wlim_hi < c * 32;
-          const uint32_t bw = bitmask ? bits[c] : 0xffffffffu;
-          const int rel = lim - c * 32;  // columns i <= rel are allowed (masked chunks)
-          uint32_t pk[16];
-          if (!empty_chunk) {
-            float mx = -INFINITY;
-            if (full_chunk) {
+        for (int c = 0; c < 4; ++c) {
+          uint32_t* cur = (c & 1) ? r2 : r;
+          uint32_t* nxt = (c & 1) ? r : r2;
+          if (c < nchunks) {
+            const bool full_chunk = wlim_lo >= c * 32 + 31;
+            const bool empty_chunk = wlim_hi < c * 32;
+            const uint32_t bw = bitmask ? bits[c] : 0xffffffffu;
+            const int rel = lim - c * 32;  // columns i <= rel are allowed (masked chunks)
+            uint32_t pk[16];
+            if (!empty_chunk) {
+              float mx = -INFINITY;
+              if (full_chunk) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) mx = fmax3(mx, __uint_as_float(cur[i]), __uint_as_float(cur[i + 1]));
-            } else {
+                for (int e = 0; e < 32; e += 2) mx = fmax3(mx, __uint_as_float(cur[e]), __uint_as_float(cur[e + 1]));
+              } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const bool ok = (i <= rel) && ((bw >> i) & 1u);
-                mx = fmaxf(mx, ok ? __uint_as_float(cur[i]) : -INFINITY);
+                for (int e = 0; e < 32; ++e) {
+                  const bool ok = (e <= rel) && ((bw >> e) & 1u);
+                  mx = fmaxf(mx, ok ? __uint_as_float(cur[e]) : -INFINITY);
+                }
               }
-            }
-            mx *= p.scale_log2;
-            const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf)
-            if (__any_sync(0xffffffffu, need)) {
-              const float alpha = need ? exp2f(m - mx) : 1.f;
-              if (need) m = mx;
-              l *= alpha;
-              l0 *= alpha, l1 *= alpha, l2 *= alpha, l3 *= alpha;
-              if (j > 0) {  // O holds P_0 V_0 .. P_{j-1} V_{j-1}, all retired (s_full commit)
-                for (int oc = 0; oc < D / 32; ++oc) {
-                  tmem_ld_32x32b_x32(tmem_O + lane_addr + oc * 32, nxt);
+              mx *= p.scale_log2;
+              const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf)
+              if (__any_sync(0xffffffffu, need)) {
+                const float alpha = need ? exp2f(m - mx) : 1.f;
+                if (need) m = mx;
+                l *= alpha;
+                l0 *= alpha, l1 *= alpha, l2 *= alpha, l3 *= alpha;
+                if (j > 0) {  // O holds P_0 V_0 .. P_{j-1} V_{j-1}, all retired (s_full commit)
+                  for (int oc = 0; oc < D / 32; ++oc) {
+                    tmem_ld_32x32b_x32(tmem_O + lane_addr + oc * 32, nxt);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) nxt[e] = __float_as_uint(__uint_as_float(nxt[e]) * alpha);
+                    tmem_st_32x32b_x32(tmem_O + lane_addr + oc * 32, nxt);
+                  }
+                }
+                for (int pc = 0; pc < c; ++pc) {  // P chunks of this tile written against the old reference
+                  tmem_ld_32x32b_x16(tmem_S + lane_addr + pc * 16, nxt);
                   tmem_ld_wait();
 #pragma unroll
-                  for (int i = 0; i < 32; ++i) nxt[i] = __float_as_uint(__uint_as_float(nxt[i]) * alpha);
-                  tmem_st_32x32b_x32(tmem_O + lane_addr + oc * 32, nxt);
+                  for (int e = 0; e < 16; ++e) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&nxt[e]));
+                    nxt[e] = pack_bf16x2(f.x * alpha, f.y * alpha);
+                  }
+                  tmem_st_32x32b_x16(tmem_S + lane_addr + pc * 16, nxt);
                 }
               }
-              for (int pc = 0; pc < c; ++pc) {  // P chunks of this tile written against the old reference
-                tmem_ld_32x32b_x16(tmem_S + lane_addr + pc * 16, nxt);
-                tmem_ld_wait();
+            }
+            if (c + 1 < nchunks) tmem_ld_32x32b_x32(tmem_S + lane_addr + (c + 1) * 32, nxt);
+            const float neg_m = (m == -INFINITY) ? 0.f : -m;
+            if (empty_chunk) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&nxt[i]));
-                  nxt[i] = pack_bf16x2(f.x * alpha, f.y * alpha);
-                }
-                tmem_st_32x32b_x16(tmem_S + lane_addr + pc * 16, nxt);
+              for (int e = 0; e < 16; ++e) pk[e] = 0u;
+            } else if (full_chunk) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                const float p0 = exp2f(fmaf(__uint_as_float(cur[e]), p.scale_log2, neg_m));
+                const float p1 = exp2f(fmaf(__uint_as_float(cur[e + 1]), p.scale_log2, neg_m));
+                const float p2 = exp2f(fmaf(__uint_as_float(cur[e + 2]), p.scale_log2, neg_m));
+                const float p3 = exp2f(fmaf(__uint_as_float(cur[e + 3]), p.scale_log2, neg_m));
+                l0 += p0, l1 += p1, l2 += p2, l3 += p3;
+                pk[e >> 1] = pack_bf16x2(p0, p1);
+                pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 32; e += 2) {
+                const bool ok0 = (e <= rel) && ((bw >> e) & 1u);
+                const bool ok1 = (e + 1 <= rel) && ((bw >> (e + 1)) & 1u);
+                const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(cur[e]), p.scale_log2, neg_m)) : 0.f;
+                const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(cur[e + 1]), p.scale_log2, neg_m)) : 0.f;
+                l0 += p0, l1 += p1;
+                pk[e >> 1] = pack_bf16x2(p0, p1);
               }
             }
+            if (c + 1 < nchunks) tmem_ld_wait();  // S chunk c+1 is in registers before P chunk c lands on S columns
+            tmem_st_32x32b_x16(tmem_S + lane_addr + c * 16, pk);
           }
-          if (c + 1 < nchunks) tmem_ld_32x32b_x32(tmem_S + lane_addr + (c + 1) * 32, nxt);
-          const float neg_m = (m == -INFINITY) ? 0.f : -m;
-          if (empty_chunk) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pk[i] = 0u;
-          } else if (full_chunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float p0 = exp2f(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m));
-              const float p1 = exp2f(fmaf(__uint_as_float(cur[i + 1]), p.scale_log2, neg_m));
-              const float p2 = exp2f(fmaf(__uint_as_float(cur[i + 2]), p.scale_log2, neg_m));
-              const float p3 = exp2f(fmaf(__uint_as_float(cur[i + 3]), p.scale_log2, neg_m));
-              l0 += p0, l1 += p1, l2 += p2, l3 += p3;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-              pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const bool ok0 = (i <= rel) && ((bw >> i) & 1u);
-              const bool ok1 = (i + 1 <= rel) && ((bw >> (i + 1)) & 1u);
-              const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(cur[i]), p.scale_log2, neg_m)) : 0.f;
-              const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(cur[i + 1]), p.scale_log2, neg_m)) : 0.f;
-              l0 += p0, l1 += p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-          }
-          if (c + 1 < nchunks) tmem_ld_wait();  // S chunk c+1 is in registers before P chunk c lands on S columns
-          tmem_st_32x32b_x16(tmem_S + lane_addr + c * 16, pk);
         }
+        l += (l0 + l1) + (l2 + l3);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full);
       }
-      l += (l0 + l1) + (l2 + l3);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full);
-      if (j == 0) STAMP(3);
-    }
 
-    // ---- epilogue ----
-    if (n_kv > 0) {
-      mbar_wait(&o_full, 0);
+      // ---- epilogue: O / l -> bf16 -> staging rows in the (now idle) V buffer -> one bulk copy per row ----
+      mbar_wait(&o_full, nq & 1);
       tc_fence_after();
-    }
-    STAMP(4);
-    const bool valid = row < nrows;
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    // Stage the bf16 row in shared memory (Q/K/V tiles are dead once o_full fired), then let the bulk-copy engine
-    // write each row as one contiguous D*2-byte burst: 32 rows per warp would otherwise mean 32 partial lines per
-    // store instruction.
-    constexpr int ROW_BYTES = D * 2 + 16;  // +16 B: conflict-free 16-byte stores at a row stride
-    uint8_t* srow = smem + row * ROW_BYTES;
-    const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(b) * p.Hkv + hkv) * D;
-    if (n_kv > 0) tmem_ld_32x32b_x32(tmem_O + lane_addr, r);
+      const bool valid = row < it.nrows;
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      constexpr int HALF_BYTES = 128 + 16;  // 64 bf16 per round; +16 B keeps 16-byte stores at a row stride conflict-free
+      uint8_t* srow = sV + row * HALF_BYTES;
+      __nv_bfloat16* orow = p.out + it.b * p.so_b + static_cast<long long>(q0 + row) * p.so_l + it.h * p.so_h;
+      tmem_ld_32x32b_x32(tmem_O + lane_addr, r);
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t* cur = (c & 1) ? r2 : r;
-      uint32_t* nxt = (c & 1) ? r : r2;
-      if (n_kv > 0) {
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t* cur = (c & 1) ? r2 : r;
+        uint32_t* nxt = (c & 1) ? r : r2;
         tmem_ld_wait();
-        if (c + 1 < D / 32) tmem_ld_32x32b_x32(tmem_O + lane_addr + (c + 1) * 32, nxt);
-      }
-      uint32_t o[16];
-      if (l > 0.f) {
+        if (c + 1 < D / 32) {
+          tmem_ld_32x32b_x32(tmem_O + lane_addr + (c + 1) * 32, nxt);
+        } else {
+          tc_fence_before();
+          mbar_arrive(&o_empty);  // O is in registers: the next item's first P.V may overwrite it
+        }
+        uint32_t o[16];
+        if (l > 0.f) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          o[i >> 1] = pack_bf16x2(__uint_as_float(cur[i]) * inv, __uint_as_float(cur[i + 1]) * inv);
-      } else {
-        // no allowed key in the whole row: uniform softmax over all Skv keys = mean of V
+          for (int e = 0; e < 32; e += 2)
+            o[e >> 1] = pack_bf16x2(__uint_as_float(cur[e]) * inv, __uint_as_float(cur[e + 1]) * inv);
+        } else {
+          // no allowed key in the whole row: uniform softmax over all Skv keys = mean of V
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 f = valid ? *reinterpret_cast<const float4*>(vm + c * 32 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          o[i >> 1] = pack_bf16x2(f.x, f.y);
-          o[(i >> 1) + 1] = pack_bf16x2(f.z, f.w);
+          for (int e = 0; e < 32; e += 4) {
+            const float4 f = valid ? *reinterpret_cast<const float4*>(vm + c * 32 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            o[e >> 1] = pack_bf16x2(f.x, f.y);
+            o[(e >> 1) + 1] = pack_bf16x2(f.z, f.w);
+          }
+        }
+        if ((c & 1) == 0 && c > 0) {
+          // second round reuses the staging rows: wait until the bulk engine has read the first round
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        uint4* dst = reinterpret_cast<uint4*>(srow + (c & 1) * 64);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+        if ((c & 1) == 1 || c == D / 32 - 1) {
+          fence_proxy_async_smem();
+          if (valid) {
+            const int bytes = ((c & 1) + 1) * 64;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(orow + (c >> 1) * 64),
+                         "r"(smem_u32(srow)), "r"(bytes)
+                         : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
-      uint4* dst = reinterpret_cast<uint4*>(srow + c * 64);
-      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-      dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      // all 128 rows have left the V buffer -> the producer may load the next item's first V tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (stid == 0) mbar_arrive(&stage_free);
+      ++nq;
     }
-    fence_proxy_async_smem();
-    if (valid) {
-      __nv_bfloat16* orow = p.out + b * p.so_b + static_cast<long long>(q0 + row) * p.so_l + h * p.so_h;
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(orow), "r"(smem_u32(srow)), "n"(D * 2)
-                   : "memory");
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be released once it has been read
   }
 
-  STAMP(5);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
-  STAMP(6);
+  if (warp == 5) tmem_dealloc(tmem, 256);
 }
 
 // Partial column sums of V over VSUM_CHUNKS row ranges: vsum[b][hkv][chunk][d] (fp32, deterministic).
@@ -429,6 +493,8 @@ template <int D>
 __global__ void __launch_bounds__(D) v_mean_kernel(float* __restrict__ vsum, int B, int Hkv, int Skv,
                                                    const int32_t* __restrict__ blockmaps, long long bm_stride_ints) {
   const int hkv = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  if (hkv == 0 && b == 0 && d == 0)  // work-stealing counter of the attention kernel that follows on the stream
+    *reinterpret_cast<int*>(vsum + static_cast<long long>(B) * Hkv * (VSUM_CHUNKS + 1) * D) = 0;
   if (blockmaps && blockmaps[static_cast<long long>(b) * bm_stride_ints + 3] == 0) return;
   const float* part = vsum + (static_cast<long long>(b) * Hkv + hkv) * VSUM_CHUNKS * D;
   float s = 0.f;
@@ -449,14 +515,19 @@ template <int D>
 int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const PrefillParams& p,
                    int cap_qtiles, cudaStream_t st) {
   static bool configured = false;
+  static int n_sm = 148;
   const int smem = Smem<D>::kTotal > 100 * 1024 ? Smem<D>::kTotal : 100 * 1024;  // cap residency at 2 CTAs / SM (TMEM)
   if (!configured) {
     SDAG_CUDA_TRY(cudaFuncSetAttribute(sdag_prefill_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0;
+    SDAG_CUDA_TRY(cudaGetDevice(&dev));
+    SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
-  const long long grid = static_cast<long long>(cap_qtiles) * p.H * p.B;
-  if (grid <= 0 || grid > 0x7fffffffll) return SDAG_ERR_INVALID;
-  sdag_prefill_kernel<D><<<static_cast<unsigned>(grid), 192, smem, st>>>(tq, tk, tv, p);
+  const long long n_items = static_cast<long long>(cap_qtiles) * p.H * p.B;
+  if (n_items <= 0) return SDAG_ERR_INVALID;
+  const long long grid = n_items < 2ll * n_sm ? n_items : 2ll * n_sm;
+  sdag_prefill_kernel<D><<<static_cast<unsigned>(grid), 256, smem, st>>>(tq, tk, tv, p, n_items);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -464,15 +535,10 @@ int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
 
 extern "C" {
 
-#ifdef SDAG_DEBUG_TIMING
-int sdag_debug_set_timing(unsigned long long* buf) {
-  return static_cast<int>(cudaMemcpyToSymbol(g_timing, &buf, sizeof(buf)));
-}
-#endif
 
 size_t sdag_prefill_workspace_bytes(int B, int Hkv, int D) {
   if (B <= 0 || Hkv <= 0 || D <= 0) return 0;
-  return sizeof(float) * static_cast<size_t>(B) * Hkv * (VSUM_CHUNKS + 1) * D;  // chunk partials + the mean
+  return sizeof(float) * static_cast<size_t>(B) * Hkv * (VSUM_CHUNKS + 1) * D + 16;  // chunk partials + the mean + scheduler counter
 }
 
 int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, const void* k, int64_t sk_b,
@@ -506,6 +572,7 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
   p.blockmaps = blockmaps_dev;
   p.bm_stride_ints = static_cast<long long>(blockmap_stride_bytes / 4);
   p.vsum = static_cast<const float*>(workspace);
+  p.next_item = reinterpret_cast<int*>(static_cast<float*>(workspace) + static_cast<size_t>(B) * Hkv * (VSUM_CHUNKS + 1) * D);
   p.B = B, p.H = H, p.Hkv = Hkv, p.Lq = Lq, p.Skv = Skv;
   p.scale_log2 = scaling * 1.4426950408889634f;
 

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     # pure size queries work without a GPU
     assert lib.sdag_layout_ints(10, 2) == 8 + 20 + 20
     assert lib.sdag_blockmap_bytes(2642, 10, 0) % 16 == 0 and lib.sdag_blockmap_bytes(2642, 10, 0) > 0
-    assert lib.sdag_prefill_workspace_bytes(1, 8, 128) == 4 * 8 * 33 * 128
+    assert lib.sdag_prefill_workspace_bytes(1, 8, 128) == 4 * 8 * 33 * 128 + 16
     assert lib.ip_search_workspace_bytes(4096, 1024, 10, 2048) > 4096 * 2048 * 8
 
 
