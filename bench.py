@@ -295,7 +295,10 @@ def run_b200(args):
             "remeasured_for_clocks": remeasured,
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "sdag_prefill_kernel<128> (+ v_colsum) per layer launch",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 8 prompts
+                     # (profiles/r01_ncu_sdag_prefill_cfg2.md); algorithmic q+k+v+out bytes are 433 MB
+                     "traffic": 525.5e6 * B / 8 if B == 8 else None,
+                     "kernel": "sdag_prefill_kernel<128> (+ v_colsum, v_mean) per layer launch",
                      "launch_ms": attn_avg_ms, "flops_per_launch": attn_flops_per_launch,
                      "peak_source": pk["_source"] + ", bf16 sustained"},
         "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": int(ids_host.numel() * 8 + B * 28 * 4),

@@ -108,7 +108,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Smem<D>::kQ;
   uint8_t* sV = sK + Smem<D>::kK;
-  __shared__ uint64_t q_full, q_empty, k_full, k_empty, v_full, v_empty, s_full, p_full, o_full, o_empty, stage_free;
+  __shared__ uint64_t q_full, q_empty, k_full, k_empty, v_full, v_empty, s_full[2], p_full[2], pv_done, o_full, o_empty, stage_free;
   __shared__ uint64_t sched_full[2], sched_empty[2];
   __shared__ long long sched_item[2];
   __shared__ uint32_t tmem_base_s;
@@ -122,8 +122,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(&k_empty, 1);
     mbar_init(&v_full, 1);
     mbar_init(&v_empty, 1);
-    mbar_init(&s_full, 1);
-    mbar_init(&p_full, 128);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&p_full[x], 128);
+    }
+    mbar_init(&pv_done, 1);
     mbar_init(&o_full, 1);
     mbar_init(&o_empty, 128);
     mbar_init(&stage_free, 1);
@@ -144,8 +147,10 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tmem_S = tmem;        // fp32 scores; P (bf16x2) is written over its first 64 columns
-  const uint32_t tmem_O = tmem + 128;  // fp32 output accumulator, D columns
+  // TMEM columns: two 64-column score buffers S0 / S1 (P, as bf16 pairs, is written over the first 32 columns of
+  // the buffer it came from), then the fp32 output accumulator (D columns).
+  const uint32_t tmem_S = tmem;
+  const uint32_t tmem_O = tmem + 128;
 
   if (warp >= 4) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -185,7 +190,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 5) {
     // ======================= MMA issuer =======================
-    uint32_t nq = 0, nt = 0;  // items and kv tiles processed so far
+    // Each 128-column kv tile is processed as one or two 64-column sub-steps.  Scores of sub-step g go to S[g & 1],
+    // so QK^T of sub-steps g+1 / g+2 is issued before the softmax of g has finished: issue order is
+    //   QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...   (QK(g+2) overwrites the buffer whose P was consumed by PV(g)).
+    uint32_t nq = 0;           // items with tensor work done so far
+    uint32_t ntk = 0, ntv = 0; // K / V tiles consumed so far (barrier phases)
+    uint32_t gq = 0, gp = 0;   // QK / PV sub-steps issued so far (S-buffer index and phases)
     for (uint32_t ns = 0;; ++ns) {
       const uint32_t slot = ns & 1;
       mbar_wait(&sched_full[slot], (ns >> 1) & 1);
@@ -195,40 +205,83 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const Item it = fetch_item(p, i);
       if (!it.valid || it.n_kv == 0) continue;
       mbar_wait(&q_full, nq & 1);
-      for (int j = 0; j < it.n_kv; ++j, ++nt) {
-        const int ncols = it.kvt[j].y;
-        const uint32_t n_eff = static_cast<uint32_t>((ncols + 15) & ~15);
-        const int pv_steps = (ncols + 15) >> 4;
-        mbar_wait(&k_full, nt & 1);
+      int qj = 0, qs = 0, pj = 0, ps = 0;  // cursors: (tile, sub-step) of the next QK / PV to issue
+      bool first_pv = true;
+
+      auto issue_qk = [&]() {
+        const int ncols = it.kvt[qj].y;
+        const int nsub = ncols > 64 ? 2 : 1;
+        const int sub_cols = min(64, ncols - qs * 64);
+        if (qs == 0) {
+          mbar_wait(&k_full, ntk & 1);
+          ++ntk;
+        }
         tc_fence_after();
+        const bool last_sub = qs == nsub - 1;
         if (lane == 0) {
-          const uint32_t idesc = umma_idesc_bf16_f32(BM, n_eff, 0, 0);
+          const uint32_t idesc = umma_idesc_bf16_f32(BM, static_cast<uint32_t>((sub_cols + 15) & ~15), 0, 0);
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t off = (ks >> 2) * (BM * 128) + (ks & 3) * 32;
-            const uint32_t offk = (ks >> 2) * (BN * 128) + (ks & 3) * 32;
-            umma_ss(tmem_S, umma_smem_desc_sw128(smem_u32(sQ) + off, 16, 1024),
+            const uint32_t offk = (ks >> 2) * (BN * 128) + qs * (64 * 128) + (ks & 3) * 32;
+            umma_ss(tmem_S + (gq & 1) * 64, umma_smem_desc_sw128(smem_u32(sQ) + off, 16, 1024),
                     umma_smem_desc_sw128(smem_u32(sK) + offk, 16, 1024), idesc, ks > 0);
           }
-          umma_commit(&k_empty);                        // K tile consumed -> producer may load the next K
-          if (j == it.n_kv - 1) umma_commit(&q_empty);  // Q consumed -> producer may load the next item's Q
-          umma_commit(&s_full);  // scores ready (and every earlier MMA, incl. the previous P.V, retired)
+          if (last_sub) {
+            umma_commit(&k_empty);                         // K tile consumed -> producer may load the next K
+            if (qj == it.n_kv - 1) umma_commit(&q_empty);  // Q consumed -> producer may load the next item's Q
+          }
+          umma_commit(&s_full[gq & 1]);
         }
         __syncwarp();
-        mbar_wait(&p_full, nt & 1);
-        mbar_wait(&v_full, nt & 1);
-        if (j == 0 && nq > 0) mbar_wait(&o_empty, (nq - 1) & 1);  // previous item's epilogue has read O out of TMEM
+        ++gq;
+        if (last_sub) {
+          ++qj;
+          qs = 0;
+        } else {
+          ++qs;
+        }
+      };
+      auto issue_pv = [&]() {
+        const int ncols = it.kvt[pj].y;
+        const int nsub = ncols > 64 ? 2 : 1;
+        const int sub_cols = min(64, ncols - ps * 64);
+        mbar_wait(&p_full[gp & 1], (gp >> 1) & 1);
+        if (ps == 0) {
+          mbar_wait(&v_full, ntv & 1);
+          ++ntv;
+        }
+        if (first_pv && nq > 0) mbar_wait(&o_empty, (nq - 1) & 1);  // previous item's epilogue has read O out of TMEM
         tc_fence_after();
+        const bool last_sub = ps == nsub - 1;
         if (lane == 0) {
           const uint32_t idesc = umma_idesc_bf16_f32(BM, D, 0, 1);  // B = V, MN-major
+          const int pv_steps = (sub_cols + 15) >> 4;
           for (int ks = 0; ks < pv_steps; ++ks) {
-            umma_ts(tmem_O, tmem_S + ks * 8, umma_smem_desc_sw128(smem_u32(sV) + ks * 16 * 128, BN * 128, 1024), idesc,
-                    (j > 0 || ks > 0) ? 1u : 0u);
+            umma_ts(tmem_O, tmem_S + (gp & 1) * 64 + ks * 8,
+                    umma_smem_desc_sw128(smem_u32(sV) + (ps * 64 + ks * 16) * 128, BN * 128, 1024), idesc,
+                    (!first_pv || ks > 0) ? 1u : 0u);
           }
-          umma_commit(&v_empty);
-          if (j == it.n_kv - 1) umma_commit(&o_full);
+          if (last_sub) umma_commit(&v_empty);
+          umma_commit(&pv_done);
+          if (last_sub && pj == it.n_kv - 1) umma_commit(&o_full);
         }
         __syncwarp();
+        first_pv = false;
+        ++gp;
+        if (last_sub) {
+          ++pj;
+          ps = 0;
+        } else {
+          ++ps;
+        }
+      };
+
+      issue_qk();
+      if (qj < it.n_kv) issue_qk();
+      while (pj < it.n_kv) {
+        issue_pv();
+        if (qj < it.n_kv) issue_qk();
       }
       ++nq;
     }
@@ -241,7 +294,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int stid = tid;      // 0..127 among the softmax threads
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t r[32], r2[32];
-    uint32_t nq = 0, nt = 0;
+    uint32_t nq = 0, g = 0;  // items with tensor work / 64-column sub-steps processed so far
 
     for (uint32_t ns = 0;; ++ns) {
       const uint32_t slot = ns & 1;
@@ -268,122 +321,127 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int32_t* map = it.map;
       float m = -INFINITY, l = 0.f;
 
-      for (int j = 0; j < it.n_kv; ++j, ++nt) {
+      bool first_sub = true;
+      for (int j = 0; j < it.n_kv; ++j) {
         const int4 kt = it.kvt[j];
-        const int ncols = kt.y;
         const bool bitmask = (kt.w & KV_FLAG_BITMASK) != 0;
-        int lim = min(ncols - 1, row + kt.z);  // allowed columns of this row: c <= lim
-        // warp-uniform bounds of lim over the 32 rows of this warp: chunks at or below wlim_lo need no masking at
-        // all, chunks above wlim_hi hold no allowed column for any lane
-        int wlim_lo = min(ncols - 1, quarter * 32 + kt.z);
-        int wlim_hi = min(ncols - 1, quarter * 32 + 31 + kt.z);
         uint32_t bits[4] = {0, 0, 0, 0};
-        if (bitmask) {
-          lim = ncols - 1;
-          wlim_lo = -1;  // every chunk takes the masked path
-          wlim_hi = ncols - 1;
-          if (q0 + row < p.Lq) {
-            const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
-                                                            static_cast<long long>(q0 + row) * map[7] + (kt.x >> 5));
-            bits[0] = w.x, bits[1] = w.y, bits[2] = w.z, bits[3] = w.w;
-          }
+        if (bitmask && q0 + row < p.Lq) {
+          const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
+                                                          static_cast<long long>(q0 + row) * map[7] + (kt.x >> 5));
+          bits[0] = w.x, bits[1] = w.y, bits[2] = w.z, bits[3] = w.w;
         }
-        const int nchunks = (ncols + 31) >> 5;
-        mbar_wait(&s_full, nt & 1);
-        tc_fence_after();
+        const int nsub = kt.y > 64 ? 2 : 1;
+        for (int sub = 0; sub < nsub; ++sub, ++g) {
+          const int ncols = min(64, kt.y - sub * 64);  // valid columns of this 64-column sub-step
+          const int doff = kt.z - sub * 64;            // allowed: c <= r + doff (c relative to the sub-step)
+          int lim = min(ncols - 1, row + doff);
+          // warp-uniform bounds of lim over the 32 rows of this warp: chunks at or below wlim_lo need no masking at
+          // all, chunks above wlim_hi hold no allowed column for any lane
+          int wlim_lo = min(ncols - 1, quarter * 32 + doff);
+          int wlim_hi = min(ncols - 1, quarter * 32 + 31 + doff);
+          if (bitmask) {
+            lim = ncols - 1;
+            wlim_lo = -1;  // every chunk takes the masked path
+            wlim_hi = ncols - 1;
+          }
+          const int nchunks = (ncols + 31) >> 5;
+          const uint32_t tS = tmem_S + lane_addr + (g & 1) * 64;
+          mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+          tc_fence_after();
 
-        // Single pass over the scores: per 32-column chunk take the chunk maximum, keep the running reference
-        // maximum m unless it is exceeded by more than RESCALE_TAU, and write P = exp2(S*scale - m) straight back
-        // over the S columns already consumed.  When m does move, everything accumulated against the old reference
-        // — l, O, and the P chunks of this tile already written — is rescaled (rare after the first chunk).
-        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-        tmem_ld_32x32b_x32(tmem_S + lane_addr, r);
-        tmem_ld_wait();
+          // Single pass over the 64 scores of this sub-step: maximum over the allowed columns, keep the running
+          // reference maximum m unless it is exceeded by more than RESCALE_TAU (then l and O, accumulated against
+          // the old reference, are rescaled — rare), and write P = exp2(S*scale - m) as bf16 pairs over the first
+          // 32 columns of the same buffer.
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+          tmem_ld_32x32b_x32(tS, r);
+          if (nchunks > 1) tmem_ld_32x32b_x32(tS + 32, r2);
+          tmem_ld_wait();
+          float mxa = -INFINITY, mxb = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t* cur = (c & 1) ? r2 : r;
-          uint32_t* nxt = (c & 1) ? r : r2;
-          if (c < nchunks) {
-            const bool full_chunk = wlim_lo >= c * 32 + 31;
-            const bool empty_chunk = wlim_hi < c * 32;
-            const uint32_t bw = bitmask ? bits[c] : 0xffffffffu;
-            const int rel = lim - c * 32;  // columns i <= rel are allowed (masked chunks)
-            uint32_t pk[16];
-            if (!empty_chunk) {
-              float mx = -INFINITY;
-              if (full_chunk) {
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t* cur = c ? r2 : r;
+            if (c < nchunks && wlim_hi >= c * 32) {
+              if (wlim_lo >= c * 32 + 31) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) mx = fmax3(mx, __uint_as_float(cur[e]), __uint_as_float(cur[e + 1]));
+                for (int e = 0; e < 32; e += 4) {
+                  mxa = fmax3(mxa, __uint_as_float(cur[e]), __uint_as_float(cur[e + 1]));
+                  mxb = fmax3(mxb, __uint_as_float(cur[e + 2]), __uint_as_float(cur[e + 3]));
+                }
               } else {
+                const uint32_t bw = bitmask ? bits[sub * 2 + c] : 0xffffffffu;
+                const int rel = lim - c * 32;  // columns e <= rel are allowed
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
                   const bool ok = (e <= rel) && ((bw >> e) & 1u);
-                  mx = fmaxf(mx, ok ? __uint_as_float(cur[e]) : -INFINITY);
-                }
-              }
-              mx *= p.scale_log2;
-              const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf)
-              if (__any_sync(0xffffffffu, need)) {
-                const float alpha = need ? exp2f(m - mx) : 1.f;
-                if (need) m = mx;
-                l *= alpha;
-                l0 *= alpha, l1 *= alpha, l2 *= alpha, l3 *= alpha;
-                if (j > 0) {  // O holds P_0 V_0 .. P_{j-1} V_{j-1}, all retired (s_full commit)
-                  for (int oc = 0; oc < D / 32; ++oc) {
-                    tmem_ld_32x32b_x32(tmem_O + lane_addr + oc * 32, nxt);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) nxt[e] = __float_as_uint(__uint_as_float(nxt[e]) * alpha);
-                    tmem_st_32x32b_x32(tmem_O + lane_addr + oc * 32, nxt);
-                  }
-                }
-                for (int pc = 0; pc < c; ++pc) {  // P chunks of this tile written against the old reference
-                  tmem_ld_32x32b_x16(tmem_S + lane_addr + pc * 16, nxt);
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int e = 0; e < 16; ++e) {
-                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&nxt[e]));
-                    nxt[e] = pack_bf16x2(f.x * alpha, f.y * alpha);
-                  }
-                  tmem_st_32x32b_x16(tmem_S + lane_addr + pc * 16, nxt);
+                  mxa = fmaxf(mxa, ok ? __uint_as_float(cur[e]) : -INFINITY);
                 }
               }
             }
-            if (c + 1 < nchunks) tmem_ld_32x32b_x32(tmem_S + lane_addr + (c + 1) * 32, nxt);
-            const float neg_m = (m == -INFINITY) ? 0.f : -m;
-            if (empty_chunk) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) pk[e] = 0u;
-            } else if (full_chunk) {
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                const float p0 = exp2f(fmaf(__uint_as_float(cur[e]), p.scale_log2, neg_m));
-                const float p1 = exp2f(fmaf(__uint_as_float(cur[e + 1]), p.scale_log2, neg_m));
-                const float p2 = exp2f(fmaf(__uint_as_float(cur[e + 2]), p.scale_log2, neg_m));
-                const float p3 = exp2f(fmaf(__uint_as_float(cur[e + 3]), p.scale_log2, neg_m));
-                l0 += p0, l1 += p1, l2 += p2, l3 += p3;
-                pk[e >> 1] = pack_bf16x2(p0, p1);
-                pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 32; e += 2) {
-                const bool ok0 = (e <= rel) && ((bw >> e) & 1u);
-                const bool ok1 = (e + 1 <= rel) && ((bw >> (e + 1)) & 1u);
-                const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(cur[e]), p.scale_log2, neg_m)) : 0.f;
-                const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(cur[e + 1]), p.scale_log2, neg_m)) : 0.f;
-                l0 += p0, l1 += p1;
-                pk[e >> 1] = pack_bf16x2(p0, p1);
-              }
-            }
-            if (c + 1 < nchunks) tmem_ld_wait();  // S chunk c+1 is in registers before P chunk c lands on S columns
-            tmem_st_32x32b_x16(tmem_S + lane_addr + c * 16, pk);
           }
+          const float mx = fmaxf(mxa, mxb) * p.scale_log2;
+          const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf)
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? exp2f(m - mx) : 1.f;
+            if (need) m = mx;
+            l *= alpha;
+            if (!first_sub) {
+              // O holds the P.V of every earlier sub-step; the latest one may still be in flight
+              mbar_wait(&pv_done, (g - 1) & 1);
+              tc_fence_after();
+              uint32_t t[32];
+              for (int oc = 0; oc < D / 32; ++oc) {
+                tmem_ld_32x32b_x32(tmem_O + lane_addr + oc * 32, t);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) * alpha);
+                tmem_st_32x32b_x32(tmem_O + lane_addr + oc * 32, t);
+              }
+            }
+          }
+          const float neg_m = (m == -INFINITY) ? 0.f : -m;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t* cur = c ? r2 : r;
+            if (c < nchunks) {
+              uint32_t pk[16];
+              if (wlim_hi < c * 32) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pk[e] = 0u;
+              } else if (wlim_lo >= c * 32 + 31) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                  const float p0 = exp2f(fmaf(__uint_as_float(cur[e]), p.scale_log2, neg_m));
+                  const float p1 = exp2f(fmaf(__uint_as_float(cur[e + 1]), p.scale_log2, neg_m));
+                  const float p2 = exp2f(fmaf(__uint_as_float(cur[e + 2]), p.scale_log2, neg_m));
+                  const float p3 = exp2f(fmaf(__uint_as_float(cur[e + 3]), p.scale_log2, neg_m));
+                  l0 += p0, l1 += p1, l2 += p2, l3 += p3;
+                  pk[e >> 1] = pack_bf16x2(p0, p1);
+                  pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+                }
+              } else {
+                const uint32_t bw = bitmask ? bits[sub * 2 + c] : 0xffffffffu;
+                const int rel = lim - c * 32;
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                  const bool ok0 = (e <= rel) && ((bw >> e) & 1u);
+                  const bool ok1 = (e + 1 <= rel) && ((bw >> (e + 1)) & 1u);
+                  const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(cur[e]), p.scale_log2, neg_m)) : 0.f;
+                  const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(cur[e + 1]), p.scale_log2, neg_m)) : 0.f;
+                  l0 += p0, l1 += p1;
+                  pk[e >> 1] = pack_bf16x2(p0, p1);
+                }
+              }
+              tmem_st_32x32b_x16(tS + c * 16, pk);  // both S chunks are already in registers
+            }
+          }
+          l += (l0 + l1) + (l2 + l3);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&p_full[g & 1]);
+          first_sub = false;
         }
-        l += (l0 + l1) + (l2 + l3);
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full);
       }
 
       // ---- epilogue: O / l -> bf16 -> staging rows in the (now idle) V buffer -> one bulk copy per row ----

@@ -72,10 +72,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Same, but the thread may stay suspended for up to `ns` nanoseconds (it still wakes as soon as the phase
+// completes): keeps waiting warps from burning issue slots of the scheduler they share with working warps.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (clock64() - t0 > SDAG_SPIN_TRAP_CYCLES) {
       printf("sdag_b200: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
