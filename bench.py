@@ -228,9 +228,8 @@ def run_b200(args):
     attn_flops_per_launch = 4.0 * D * hdr["pairs"] * H * B  # algorithmic: 4*D*P*H per prompt per layer
 
     def step_resident(meta):
-        with torch.no_grad():
-            out = model(input_ids=ids_dev, use_cache=True, sdag_meta=meta, logits_to_keep=1)
-            return out.logits[:, -1, :].argmax(dim=-1)
+        logits, _ = sdag.prefill_forward(model, ids_dev, meta)
+        return logits.argmax(dim=-1)
 
     def step_e2e():
         toks, _ = sdag.prefill_batch(model, ids_host, layouts, device)
@@ -291,7 +290,8 @@ def run_b200(args):
             "prompts_per_step_per_gpu": B, "tokens_per_step": tokens_per_step, "layers": args.layers,
             "partition": "independent query batches per GPU, weights replicated, no collective",
             "cache": "inputs larger than L2 (16 GB of weights stream through every step)",
-            "linear_layers": "cuBLAS via torch (plain library GEMMs); attention, block map: this repo's kernels",
+            "linear_layers": "cuBLAS via torch (plain library GEMMs); attention, block map, RMSNorm / RoPE+KV write / "
+                             "SwiGLU glue: this repo's kernels (llama_runner.FusedPrefill)",
             "remeasured_for_clocks": remeasured,
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

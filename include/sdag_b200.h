@@ -155,6 +155,24 @@ int centroid_select(const float* retrieved, const int32_t* r_count, int R_max, c
  * int32 [n, k_neighbors] (-1 when fewer exist). */
 int doc_knn(const float* emb, int n, int d, int k_neighbors, int32_t* nbrs_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Path A4 — element-wise glue of the decoder layer around the attention call (the prefill forward
+ * generate_with_custom_mask drives, SDAG.py:175-176 -> HF LlamaDecoderLayer.forward,
+ * models/llama/modeling_llama.py).  bf16 tensors, HF module rounding order.
+ * ---------------------------------------------------------------------------------------------- */
+/* LlamaRMSNorm.forward; with `residual` != NULL first s = x + residual (written to sum_out), then
+ * out = weight * bf16(s * rsqrt(mean(s^2) + eps)).  rows x dim, dim % 8 == 0. */
+int llm_rmsnorm(const void* x, const void* residual, const void* weight, void* sum_out, void* out,
+                int64_t rows, int dim, float eps, void* stream);
+/* apply_rotary_pos_emb + KV-cache write: qkv [B*L, (H + 2*Hkv)*D] -> q_out [B,L,H,D], k_out / v_out
+ * [B,Hkv,S_cap,D] at positions pos0..pos0+L-1 (element strides kv_stride_b / kv_stride_h);
+ * cos / sin bf16 [L, D]. */
+int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out, void* k_out, void* v_out,
+                 int B, int L, int H, int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0,
+                 void* stream);
+/* LlamaMLP activation: gate_up [rows, 2*inter] (gate first) -> out [rows, inter] = silu(gate) * up. */
+int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,9 @@ SIGNATURES = {
     "topk_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "centroid_select": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "doc_knn": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "llm_rmsnorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "llm_rope_qkv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp]),
+    "llm_swiglu": (_i32, [_vp, _vp, _i64, _i32, _vp]),
 }
 
 _lib = None

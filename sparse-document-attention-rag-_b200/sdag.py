@@ -35,6 +35,7 @@ MAX_GEN_TOKENS_RAG = _config.MAX_GEN_TOKENS_RAG
 TEMPERATURE = _config.TEMPERATURE
 
 ATTN_NAME = "sdag_b200"
+USE_FUSED_PREFILL = True  # False forces the Hugging Face forward (+ attention hook) for the prefill
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -412,14 +413,30 @@ def _pick(logits: torch.Tensor) -> torch.Tensor:
     return torch.argmax(logits, dim=-1, keepdim=True)
 
 
+def prefill_forward(model, input_ids: torch.Tensor, blockmap: Optional[BlockMap]):
+    """Last-position logits ``[B, vocab]`` and the KV cache of a prompt batch under a block map (None = causal).
+
+    Llama-family bf16 models go through ``llama_runner.FusedPrefill`` (fused element-wise glue around the same
+    attention kernel); anything else through the Hugging Face forward with the ``sdag_b200`` attention hook."""
+    from .llama_runner import get_runner
+
+    prepare_model(model)
+    runner = get_runner(model) if USE_FUSED_PREFILL else None
+    with torch.no_grad():
+        if runner is not None:
+            bm = blockmap if blockmap is not None else causal_blockmap(input_ids.shape[1], input_ids.device)
+            return runner.prefill(input_ids, bm)
+        out = model(input_ids=input_ids, use_cache=True, sdag_meta=blockmap, logits_to_keep=1)
+        return out.logits[:, -1, :], out.past_key_values
+
+
 def _generate(model, tokenizer, input_ids: torch.Tensor, blockmap: BlockMap, max_new_tokens: int) -> str:
     prepare_model(model)
     eos = tokenizer.eos_token_id
     greedy = not (TEMPERATURE > 0)
     with torch.no_grad():
-        out = model(input_ids=input_ids, use_cache=True, sdag_meta=blockmap, logits_to_keep=1)
-        past = out.past_key_values
-        nxt = _pick(out.logits[:, -1, :])
+        logits, past = prefill_forward(model, input_ids, blockmap)
+        nxt = _pick(logits)
         new_tokens = [nxt]
         # One token comes from the prefill, up to max_new_tokens more from the loop; EOS is only tested inside
         # the loop (Appendix A7).  Greedy decoding keeps tokens on the device and polls for EOS every 16 steps;
@@ -529,10 +546,8 @@ def prefill_batch(model, input_ids_host: torch.Tensor, layouts: Sequence[SdagLay
     (pinned) host memory, one ``SdagLayout`` per prompt.  Copies the ids to the device, builds the block maps
     from the token offsets there, runs the SDAG prefill (last-position logits only) and returns
     ``(first_tokens_host [B] int64, past_key_values)``.  Greedy or sampled exactly like ``_pick``."""
-    prepare_model(model)
     ids = input_ids_host.to(device, non_blocking=True)
     bm = build_blockmap(layouts, device)
-    with torch.no_grad():
-        out = model(input_ids=ids, use_cache=True, sdag_meta=bm, logits_to_keep=1)
-        nxt = _pick(out.logits[:, -1, :])
-    return nxt[:, 0].cpu(), out.past_key_values
+    logits, past = prefill_forward(model, ids, bm)
+    nxt = _pick(logits)
+    return nxt[:, 0].cpu(), past
