@@ -97,13 +97,15 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* One decode step, dense over the cache (SDAG.py:193-197 passes no mask): q [B,H,D] (stride sq_b,
- * sq_h), k/v cache [B,Hkv,S_cap,D], kv_len valid positions, out [B,H,D] contiguous. */
+ * sq_h), k/v cache [B,Hkv,S_cap,D], kv_len valid positions, out [B,H,D] contiguous.  When kv_len_dev is
+ * not NULL the kernel reads the valid length from device memory (kv_len is then the upper bound used to
+ * size the grid), so a captured CUDA graph can be replayed for every generated token. */
 size_t sdag_decode_workspace_bytes(int B, int H, int D, int kv_len);
 int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h,
                     const void* k, int64_t sk_b, int64_t sk_h, int64_t sk_l,
                     const void* v, int64_t sv_b, int64_t sv_h, int64_t sv_l,
                     void* out, int B, int H, int Hkv, int kv_len, int D, float scaling,
-                    void* workspace, size_t workspace_bytes, void* stream);
+                    void* workspace, size_t workspace_bytes, const int32_t* kv_len_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Path B — exact max-inner-product top-k.  Replaces faiss IndexFlatIP.search as called by
@@ -166,10 +168,11 @@ int llm_rmsnorm(const void* x, const void* residual, const void* weight, void* s
                 int64_t rows, int dim, float eps, void* stream);
 /* apply_rotary_pos_emb + KV-cache write: qkv [B*L, (H + 2*Hkv)*D] -> q_out [B,L,H,D], k_out / v_out
  * [B,Hkv,S_cap,D] at positions pos0..pos0+L-1 (element strides kv_stride_b / kv_stride_h);
- * cos / sin bf16 [L, D]. */
+ * cos / sin: bf16 tables [>= pos0+L, D] indexed by absolute position.  pos0_dev != NULL: read pos0
+ * from device memory (CUDA-graph replay). */
 int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out, void* k_out, void* v_out,
                  int B, int L, int H, int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0,
-                 void* stream);
+                 const int32_t* pos0_dev, void* stream);
 /* LlamaMLP activation: gate_up [rows, 2*inter] (gate first) -> out [rows, inter] = silu(gate) * up. */
 int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* stream);
 

@@ -77,13 +77,15 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 }
 
 // qkv [T, (H + 2*Hkv) * D] (row = token t = b * L + l) -> q_out [B, L, H, D] (RoPE applied), k_out / v_out
-// [B, Hkv, S_cap, D] written at positions pos0 + l (RoPE on k).  cos / sin: bf16 [L, D] for positions pos0 .. pos0+L-1.
+// [B, Hkv, S_cap, D] written at positions pos0 + l (RoPE on k).  cos / sin: bf16 tables indexed by ABSOLUTE position
+// (row pos0 + l).  pos0 may come from device memory (pos0_dev) so a captured CUDA graph can be replayed per token.
 // One thread per 8 consecutive elements of the first half of a head; it also owns the partner elements d + D/2.
 __global__ void __launch_bounds__(256)
 rope_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ cosb,
                 const __nv_bfloat16* __restrict__ sinb, __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_out,
                 __nv_bfloat16* __restrict__ v_out, int B, int L, int H, int Hkv, int D, long long kv_stride_b,
-                long long kv_stride_h, int pos0) {
+                long long kv_stride_h, int pos0_host, const int32_t* __restrict__ pos0_dev) {
+  const int pos0 = pos0_dev ? *pos0_dev : pos0_host;
   const int heads = H + 2 * Hkv;
   const int vec_per_head = D / 16;  // threads per head (each handles 8 + 8 elements)
   const long long total = static_cast<long long>(B) * L * heads * vec_per_head;
@@ -111,10 +113,10 @@ rope_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     float a[8], c[8], cl[8], ch[8], sl[8], sh[8];
     unpack8(lo, a);
     unpack8(hi, c);
-    unpack8(reinterpret_cast<const uint4*>(cosb + static_cast<long long>(l) * D)[vh], cl);
-    unpack8(reinterpret_cast<const uint4*>(cosb + static_cast<long long>(l) * D + D / 2)[vh], ch);
-    unpack8(reinterpret_cast<const uint4*>(sinb + static_cast<long long>(l) * D)[vh], sl);
-    unpack8(reinterpret_cast<const uint4*>(sinb + static_cast<long long>(l) * D + D / 2)[vh], sh);
+    unpack8(reinterpret_cast<const uint4*>(cosb + static_cast<long long>(pos0 + l) * D)[vh], cl);
+    unpack8(reinterpret_cast<const uint4*>(cosb + static_cast<long long>(pos0 + l) * D + D / 2)[vh], ch);
+    unpack8(reinterpret_cast<const uint4*>(sinb + static_cast<long long>(pos0 + l) * D)[vh], sl);
+    unpack8(reinterpret_cast<const uint4*>(sinb + static_cast<long long>(pos0 + l) * D + D / 2)[vh], sh);
     float o1[8], o2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -170,7 +172,8 @@ int llm_rmsnorm(const void* x, const void* residual, const void* weight, void* s
 }
 
 int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out, void* k_out, void* v_out, int B, int L,
-                 int H, int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0, void* stream) {
+                 int H, int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0, const int32_t* pos0_dev,
+                 void* stream) {
   if (!qkv || !cos || !sin || !q_out || !k_out || !v_out) return SDAG_ERR_INVALID;
   if (B <= 0 || L <= 0 || H <= 0 || Hkv <= 0 || D <= 0 || (D % 16) || pos0 < 0) return SDAG_ERR_INVALID;
   const long long total = static_cast<long long>(B) * L * (H + 2 * Hkv) * (D / 16);
@@ -179,7 +182,7 @@ int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out,
   rope_qkv_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(cos), static_cast<const __nv_bfloat16*>(sin),
       static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(k_out), static_cast<__nv_bfloat16*>(v_out), B, L, H, Hkv,
-      D, kv_stride_b, kv_stride_h, pos0);
+      D, kv_stride_b, kv_stride_h, pos0, pos0_dev);
   return static_cast<int>(cudaGetLastError());
 }
 

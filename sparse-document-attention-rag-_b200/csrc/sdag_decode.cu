@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(THREADS)
 decode_split_kernel(const __nv_bfloat16* __restrict__ q, long long sq_b, long long sq_h,
                     const __nv_bfloat16* __restrict__ k, long long sk_b, long long sk_h, long long sk_l,
                     const __nv_bfloat16* __restrict__ v, long long sv_b, long long sv_h, long long sv_l,
-                    float* __restrict__ partial, int H, int Hkv, int kv_len, int rows_per_split, float scale_log2) {
+                    float* __restrict__ partial, int H, int Hkv, int kv_len_host, int rows_per_split, float scale_log2,
+                    const int32_t* __restrict__ kv_len_dev) {
+  const int kv_len = kv_len_dev ? *kv_len_dev : kv_len_host;  // device value: CUDA-graph replay per token
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* tiles = smem;
   float* sp = reinterpret_cast<float*>(smem + DecodeSmem<D>::kTiles);          // [MAX_CHUNK][MAX_G]
@@ -244,7 +246,7 @@ size_t sdag_decode_workspace_bytes(int B, int H, int D, int kv_len) {
 
 int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h, const void* k, int64_t sk_b, int64_t sk_h, int64_t sk_l,
                     const void* v, int64_t sv_b, int64_t sv_h, int64_t sv_l, void* out, int B, int H, int Hkv, int kv_len,
-                    int D, float scaling, void* workspace, size_t workspace_bytes, void* stream) {
+                    int D, float scaling, void* workspace, size_t workspace_bytes, const int32_t* kv_len_dev, void* stream) {
   if (!q || !k || !v || !out || !workspace) return SDAG_ERR_INVALID;
   if (B <= 0 || H <= 0 || Hkv <= 0 || kv_len <= 0 || H % Hkv) return SDAG_ERR_INVALID;
   if (D != 64 && D != 128) return SDAG_ERR_UNSUPPORTED;
@@ -270,7 +272,7 @@ int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h, const void* k, in
       cfg = true;
     }
     decode_split_kernel<128><<<grid, THREADS, DecodeSmem<128>::kTotal, st>>>(qq, sq_b, sq_h, kk, sk_b, sk_h, sk_l, vv, sv_b,
-                                                                             sv_h, sv_l, part, H, Hkv, kv_len, rows, sl2);
+                                                                             sv_h, sv_l, part, H, Hkv, kv_len, rows, sl2, kv_len_dev);
     SDAG_CUDA_TRY(cudaGetLastError());
     decode_merge_kernel<128><<<dim3(H, B), 128, 0, st>>>(part, static_cast<__nv_bfloat16*>(out), H, Hkv, nsplit);
   } else {
@@ -281,7 +283,7 @@ int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h, const void* k, in
       cfg = true;
     }
     decode_split_kernel<64><<<grid, THREADS, DecodeSmem<64>::kTotal, st>>>(qq, sq_b, sq_h, kk, sk_b, sk_h, sk_l, vv, sv_b,
-                                                                           sv_h, sv_l, part, H, Hkv, kv_len, rows, sl2);
+                                                                           sv_h, sv_l, part, H, Hkv, kv_len, rows, sl2, kv_len_dev);
     SDAG_CUDA_TRY(cudaGetLastError());
     decode_merge_kernel<64><<<dim3(H, B), 64, 0, st>>>(part, static_cast<__nv_bfloat16*>(out), H, Hkv, nsplit);
   }

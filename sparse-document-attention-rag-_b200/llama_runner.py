@@ -84,9 +84,19 @@ class FusedPrefill:
         except Exception:
             return None
 
+    def rope_tables(self, n_pos: int, device):
+        """bf16 cos / sin tables ``[n_pos, D]`` indexed by absolute position (HF rotary module, rounded like HF does)."""
+        inner = self.model.model
+        dummy = torch.empty((1, 1, self.hidden), dtype=torch.bfloat16, device=device)
+        cos, sin = inner.rotary_emb(dummy, torch.arange(n_pos, device=device).unsqueeze(0))
+        return cos[0].contiguous(), sin[0].contiguous()
+
     @torch.no_grad()
-    def prefill(self, input_ids: torch.Tensor, blockmap, want_cache: bool = True):
-        """input_ids int64 [B, L] on the model's device -> (last-position logits [B, vocab], DynamicCache | None)."""
+    def prefill(self, input_ids: torch.Tensor, blockmap, want_cache: bool = True, kv=None):
+        """input_ids int64 [B, L] on the model's device -> (last-position logits [B, vocab], DynamicCache | None).
+
+        ``kv = (k_cache, v_cache, cos, sin)`` with caches ``[n_layers, B, Hkv, S_cap, D]`` makes the prefill write K/V
+        straight into a preallocated cache (the decode engine's) instead of building a ``DynamicCache``."""
         from . import sdag  # late import (sdag imports this module lazily too)
 
         lib = _lib.load()
@@ -97,13 +107,14 @@ class FusedPrefill:
         H, Hkv, D = self.H, self.Hkv, self.D
         stream = _lib.stream_ptr(dev)
         h = inner.embed_tokens(input_ids)
-        pos = torch.arange(L, device=dev).unsqueeze(0)
-        cos, sin = inner.rotary_emb(h, pos)  # [1, L, D] in the model dtype
-        cos, sin = cos[0].contiguous(), sin[0].contiguous()
+        if kv is not None:
+            kc_all, vc_all, cos, sin = kv
+        else:
+            cos, sin = self.rope_tables(L, dev)
         resid = h.view(T, self.hidden)
         _, normed = _rmsnorm(resid, None, self.layers[0]["w_in"], self.layers[0]["eps_in"])
         cache = None
-        if want_cache:
+        if want_cache and kv is None:
             from transformers import DynamicCache
 
             cache = DynamicCache(config=model.config) if _accepts_config(DynamicCache) else DynamicCache()
@@ -112,11 +123,16 @@ class FusedPrefill:
         for i, ly in enumerate(self.layers):
             qkv = F.linear(normed, ly["wqkv"], ly["bqkv"])
             q = torch.empty((B, L, H, D), dtype=torch.bfloat16, device=dev)
-            k = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
-            v = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
+            if kv is not None:
+                kbuf, vbuf = kc_all[i], vc_all[i]
+                k, v = kbuf[:, :, :L], vbuf[:, :, :L]
+            else:
+                kbuf = k = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
+                vbuf = v = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
             _lib.count_launches(1)
-            _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(),
-                                        B, L, H, Hkv, D, k.stride(0), k.stride(1), 0, stream), "llm_rope_qkv")
+            _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kbuf.data_ptr(),
+                                        vbuf.data_ptr(), B, L, H, Hkv, D, kbuf.stride(0), kbuf.stride(1), 0, 0, stream),
+                       "llm_rope_qkv")
             del qkv
             if cache is not None:
                 cache.update(k, v, i)
@@ -125,21 +141,140 @@ class FusedPrefill:
             last = i == n_layers - 1
             if last:  # only the last position of each prompt is read after the final layer
                 attn, resid = attn[last_rows], resid[last_rows]
-            o = F.linear(attn, ly["wo"], ly["bo"])
-            resid, normed = _rmsnorm(o, resid, ly["w_post"], ly["eps_post"])
-            gu = F.linear(normed, ly["wgu"])
-            act = torch.empty((gu.shape[0], self.inter), dtype=torch.bfloat16, device=dev)
-            _lib.count_launches(1)
-            _lib.check(lib.llm_swiglu(gu.data_ptr(), act.data_ptr(), gu.shape[0], self.inter, stream), "llm_swiglu")
-            del gu
-            d = F.linear(act, ly["wdown"])
-            if not last:
-                nxt = self.layers[i + 1]
-                resid, normed = _rmsnorm(d, resid, nxt["w_in"], nxt["eps_in"])
-            else:
-                _, normed = _rmsnorm(d, resid, inner.norm.weight, inner.norm.variance_epsilon)
+            normed, resid = self._mlp_block(attn, resid, i)
         logits = model.lm_head(normed)
         return logits, cache
+
+    def _mlp_block(self, attn_rows, resid, i):
+        """o_proj + residual + post-norm + SwiGLU MLP + residual + the next layer's (or the final) norm."""
+        lib = _lib.load()
+        ly = self.layers[i]
+        inner = self.model.model
+        o = F.linear(attn_rows, ly["wo"], ly["bo"])
+        resid, normed = _rmsnorm(o, resid, ly["w_post"], ly["eps_post"])
+        gu = F.linear(normed, ly["wgu"])
+        act = torch.empty((gu.shape[0], self.inter), dtype=torch.bfloat16, device=gu.device)
+        _lib.count_launches(1)
+        _lib.check(lib.llm_swiglu(gu.data_ptr(), act.data_ptr(), gu.shape[0], self.inter, _lib.stream_ptr(gu.device)), "llm_swiglu")
+        d = F.linear(act, ly["wdown"])
+        if i + 1 < len(self.layers):
+            nxt = self.layers[i + 1]
+            resid, normed = _rmsnorm(d, resid, nxt["w_in"], nxt["eps_in"])
+        else:
+            resid, normed = _rmsnorm(d, resid, inner.norm.weight, inner.norm.variance_epsilon)
+        return normed, resid
+
+    # ------------------------------------------------------------------------------------------------
+    # generation: prefill into a preallocated cache, then a CUDA-graph-captured decode step replayed per token
+    # ------------------------------------------------------------------------------------------------
+    def _decode_context(self, B: int, need_cap: int, temperature: float, dev, use_graph: bool):
+        """Preallocated KV cache + device-side step state + captured decode graph, cached per (batch, capacity bucket,
+        sampling mode).  Capturing costs a few hundred ms, so it is done once per bucket and replayed across calls."""
+        from . import sdag
+
+        lib = _lib.load()
+        S_cap = max(2048, (need_cap + 2047) // 2048 * 2048)
+        key = (B, S_cap, temperature > 0, use_graph, str(dev))
+        ctxs = self.__dict__.setdefault("_ctx", {})
+        ctx = ctxs.get(key)
+        if ctx is not None:
+            return ctx
+        if len(ctxs) >= 2:  # keep HBM bounded: drop the oldest context
+            ctxs.pop(next(iter(ctxs)))
+            torch.cuda.empty_cache()
+        model, inner = self.model, self.model.model
+        H, Hkv, D = self.H, self.Hkv, self.D
+        n_layers = len(self.layers)
+        c = dict(S_cap=S_cap)
+        c["kc"] = torch.zeros((n_layers, B, Hkv, S_cap, D), dtype=torch.bfloat16, device=dev)
+        c["vc"] = torch.zeros_like(c["kc"])
+        c["cos"], c["sin"] = self.rope_tables(S_cap, dev)
+        c["gen"] = torch.zeros((B, S_cap), dtype=torch.int64, device=dev)
+        c["tok"] = torch.zeros((B, 1), dtype=torch.int64, device=dev)
+        c["pos"] = torch.zeros((1,), dtype=torch.int32, device=dev)    # position of the token being fed
+        c["len"] = torch.ones((1,), dtype=torch.int32, device=dev)     # cache length once its K/V are written
+        c["slot"] = torch.ones((B, 1), dtype=torch.int64, device=dev)  # output column
+        c["temp"] = torch.ones((1,), dtype=torch.float32, device=dev)
+        q = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=dev)
+        attn_out = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=dev)
+        kc, vc, cos, sin = c["kc"], c["vc"], c["cos"], c["sin"]
+        sample = temperature > 0
+
+        def step():
+            h = inner.embed_tokens(c["tok"]).view(B, self.hidden)
+            resid = h
+            _, normed = _rmsnorm(resid, None, self.layers[0]["w_in"], self.layers[0]["eps_in"])
+            for i, ly in enumerate(self.layers):
+                qkv = F.linear(normed, ly["wqkv"], ly["bqkv"])
+                _lib.count_launches(1)
+                _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kc[i].data_ptr(),
+                                            vc[i].data_ptr(), B, 1, H, Hkv, D, kc[i].stride(0), kc[i].stride(1), 0,
+                                            c["pos"].data_ptr(), _lib.stream_ptr(dev)), "llm_rope_qkv")
+                sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out)
+                normed, resid = self._mlp_block(attn_out.view(B, H * D), resid, i)
+            lg = model.lm_head(normed)
+            if sample:
+                nxt = torch.multinomial(torch.softmax(lg.float() / c["temp"], dim=-1), num_samples=1)
+            else:
+                nxt = torch.argmax(lg, dim=-1, keepdim=True)
+            c["gen"].scatter_(1, c["slot"], nxt)
+            c["tok"].copy_(nxt)
+            c["pos"].add_(1)
+            c["len"].add_(1)
+            c["slot"].add_(1)
+
+        c["step"] = step
+        c["graph"] = None
+        if use_graph:
+            try:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    step()  # warm-up outside capture: workspaces, cuBLAS handles
+                torch.cuda.current_stream(dev).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    step()
+                c["graph"] = graph
+            except Exception:
+                c["graph"] = None
+                torch.cuda.synchronize(dev)
+        ctxs[key] = c
+        return c
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor, blockmap, max_new_tokens: int, eos_token_id, temperature: float = 0.0,
+                 use_graph: bool = True, poll_every: int = 16) -> torch.Tensor:
+        """New token ids ``[B, <= max_new_tokens + 1]`` (one from the prefill, the rest from the decode loop —
+        SDAG.py:181-211; trimming at EOS is the caller's job).  The decode step (fused glue, split-KV decode
+        attention over the preallocated cache, cuBLAS GEMMs, token pick) is captured once into a CUDA graph; position,
+        cache length and output slot live in device memory and advance inside the graph, so the host only replays."""
+        B, L = input_ids.shape
+        dev = input_ids.device
+        c = self._decode_context(B, L + max_new_tokens + 1, temperature, dev, use_graph)
+        logits, _ = self.prefill(input_ids, blockmap, want_cache=False, kv=(c["kc"], c["vc"], c["cos"], c["sin"]))
+        if temperature > 0:
+            c["temp"].fill_(temperature)
+            tok = torch.multinomial(torch.softmax(logits.float() / temperature, dim=-1), num_samples=1)
+        else:
+            tok = torch.argmax(logits, dim=-1, keepdim=True)
+        c["gen"][:, 0:1] = tok
+        c["tok"].copy_(tok)
+        c["pos"].fill_(L)
+        c["len"].fill_(L + 1)
+        c["slot"].fill_(1)
+        done = 0
+        while done < max_new_tokens:
+            n = min(poll_every, max_new_tokens - done)
+            for _ in range(n):
+                if c["graph"] is not None:
+                    c["graph"].replay()
+                else:
+                    c["step"]()
+            done += n
+            if eos_token_id is not None and bool((c["gen"][:, 1 : done + 1] == eos_token_id).any(dim=1).all()):
+                break
+        return c["gen"][:, : done + 1].clone()
 
 
 def _accepts_config(cls) -> bool:

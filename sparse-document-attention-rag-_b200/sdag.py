@@ -333,8 +333,11 @@ def compute_doc_knn_for_docs(ranker, docs: List[str], k_neighbors: int, device="
 # ------------------------------------------------------------------------------------------------------
 # Hugging Face attention hook
 # ------------------------------------------------------------------------------------------------------
-def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling: Optional[float] = None) -> torch.Tensor:
-    """One decode step, dense over the cache: q ``[B,H,1,D]``, k/v ``[B,Hkv,S,D]`` bf16 -> ``[B,1,H,D]``."""
+def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling: Optional[float] = None,
+                          kv_len_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One decode step, dense over the cache: q ``[B,H,1,D]``, k/v ``[B,Hkv,S,D]`` bf16 -> ``[B,1,H,D]``.
+    ``kv_len_dev`` (int32 device scalar) makes the valid cache length a device-side value (``S`` is then the bound
+    the grid is sized for) so the call can sit inside a CUDA graph that is replayed per token."""
     lib = _lib.load()
     B, H, _, D = q.shape
     Hkv, S = k.shape[1], k.shape[2]
@@ -342,7 +345,8 @@ def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sca
     if q2.stride(-1) != 1:
         q2 = q2.contiguous()
     k, v = _unit_inner(k), _unit_inner(v)
-    out = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=q.device)
+    if out is None:
+        out = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=q.device)
     ws_bytes = int(lib.sdag_decode_workspace_bytes(B, H, D, S))
     ws = _workspace(q.device, ws_bytes)
     scaling = float(D ** -0.5 if scaling is None else scaling)
@@ -351,7 +355,8 @@ def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sca
         lib.sdag_decode_fwd(q2.data_ptr(), q2.stride(0), q2.stride(1),
                             k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
                             v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
-                            out.data_ptr(), B, H, Hkv, S, D, scaling, ws.data_ptr(), ws.numel(), _lib.stream_ptr(q.device)),
+                            out.data_ptr(), B, H, Hkv, S, D, scaling, ws.data_ptr(), ws.numel(), _lib.ptr(kv_len_dev),
+                            _lib.stream_ptr(q.device)),
         "sdag_decode_fwd",
     )
     return out
@@ -434,6 +439,14 @@ def _generate(model, tokenizer, input_ids: torch.Tensor, blockmap: BlockMap, max
     prepare_model(model)
     eos = tokenizer.eos_token_id
     greedy = not (TEMPERATURE > 0)
+    from .llama_runner import get_runner
+
+    runner = get_runner(model) if (USE_FUSED_PREFILL and greedy) else None
+    if runner is not None:
+        # Llama-family bf16 model, greedy: fused prefill into a preallocated cache + CUDA-graph decode loop.
+        # (Sampling keeps the reference's per-token loop below so the global torch RNG is consumed identically.)
+        ids = runner.generate(input_ids, blockmap, max_new_tokens, eos, temperature=0.0)[0].tolist()
+        return tokenizer.decode(_trim_at_eos(ids, eos), skip_special_tokens=True).strip()
     with torch.no_grad():
         logits, past = prefill_forward(model, input_ids, blockmap)
         nxt = _pick(logits)
@@ -452,12 +465,17 @@ def _generate(model, tokenizer, input_ids: torch.Tensor, blockmap: BlockMap, max
             elif eos is not None and (step % 16 == 15) and bool((torch.cat(new_tokens[1:], dim=1) == eos).any()):
                 break
     ids = torch.cat(new_tokens, dim=1)[0].tolist()
+    return tokenizer.decode(_trim_at_eos(ids, eos), skip_special_tokens=True).strip()
+
+
+def _trim_at_eos(ids: List[int], eos) -> List[int]:
+    """Cut after the first EOS produced inside the decode loop; the prefill token (index 0) never stops generation
+    (SURVEY.md Appendix A7)."""
     if eos is not None:
         for pos in range(1, len(ids)):
             if ids[pos] == eos:
-                ids = ids[: pos + 1]
-                break
-    return tokenizer.decode(ids, skip_special_tokens=True).strip()
+                return ids[: pos + 1]
+    return ids
 
 
 def generate_with_custom_mask(model, tokenizer, input_ids: torch.Tensor, prompt_mask: torch.Tensor,
