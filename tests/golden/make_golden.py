@@ -14,7 +14,7 @@ that are not installable here are replaced by stubs *before* import:
   (so the search arithmetic itself stays "parity unpinned", see oracle/__init__.py).
 
 Outputs (all small): masks.npz, attention.npz, generation.json, knn.json, selector.json, retrieval.json,
-ranked_list.json.
+ranked_list.json, pipeline.json.
 """
 from __future__ import annotations
 
@@ -231,6 +231,45 @@ def gen_retrieval():
         json.dump(dict(corpus=corpus, meta=meta, records=recs), f, indent=1)
 
 
+def gen_pipeline():
+    """The reference's own functions chained the way main.py:764-796 + 467-496 chains them (config-1 shape in
+    miniature): retrieve_batch -> select_malicious_docs_for_batch -> pool = first k+1 -> run_rag_with_doc_isolation
+    per query, greedy, on the tiny fp32 Llama.  The retriever's index is the oracle (faiss is not installable)."""
+    ref_sdag.TEMPERATURE = 0
+    tok = synth.make_tokenizer()
+    model = synth.tiny_llama(len(tok))
+    ranker = synth.HashRanker()
+    rng = random.Random(42)
+    topics = ["rivers", "volcanoes", "composers", "planets", "bridges", "vaccines", "dynasties", "alloys"]
+    corpus = [f"Passage {i}: notes on {topics[i % 8]} number {i}, with detail {rng.randint(0, 999)}." for i in range(300)]
+    meta = [dict(id=f"d{i}", text=t) for i, t in enumerate(corpus)]
+    emb = np.stack([synth.text_embedding("passage: " + t) for t in corpus])
+    index = FlatIPOracle(emb.shape[1])
+    index.add(emb)
+    retr = ref_dense.DenseRetriever(ranker, index, meta)
+    queries = [f"What is known about {t}?" for t in topics[:6]]
+    cands = [[f"Fabricated claim {j} about {t}: the answer is {j * 7}." for j in range(5)] for t in topics[:6]]
+    top_k, strategy, max_docs, rank, nbr_k = 5, "closest_to_centroid", 1, 1, 0
+    rb = retr.retrieve_batch(queries, max_k_needed=top_k + 1, embed_batch_size=32)
+    chosen = ref_sel.select_malicious_docs_for_batch(ranker, rb.docs_texts_full, cands, strategy, max_docs)
+    answers, token_ids = [], []
+    orig_decode = tok.decode
+    for q, docs, mal in zip(queries, rb.docs_texts_full, chosen):
+        seen = {}
+        tok.decode = lambda ids, _s=seen, **kw: (_s.__setitem__("ids", [int(x) for x in ids]), orig_decode(ids, **kw))[1]
+        ans = ref_sdag.run_rag_with_doc_isolation(model=model, tokenizer=tok, query=q, malicious_docs=mal,
+                                                  retrieved_docs=docs[: top_k + 1], max_new_tokens=5, device="cpu",
+                                                  add_attack_in_rank=rank, ranker=ranker, doc_neighbors_k=nbr_k)
+        tok.decode = orig_decode
+        answers.append(ans)
+        token_ids.append(seen["ids"])
+    with open(os.path.join(HERE, "pipeline.json"), "w") as f:
+        json.dump(dict(corpus=corpus, queries=queries, candidates=cands, top_k=top_k, strategy=strategy, max_docs=max_docs,
+                       rank=rank, doc_neighbors_k=nbr_k, ids_full=rb.ids_full, chosen=chosen, answers=answers,
+                       token_ids=token_ids), f, indent=1)
+    print("pipeline:", token_ids)
+
+
 def gen_ranked_list():
     base = ["a", "b", "c", "d"]
     recs = []
@@ -252,4 +291,5 @@ if __name__ == "__main__":
     gen_selector()
     gen_retrieval()
     gen_ranked_list()
+    gen_pipeline()
     print("golden fixtures written to", HERE)

@@ -1,0 +1,82 @@
+"""End-to-end drop-in check (BASELINE config 1 / 4 in miniature): the three replaced entry points chained the way the
+reference's main.py chains them — retrieve_batch -> select_malicious_docs_for_batch -> run_rag_with_doc_isolation —
+against tests/golden/pipeline.json, produced by chaining the reference's own functions on the same inputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_chained_pipeline_matches_reference_golden(golden_dir):
+    import sdag_b200.sdag as sdag
+    from sdag_b200.retrieval import DenseRetriever, FlatIPIndex
+    from sdag_b200.selection import select_malicious_docs_for_batch
+
+    with open(os.path.join(golden_dir, "pipeline.json")) as f:
+        g = json.load(f)
+    sdag.TEMPERATURE = 0
+    tok = synth.make_tokenizer()
+    model = synth.tiny_llama(len(tok)).cuda()
+    ranker = synth.HashRanker()
+    meta = [dict(id=f"d{i}", text=t) for i, t in enumerate(g["corpus"])]
+    emb = np.stack([synth.text_embedding("passage: " + t) for t in g["corpus"]])
+    index = FlatIPIndex(emb.shape[1])
+    index.add(emb)
+    retr = DenseRetriever(ranker, index, meta)
+    k = g["top_k"]
+    rb = retr.retrieve_batch(g["queries"], max_k_needed=k + 1, embed_batch_size=32)
+    assert rb.ids_full == g["ids_full"]
+    chosen = select_malicious_docs_for_batch(ranker, rb.docs_texts_full, g["candidates"], g["strategy"], g["max_docs"])
+    assert chosen == g["chosen"]
+    exact = 0
+    orig = tok.decode
+    for q, docs, mal, want_ids, want_ans in zip(g["queries"], rb.docs_texts_full, chosen, g["token_ids"], g["answers"]):
+        seen = {}
+        tok.decode = lambda ids, _s=seen, **kw: (_s.__setitem__("ids", [int(x) for x in ids]), orig(ids, **kw))[1]
+        ans = sdag.run_rag_with_doc_isolation(model=model, tokenizer=tok, query=q, malicious_docs=mal, retrieved_docs=docs[: k + 1],
+                                              max_new_tokens=5, device="cuda", add_attack_in_rank=g["rank"], ranker=ranker,
+                                              doc_neighbors_k=g["doc_neighbors_k"])
+        tok.decode = orig
+        assert seen["ids"][0] == want_ids[0]  # the prefill token must always agree
+        if seen["ids"] == want_ids:
+            assert ans == want_ans
+            exact += 1
+    # fp32 reference on CPU vs bf16 attention on the GPU: a chaotic random-init model may flip a late near-tie
+    assert exact >= len(g["queries"]) - 1, exact
+
+
+def test_qwen2_geometry_runs_through_fused_engine():
+    """Qwen2.5-0.5B head geometry (14 q heads / 2 kv heads, head_dim 64, qkv biases) in miniature: fused runner vs
+    the HF forward with the attention hook."""
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+
+    import sdag_b200.sdag as sdag
+    from sdag_b200.llama_runner import get_runner
+
+    cfg = Qwen2Config(vocab_size=300, hidden_size=896, intermediate_size=512, num_hidden_layers=2, num_attention_heads=14,
+                      num_key_value_heads=2, max_position_embeddings=4096, tie_word_embeddings=True)
+    torch.manual_seed(1)
+    model = Qwen2ForCausalLM(cfg).to(torch.bfloat16).cuda().eval()
+    sdag.prepare_model(model)
+    assert get_runner(model) is not None
+    from oracle.sdag_mask import synthetic_layout
+
+    L, S, spans, qa = synthetic_layout(20, 3, 70, 2, 11)
+    ids = torch.randint(0, 300, (2, L), generator=torch.Generator().manual_seed(3)).cuda()
+    bm = sdag.build_blockmap([sdag.SdagLayout(L, S, spans, qa, [[1], [2, 0], []])])
+    sdag.USE_FUSED_PREFILL = False
+    try:
+        ref, _ = sdag.prefill_forward(model, ids, bm)
+    finally:
+        sdag.USE_FUSED_PREFILL = True
+    got, _ = sdag.prefill_forward(model, ids, bm)
+    torch.testing.assert_close(got.float(), ref.float(), atol=0.06, rtol=0.05)
+    assert torch.equal(got.argmax(-1), ref.argmax(-1))
+    out = get_runner(model).generate(ids, bm, 12, None)
+    assert out.shape == (2, 13)
