@@ -65,6 +65,7 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
 
 struct Item {
   int q0, nrows, n_kv, h, b, hkv;
+  int pack, R;  // GQA packing: `pack` query heads of one kv group share the tile, R = 128 / pack rows each
   const int4* kvt;
   const int32_t* map;
   bool valid;
@@ -84,10 +85,20 @@ __device__ __forceinline__ Item fetch_item(const PrefillParams& p, long long i) 
   it.valid = t < it.map[0] && it.map[2] == 0;
   it.q0 = it.nrows = it.n_kv = 0;
   it.kvt = nullptr;
+  it.pack = 1, it.R = BM;
   if (it.valid) {
     const int4 qt = reinterpret_cast<const int4*>(it.map + SDAG_BLOCKMAP_HEADER)[t];
     it.q0 = qt.x, it.nrows = qt.y, it.n_kv = qt.w;
     it.kvt = reinterpret_cast<const int4*>(it.map + SDAG_BLOCKMAP_HEADER) + it.map[5] + qt.z;
+    // Short query tiles (question block, system block): stack 4 or 2 query heads of the same kv group into the
+    // 128-row MMA tile — K/V tiles are shared by the group, so one pass serves all of them.
+    const int G = p.H / p.Hkv;
+    if (it.n_kv > 0) {
+      if (it.nrows <= 32 && (G % 4) == 0) it.pack = 4;
+      else if (it.nrows <= 64 && (G % 2) == 0) it.pack = 2;
+    }
+    it.R = BM / it.pack;
+    if (it.h % it.pack) it.valid = false;  // handled by the item of the group's first head
   }
   return it;
 }
@@ -101,7 +112,8 @@ __device__ __forceinline__ Item fetch_item(const PrefillParams& p, long long i) 
 // producer, warp 5 = MMA issuer (+ TMEM allocation), warps 6-7 idle; the second warpgroup shrinks to 56 registers.
 template <int D>
 __global__ void __launch_bounds__(256, 2)
-sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ64,
+                    const __grid_constant__ CUtensorMap tmQ32, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const PrefillParams p, const long long n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -136,6 +148,8 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmQ64);
+    tma_prefetch_desc(&tmQ32);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
@@ -172,7 +186,14 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (!it.valid || it.n_kv == 0) continue;
         mbar_wait(&q_empty, (nq & 1) ^ 1);
         mbar_expect_tx(&q_full, Smem<D>::kQ);
-        for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sQ + dh * BM * 128, &tmQ, &q_full, dh * 64, it.q0, it.h, it.b);
+        if (it.pack == 1) {
+          for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sQ + dh * BM * 128, &tmQ, &q_full, dh * 64, it.q0, it.h, it.b);
+        } else {
+          const CUtensorMap* tm = it.pack == 2 ? &tmQ64 : &tmQ32;
+          for (int g = 0; g < it.pack; ++g)
+            for (int dh = 0; dh < D / 64; ++dh)
+              tma_load_4d(sQ + dh * BM * 128 + g * it.R * 128, tm, &q_full, dh * 64, it.q0, it.h + g, it.b);
+        }
         for (int j = 0; j < it.n_kv; ++j) {
           const int k0 = it.kvt[j].x;
           mbar_wait(&k_empty, (nk & 1) ^ 1);
@@ -320,26 +341,30 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int q0 = it.q0;
       const int32_t* map = it.map;
       float m = -INFINITY, l = 0.f;
+      // with GQA packing the tile row splits into (head within the group, row within the query tile)
+      const int rr = row & (it.R - 1);
+      const int head = it.h + row / it.R;
+      const int wrow0 = (quarter * 32) & (it.R - 1);  // first query-tile row handled by this warp
 
       bool first_sub = true;
       for (int j = 0; j < it.n_kv; ++j) {
         const int4 kt = it.kvt[j];
         const bool bitmask = (kt.w & KV_FLAG_BITMASK) != 0;
         uint32_t bits[4] = {0, 0, 0, 0};
-        if (bitmask && q0 + row < p.Lq) {
+        if (bitmask && q0 + rr < p.Lq) {
           const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
-                                                          static_cast<long long>(q0 + row) * map[7] + (kt.x >> 5));
+                                                          static_cast<long long>(q0 + rr) * map[7] + (kt.x >> 5));
           bits[0] = w.x, bits[1] = w.y, bits[2] = w.z, bits[3] = w.w;
         }
         const int nsub = kt.y > 64 ? 2 : 1;
         for (int sub = 0; sub < nsub; ++sub, ++g) {
           const int ncols = min(64, kt.y - sub * 64);  // valid columns of this 64-column sub-step
           const int doff = kt.z - sub * 64;            // allowed: c <= r + doff (c relative to the sub-step)
-          int lim = min(ncols - 1, row + doff);
+          int lim = min(ncols - 1, rr + doff);
           // warp-uniform bounds of lim over the 32 rows of this warp: chunks at or below wlim_lo need no masking at
           // all, chunks above wlim_hi hold no allowed column for any lane
-          int wlim_lo = min(ncols - 1, quarter * 32 + doff);
-          int wlim_hi = min(ncols - 1, quarter * 32 + 31 + doff);
+          int wlim_lo = min(ncols - 1, wrow0 + doff);
+          int wlim_hi = min(ncols - 1, wrow0 + 31 + doff);
           if (bitmask) {
             lim = ncols - 1;
             wlim_lo = -1;  // every chunk takes the masked path
@@ -447,11 +472,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ---- epilogue: O / l -> bf16 -> staging rows in the (now idle) V buffer -> one bulk copy per row ----
       mbar_wait(&o_full, nq & 1);
       tc_fence_after();
-      const bool valid = row < it.nrows;
+      const bool valid = rr < it.nrows;
       const float inv = l > 0.f ? 1.f / l : 0.f;
       constexpr int HALF_BYTES = 128 + 16;  // 64 bf16 per round; +16 B keeps 16-byte stores at a row stride conflict-free
       uint8_t* srow = sV + row * HALF_BYTES;
-      __nv_bfloat16* orow = p.out + it.b * p.so_b + static_cast<long long>(q0 + row) * p.so_l + it.h * p.so_h;
+      __nv_bfloat16* orow = p.out + it.b * p.so_b + static_cast<long long>(q0 + rr) * p.so_l + head * p.so_h;
       tmem_ld_32x32b_x32(tmem_O + lane_addr, r);
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
@@ -570,8 +595,8 @@ int make_map_4d(CUtensorMap* m, const void* base, int D, int rows, int heads, in
 }
 
 template <int D>
-int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const PrefillParams& p,
-                   int cap_qtiles, cudaStream_t st) {
+int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtensorMap& tq32, const CUtensorMap& tk,
+                   const CUtensorMap& tv, const PrefillParams& p, int cap_qtiles, cudaStream_t st) {
   static bool configured = false;
   static int n_sm = 148;
   const int smem = Smem<D>::kTotal > 100 * 1024 ? Smem<D>::kTotal : 100 * 1024;  // cap residency at 2 CTAs / SM (TMEM)
@@ -585,7 +610,7 @@ int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
   const long long n_items = static_cast<long long>(cap_qtiles) * p.H * p.B;
   if (n_items <= 0) return SDAG_ERR_INVALID;
   const long long grid = n_items < 2ll * n_sm ? n_items : 2ll * n_sm;
-  sdag_prefill_kernel<D><<<static_cast<unsigned>(grid), 256, smem, st>>>(tq, tk, tv, p, n_items);
+  sdag_prefill_kernel<D><<<static_cast<unsigned>(grid), 256, smem, st>>>(tq, tq64, tq32, tk, tv, p, n_items);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -617,10 +642,12 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
   if (workspace_bytes < sdag_prefill_workspace_bytes(B, Hkv, D)) return SDAG_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tq64, tq32, tk, tv;
   // batch stride of a size-1 dim is irrelevant to addressing but must still be a legal stride
   auto bs = [](int64_t s, int64_t fallback) { return s > 0 ? s : fallback; };
   if (make_map_4d(&tq, q, D, Lq, H, B, sq_l, sq_h, bs(sq_b, sq_l * Lq), BM)) return SDAG_ERR_DRIVER;
+  if (make_map_4d(&tq64, q, D, Lq, H, B, sq_l, sq_h, bs(sq_b, sq_l * Lq), 64)) return SDAG_ERR_DRIVER;
+  if (make_map_4d(&tq32, q, D, Lq, H, B, sq_l, sq_h, bs(sq_b, sq_l * Lq), 32)) return SDAG_ERR_DRIVER;
   if (make_map_4d(&tk, k, D, Skv, Hkv, B, sk_l, sk_h, bs(sk_b, sk_l * Skv), BN)) return SDAG_ERR_DRIVER;
   if (make_map_4d(&tv, v, D, Skv, Hkv, B, sv_l, sv_h, bs(sv_b, sv_l * Skv), BN)) return SDAG_ERR_DRIVER;
 
@@ -640,13 +667,13 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
                                                 static_cast<float*>(workspace), blockmaps_dev, p.bm_stride_ints);
     v_mean_kernel<128><<<dim3(Hkv, B), 128, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints);
     SDAG_CUDA_TRY(cudaGetLastError());
-    return launch_prefill<128>(tq, tk, tv, p, cap_qtiles, st);
+    return launch_prefill<128>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
   }
   v_colsum_kernel<64><<<vgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(v), sv_b, sv_h, sv_l, Skv,
                                              static_cast<float*>(workspace), blockmaps_dev, p.bm_stride_ints);
   v_mean_kernel<64><<<dim3(Hkv, B), 64, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints);
   SDAG_CUDA_TRY(cudaGetLastError());
-  return launch_prefill<64>(tq, tk, tv, p, cap_qtiles, st);
+  return launch_prefill<64>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
 }
 
 }  // extern "C"
