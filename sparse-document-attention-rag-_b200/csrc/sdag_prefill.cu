@@ -40,12 +40,38 @@ struct Smem {
   static constexpr int kQ = BM * D * 2;
   static constexpr int kK = BN * D * 2;
   static constexpr int kV = BN * D * 2;
-  static constexpr int kTotal = kQ + kK + kV + 1024;  // + alignment slack
+  static constexpr int kStage = 4 * 32 * 80;              // per softmax warp: 32 rows x (64 B + 16 B pad) of output
+  static constexpr int kTotal = kQ + kK + kV + kStage + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two lanes of a 64-bit register pair per instruction.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long pack2u(uint32_t lo, uint32_t hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 
@@ -62,6 +88,31 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+
+#ifdef SDAG_DEBUG_TIMING
+__device__ unsigned long long* g_timing = nullptr;  // [n_items][8] globaltimer stamps (bring-up only)
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define STAMP(item, slot)                                                                  \
+  do {                                                                                     \
+    if (g_timing && threadIdx.x == 0) g_timing[(item) * 8ull + (slot)] = gtime();          \
+  } while (0)
+#else
+#define STAMP(item, slot) \
+  do {                    \
+  } while (0)
+#endif
+
+#ifdef SDAG_DEBUG_TIMING
+__device__ __forceinline__ bool g_timing_enabled() { return g_timing != nullptr; }
+__device__ __forceinline__ void g_timing_write(long long item, int slot, long long v) { g_timing[item * 8ull + slot] = v; }
+#else
+__device__ __forceinline__ bool g_timing_enabled() { return false; }
+__device__ __forceinline__ void g_timing_write(long long, int, long long) {}
+#endif
 
 struct Item {
   int q0, nrows, n_kv, h, b, hkv;
@@ -120,7 +171,8 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Smem<D>::kQ;
   uint8_t* sV = sK + Smem<D>::kK;
-  __shared__ uint64_t q_full, q_empty, k_full, k_empty, v_full, v_empty, s_full[2], p_full[2], pv_done, o_full, o_empty, stage_free;
+  uint8_t* sStage = sV + Smem<D>::kV;
+  __shared__ uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done, o_full, o_empty;
   __shared__ uint64_t sched_full[2], sched_empty[2];
   __shared__ long long sched_item[2];
   __shared__ uint32_t tmem_base_s;
@@ -130,10 +182,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (tid == 0) {
     mbar_init(&q_full, 1);
     mbar_init(&q_empty, 1);
-    mbar_init(&k_full, 1);
-    mbar_init(&k_empty, 1);
-    mbar_init(&v_full, 1);
-    mbar_init(&v_empty, 1);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&k_full[x], 1);
+      mbar_init(&k_empty[x], 1);
+      mbar_init(&v_full[x], 1);
+      mbar_init(&v_empty[x], 1);
+    }
     for (int x = 0; x < 2; ++x) {
       mbar_init(&s_full[x], 1);
       mbar_init(&p_full[x], 128);
@@ -141,10 +195,9 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(&pv_done, 1);
     mbar_init(&o_full, 1);
     mbar_init(&o_empty, 128);
-    mbar_init(&stage_free, 1);
     for (int x = 0; x < 2; ++x) {
       mbar_init(&sched_full[x], 1);
-      mbar_init(&sched_empty[x], 32 + 128);  // every MMA-warp lane and softmax thread reads the slot
+      mbar_init(&sched_empty[x], 32 + 128 + 1);  // every MMA-warp lane, softmax thread and the V producer reads the slot
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
@@ -171,10 +224,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
    if (warp == 4) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      uint32_t nq = 0, nk = 0, nv = 0;  // loads issued so far per buffer
+      uint32_t nq = 0, nk = 0;  // loads issued so far per buffer
       // Dynamic longest-first scheduling: the first item is blockIdx.x, later ones come from a global counter; the
       // producer publishes each item index to the other roles through a two-slot ring (so it can run one item ahead).
       long long i = blockIdx.x;
+      long long i_next = static_cast<long long>(gridDim.x) + atomicAdd(p.next_item, 1);
       for (uint32_t ns = 0;; ++ns) {
         const uint32_t slot = ns & 1;
         mbar_wait(&sched_empty[slot], ((ns >> 1) & 1) ^ 1);
@@ -182,7 +236,27 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_arrive(&sched_full[slot]);
         if (i >= n_items) break;
         const Item it = fetch_item(p, i);
-        i = static_cast<long long>(gridDim.x) + atomicAdd(p.next_item, 1);
+        // The item after this one is already known: pull its Q and its first K / V halves into L2 now, so that the
+        // ring loads issued a few microseconds from now do not pay HBM latency (short items are latency-bound).
+        if (i_next < n_items) {
+          const Item nx = fetch_item(p, i_next);
+          if (nx.valid && nx.n_kv > 0) {
+            for (int g = 0; g < nx.pack; ++g)
+              for (int dh = 0; dh < D / 64; ++dh)
+                tma_prefetch_l2_4d(nx.pack == 1 ? &tmQ : (nx.pack == 2 ? &tmQ64 : &tmQ32), dh * 64, nx.q0, nx.h + g, nx.b);
+            int halves = 0;
+            for (int j = 0; j < nx.n_kv && halves < 6; ++j) {
+              const int4 kt = nx.kvt[j];
+              for (int sub = 0; sub < (kt.y > 64 ? 2 : 1) && halves < 6; ++sub, ++halves)
+                for (int dh = 0; dh < D / 64; ++dh) {
+                  tma_prefetch_l2_4d(&tmK, dh * 64, kt.x + sub * 64, nx.hkv, nx.b);
+                  tma_prefetch_l2_4d(&tmV, dh * 64, kt.x + sub * 64, nx.hkv, nx.b);
+                }
+            }
+          }
+        }
+        i = i_next;
+        i_next = static_cast<long long>(gridDim.x) + atomicAdd(p.next_item, 1);
         if (!it.valid || it.n_kv == 0) continue;
         mbar_wait(&q_empty, (nq & 1) ^ 1);
         mbar_expect_tx(&q_full, Smem<D>::kQ);
@@ -195,16 +269,48 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               tma_load_4d(sQ + dh * BM * 128 + g * it.R * 128, tm, &q_full, dh * 64, it.q0, it.h + g, it.b);
         }
         for (int j = 0; j < it.n_kv; ++j) {
-          const int k0 = it.kvt[j].x;
-          mbar_wait(&k_empty, (nk & 1) ^ 1);
-          mbar_expect_tx(&k_full, Smem<D>::kK);
-          for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sK + dh * BN * 128, &tmK, &k_full, dh * 64, k0, it.hkv, it.b);
-          ++nk;
-          mbar_wait(&v_empty, (nv & 1) ^ 1);
-          if (j == 0 && nq > 0) mbar_wait(&stage_free, (nq - 1) & 1);  // previous item's output rows have left sV
-          mbar_expect_tx(&v_full, Smem<D>::kV);
-          for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sV + dh * BN * 128, &tmV, &v_full, dh * 64, k0, it.hkv, it.b);
-          ++nv;
+          const int4 kt = it.kvt[j];
+          const int nsub = kt.y > 64 ? 2 : 1;
+          for (int sub = 0; sub < nsub; ++sub) {
+            // K travels as 64-row halves through a two-slot ring, so the load of sub-step u+1 is in flight while
+            // sub-step u is being computed — also across tile and item boundaries.  (V has its own producer warp:
+            // its slots free up later, after P.V, and must not hold back the K loads.)
+            const int k0 = kt.x + sub * 64;
+            const uint32_t ks = nk & 1;
+            mbar_wait(&k_empty[ks], ((nk >> 1) & 1) ^ 1);
+            mbar_expect_tx(&k_full[ks], Smem<D>::kK / 2);
+            for (int dh = 0; dh < D / 64; ++dh)
+              tma_load_4d(sK + ks * (Smem<D>::kK / 2) + dh * 64 * 128, &tmK, &k_full[ks], dh * 64, k0, it.hkv, it.b);
+            ++nk;
+          }
+        }
+        ++nq;
+      }
+    }
+  } else if (warp == 6) {
+    // ======================= TMA producer for V =======================
+    if (lane == 0) {
+      uint32_t nq = 0, nv = 0;
+      for (uint32_t ns = 0;; ++ns) {
+        const uint32_t slot = ns & 1;
+        mbar_wait(&sched_full[slot], (ns >> 1) & 1);
+        const long long i = sched_item[slot];
+        mbar_arrive(&sched_empty[slot]);
+        if (i < 0) break;
+        const Item it = fetch_item(p, i);
+        if (!it.valid || it.n_kv == 0) continue;
+        int sub_in_item = 0;
+        for (int j = 0; j < it.n_kv; ++j) {
+          const int4 kt = it.kvt[j];
+          const int nsub = kt.y > 64 ? 2 : 1;
+          for (int sub = 0; sub < nsub; ++sub, ++sub_in_item) {
+            const uint32_t vs = nv & 1;
+            mbar_wait(&v_empty[vs], ((nv >> 1) & 1) ^ 1);
+            mbar_expect_tx(&v_full[vs], Smem<D>::kV / 2);
+            for (int dh = 0; dh < D / 64; ++dh)
+              tma_load_4d(sV + vs * (Smem<D>::kV / 2) + dh * 64 * 128, &tmV, &v_full[vs], dh * 64, kt.x + sub * 64, it.hkv, it.b);
+            ++nv;
+          }
         }
         ++nq;
       }
@@ -215,7 +321,6 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // so QK^T of sub-steps g+1 / g+2 is issued before the softmax of g has finished: issue order is
     //   QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...   (QK(g+2) overwrites the buffer whose P was consumed by PV(g)).
     uint32_t nq = 0;           // items with tensor work done so far
-    uint32_t ntk = 0, ntv = 0; // K / V tiles consumed so far (barrier phases)
     uint32_t gq = 0, gp = 0;   // QK / PV sub-steps issued so far (S-buffer index and phases)
     for (uint32_t ns = 0;; ++ns) {
       const uint32_t slot = ns & 1;
@@ -233,10 +338,8 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int ncols = it.kvt[qj].y;
         const int nsub = ncols > 64 ? 2 : 1;
         const int sub_cols = min(64, ncols - qs * 64);
-        if (qs == 0) {
-          mbar_wait(&k_full, ntk & 1);
-          ++ntk;
-        }
+        const uint32_t slot = gq & 1;  // K ring slot == S buffer index: both advance once per sub-step
+        mbar_wait(&k_full[slot], (gq >> 1) & 1);
         tc_fence_after();
         const bool last_sub = qs == nsub - 1;
         if (lane == 0) {
@@ -244,15 +347,13 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t off = (ks >> 2) * (BM * 128) + (ks & 3) * 32;
-            const uint32_t offk = (ks >> 2) * (BN * 128) + qs * (64 * 128) + (ks & 3) * 32;
-            umma_ss(tmem_S + (gq & 1) * 64, umma_smem_desc_sw128(smem_u32(sQ) + off, 16, 1024),
+            const uint32_t offk = slot * (Smem<D>::kK / 2) + (ks >> 2) * (64 * 128) + (ks & 3) * 32;
+            umma_ss(tmem_S + slot * 64, umma_smem_desc_sw128(smem_u32(sQ) + off, 16, 1024),
                     umma_smem_desc_sw128(smem_u32(sK) + offk, 16, 1024), idesc, ks > 0);
           }
-          if (last_sub) {
-            umma_commit(&k_empty);                         // K tile consumed -> producer may load the next K
-            if (qj == it.n_kv - 1) umma_commit(&q_empty);  // Q consumed -> producer may load the next item's Q
-          }
-          umma_commit(&s_full[gq & 1]);
+          umma_commit(&k_empty[slot]);                               // K half consumed -> producer may refill the slot
+          if (last_sub && qj == it.n_kv - 1) umma_commit(&q_empty);  // Q consumed -> next item's Q may load
+          umma_commit(&s_full[slot]);
         }
         __syncwarp();
         ++gq;
@@ -267,11 +368,9 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int ncols = it.kvt[pj].y;
         const int nsub = ncols > 64 ? 2 : 1;
         const int sub_cols = min(64, ncols - ps * 64);
-        mbar_wait(&p_full[gp & 1], (gp >> 1) & 1);
-        if (ps == 0) {
-          mbar_wait(&v_full, ntv & 1);
-          ++ntv;
-        }
+        const uint32_t slot = gp & 1;
+        mbar_wait(&p_full[slot], (gp >> 1) & 1);
+        mbar_wait(&v_full[slot], (gp >> 1) & 1);
         if (first_pv && nq > 0) mbar_wait(&o_empty, (nq - 1) & 1);  // previous item's epilogue has read O out of TMEM
         tc_fence_after();
         const bool last_sub = ps == nsub - 1;
@@ -279,11 +378,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t idesc = umma_idesc_bf16_f32(BM, D, 0, 1);  // B = V, MN-major
           const int pv_steps = (sub_cols + 15) >> 4;
           for (int ks = 0; ks < pv_steps; ++ks) {
-            umma_ts(tmem_O, tmem_S + (gp & 1) * 64 + ks * 8,
-                    umma_smem_desc_sw128(smem_u32(sV) + (ps * 64 + ks * 16) * 128, BN * 128, 1024), idesc,
+            umma_ts(tmem_O, tmem_S + slot * 64 + ks * 8,
+                    umma_smem_desc_sw128(smem_u32(sV) + slot * (Smem<D>::kV / 2) + ks * 16 * 128, 64 * 128, 1024), idesc,
                     (!first_pv || ks > 0) ? 1u : 0u);
           }
-          if (last_sub) umma_commit(&v_empty);
+          umma_commit(&v_empty[slot]);
           umma_commit(&pv_done);
           if (last_sub && pj == it.n_kv - 1) umma_commit(&o_full);
         }
@@ -325,6 +424,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (i < 0) break;
       const Item it = fetch_item(p, i);
       if (!it.valid) continue;
+      STAMP(i, 0);
       const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(it.b) * p.Hkv + it.hkv) * D;
       if (it.n_kv == 0) {
         // Gap rows only (no allowed key): every row is the mean of V over all keys.  No tensor work.
@@ -343,7 +443,6 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float m = -INFINITY, l = 0.f;
       // with GQA packing the tile row splits into (head within the group, row within the query tile)
       const int rr = row & (it.R - 1);
-      const int head = it.h + row / it.R;
       const int wrow0 = (quarter * 32) & (it.R - 1);  // first query-tile row handled by this warp
 
       bool first_sub = true;
@@ -374,6 +473,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint32_t tS = tmem_S + lane_addr + (g & 1) * 64;
           mbar_wait(&s_full[g & 1], (g >> 1) & 1);
           tc_fence_after();
+          if (first_sub) STAMP(i, 1);
 
           // Single pass over the 64 scores of this sub-step: maximum over the allowed columns, keep the running
           // reference maximum m unless it is exceeded by more than RESCALE_TAU (then l and O, accumulated against
@@ -426,6 +526,8 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
           }
           const float neg_m = (m == -INFINITY) ? 0.f : -m;
+          const unsigned long long scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(neg_m, neg_m);
+          unsigned long long lsA = pack2(0.f, 0.f), lsB = lsA;
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const uint32_t* cur = c ? r2 : r;
@@ -437,11 +539,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               } else if (wlim_lo >= c * 32 + 31) {
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
-                  const float p0 = exp2f(fmaf(__uint_as_float(cur[e]), p.scale_log2, neg_m));
-                  const float p1 = exp2f(fmaf(__uint_as_float(cur[e + 1]), p.scale_log2, neg_m));
-                  const float p2 = exp2f(fmaf(__uint_as_float(cur[e + 2]), p.scale_log2, neg_m));
-                  const float p3 = exp2f(fmaf(__uint_as_float(cur[e + 3]), p.scale_log2, neg_m));
-                  l0 += p0, l1 += p1, l2 += p2, l3 += p3;
+                  float x0, x1, x2, x3;
+                  unpack2(fma2(pack2u(cur[e], cur[e + 1]), scale2, negm2), x0, x1);
+                  unpack2(fma2(pack2u(cur[e + 2], cur[e + 3]), scale2, negm2), x2, x3);
+                  const float p0 = exp2f(x0), p1 = exp2f(x1), p2 = exp2f(x2), p3 = exp2f(x3);
+                  lsA = add2(lsA, pack2(p0, p1));
+                  lsB = add2(lsB, pack2(p2, p3));
                   pk[e >> 1] = pack_bf16x2(p0, p1);
                   pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
                 }
@@ -461,7 +564,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               tmem_st_32x32b_x16(tS + c * 16, pk);  // both S chunks are already in registers
             }
           }
-          l += (l0 + l1) + (l2 + l3);
+          {
+            float a0, a1, b0, b1;
+            unpack2(add2(lsA, lsB), a0, a1);
+            (void)b0, (void)b1;
+            l += (l0 + l1) + (l2 + l3) + (a0 + a1);
+          }
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&p_full[g & 1]);
@@ -470,13 +578,18 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
 
       // ---- epilogue: O / l -> bf16 -> staging rows in the (now idle) V buffer -> one bulk copy per row ----
+      STAMP(i, 2);
       mbar_wait(&o_full, nq & 1);
       tc_fence_after();
+      STAMP(i, 3);
       const bool valid = rr < it.nrows;
       const float inv = l > 0.f ? 1.f / l : 0.f;
-      constexpr int HALF_BYTES = 128 + 16;  // 64 bf16 per round; +16 B keeps 16-byte stores at a row stride conflict-free
-      uint8_t* srow = sV + row * HALF_BYTES;
-      __nv_bfloat16* orow = p.out + it.b * p.so_b + static_cast<long long>(q0 + rr) * p.so_l + head * p.so_h;
+      // Each warp stages its 32 rows, 32 columns at a time, in its private staging rows and writes them out itself
+      // with coalesced 16-byte stores: 8 rows x 64 B per instruction instead of 32 partial lines.
+      constexpr int SROW = 64 + 16;  // +16 B spreads the row-strided 16-byte stores over the banks
+      uint8_t* wbase = sStage + quarter * 32 * SROW;
+      uint8_t* srow = wbase + lane * SROW;
+      const int wr = lane >> 2, ch = lane & 3;  // write-out role: row within a group of 8, 16-byte chunk of the row
       tmem_ld_32x32b_x32(tmem_O + lane_addr, r);
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
@@ -503,30 +616,27 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             o[(e >> 1) + 1] = pack_bf16x2(f.z, f.w);
           }
         }
-        if ((c & 1) == 0 && c > 0) {
-          // second round reuses the staging rows: wait until the bulk engine has read the first round
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-        uint4* dst = reinterpret_cast<uint4*>(srow + (c & 1) * 64);
+        uint4* dst = reinterpret_cast<uint4*>(srow);
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
         dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
         dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
-        if ((c & 1) == 1 || c == D / 32 - 1) {
-          fence_proxy_async_smem();
-          if (valid) {
-            const int bytes = ((c & 1) + 1) * 64;
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(orow + (c >> 1) * 64),
-                         "r"(smem_u32(srow)), "r"(bytes)
-                         : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int trow = quarter * 32 + g8 * 8 + wr;  // tile row
+          const int orr = trow & (it.R - 1);
+          if (orr < it.nrows) {
+            const uint4 val = *reinterpret_cast<const uint4*>(wbase + (g8 * 8 + wr) * SROW + ch * 16);
+            __nv_bfloat16* gp = p.out + it.b * p.so_b + static_cast<long long>(q0 + orr) * p.so_l +
+                                (it.h + trow / it.R) * p.so_h + c * 32 + ch * 8;
+            *reinterpret_cast<uint4*>(gp) = val;
           }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        __syncwarp();
       }
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      // all 128 rows have left the V buffer -> the producer may load the next item's first V tile
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (stid == 0) mbar_arrive(&stage_free);
+      STAMP(i, 4);
+      if (g_timing_enabled() && threadIdx.x == 0) g_timing_write(i, 5, it.n_kv), g_timing_write(i, 6, blockIdx.x);
       ++nq;
     }
   }
@@ -618,6 +728,11 @@ int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtenso
 
 extern "C" {
 
+#ifdef SDAG_DEBUG_TIMING
+int sdag_debug_set_timing(unsigned long long* buf) {
+  return static_cast<int>(cudaMemcpyToSymbol(g_timing, &buf, sizeof(buf)));
+}
+#endif
 
 size_t sdag_prefill_workspace_bytes(int B, int Hkv, int D) {
   if (B <= 0 || Hkv <= 0 || D <= 0) return 0;
@@ -648,8 +763,8 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
   if (make_map_4d(&tq, q, D, Lq, H, B, sq_l, sq_h, bs(sq_b, sq_l * Lq), BM)) return SDAG_ERR_DRIVER;
   if (make_map_4d(&tq64, q, D, Lq, H, B, sq_l, sq_h, bs(sq_b, sq_l * Lq), 64)) return SDAG_ERR_DRIVER;
   if (make_map_4d(&tq32, q, D, Lq, H, B, sq_l, sq_h, bs(sq_b, sq_l * Lq), 32)) return SDAG_ERR_DRIVER;
-  if (make_map_4d(&tk, k, D, Skv, Hkv, B, sk_l, sk_h, bs(sk_b, sk_l * Skv), BN)) return SDAG_ERR_DRIVER;
-  if (make_map_4d(&tv, v, D, Skv, Hkv, B, sv_l, sv_h, bs(sv_b, sv_l * Skv), BN)) return SDAG_ERR_DRIVER;
+  if (make_map_4d(&tk, k, D, Skv, Hkv, B, sk_l, sk_h, bs(sk_b, sk_l * Skv), 64)) return SDAG_ERR_DRIVER;  // 64-row halves
+  if (make_map_4d(&tv, v, D, Skv, Hkv, B, sv_l, sv_h, bs(sv_b, sv_l * Skv), 64)) return SDAG_ERR_DRIVER;
 
   PrefillParams p;
   p.out = static_cast<__nv_bfloat16*>(out);

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Bring-up tool: per-CTA stage timestamps of the prefill kernel (needs a library built with
-SDAG_EXTRA_NVCC_FLAGS=-DSDAG_DEBUG_TIMING)."""
+"""Bring-up tool: per-item stage timestamps of the persistent prefill kernel (needs a library built with
+SDAG_EXTRA_NVCC_FLAGS=-DSDAG_DEBUG_TIMING).  Stamps are taken by softmax thread 0 of the CTA that ran the item."""
 import ctypes
 import os
 import sys
@@ -24,8 +24,8 @@ k = torch.randn(B, Hkv, Lq, D, generator=g, device=dev).to(torch.bfloat16)
 v = torch.randn(B, Hkv, Lq, D, generator=g, device=dev).to(torch.bfloat16)
 bm = sdag.causal_blockmap(Lq, dev) if c["causal"] else sdag.build_blockmap([sdag.SdagLayout(Lq, S, spans, qa)], dev)
 lib = L.load()
-grid = bm.launch_qtiles * H * B
-buf = torch.zeros(grid * 8, dtype=torch.int64, device=dev)
+n_items = bm.launch_qtiles * H * B
+buf = torch.zeros(n_items * 8, dtype=torch.int64, device=dev)
 for _ in range(2):
     sdag.sdag_prefill_attention(q, k, v, bm)
 lib.sdag_debug_set_timing.argtypes = [ctypes.c_void_p]
@@ -33,21 +33,30 @@ assert lib.sdag_debug_set_timing(buf.data_ptr()) == 0
 torch.cuda.synchronize()
 sdag.sdag_prefill_attention(q, k, v, bm)
 torch.cuda.synchronize()
-t = buf.cpu().numpy().reshape(grid, 8).astype(np.int64)
-real = t[:, 1] > 0
-t0 = t[t[:, 0] > 0, 0].min()
-print(f"{name}: grid {grid}, real CTAs {real.sum()}, kernel span {(t[real][:, 6].max() - t0) / 1e3:.1f} us")
+t = buf.cpu().numpy().reshape(n_items, 8).astype(np.int64)
+real = t[:, 4] > 0
 tr = t[real]
-n_kv_known = tr[:, 2] > 0
+t0 = t[t[:, 0] > 0, 0].min()
+print(f"{name}: items {n_items}, with tensor work {real.sum()}, span {(tr[:, 4].max() - t0) / 1e3:.1f} us")
+
+
 def stat(x):
-    return f"mean {x.mean() / 1e3:7.2f} us  p50 {np.median(x) / 1e3:7.2f}  p95 {np.percentile(x, 95) / 1e3:7.2f}"
-print("setup (start -> after tmem alloc+sync):", stat(tr[:, 1] - tr[:, 0]))
-w = tr[n_kv_known]
-print("first S ready (after setup):          ", stat(w[:, 2] - w[:, 1]))
-print("first softmax:                        ", stat(w[:, 3] - w[:, 2]))
-print("rest of loop until O ready:           ", stat(w[:, 4] - w[:, 3]))
-print("epilogue:                             ", stat(tr[:, 5] - tr[:, 4]))
-print("teardown:                             ", stat(tr[:, 6] - tr[:, 5]))
-print("whole CTA:                            ", stat(tr[:, 6] - tr[:, 0]))
-starts = np.sort(tr[:, 0] - t0)
-print("CTA start times (us) percentiles 10/50/90/100:", [round(float(np.percentile(starts, p)) / 1e3, 1) for p in (10, 50, 90, 100)])
+    return f"mean {x.mean() / 1e3:6.2f} us  p50 {np.median(x) / 1e3:6.2f}  p95 {np.percentile(x, 95) / 1e3:6.2f}"
+
+
+for nk in sorted(set(tr[:, 5])):
+    w = tr[tr[:, 5] == nk]
+    print(f"-- items with {nk} kv tiles: {len(w)}")
+    print("   item start -> first scores ready :", stat(w[:, 1] - w[:, 0]))
+    print("   softmax loop                     :", stat(w[:, 2] - w[:, 1]))
+    print("   wait for last P.V                :", stat(w[:, 3] - w[:, 2]))
+    print("   epilogue                         :", stat(w[:, 4] - w[:, 3]))
+    print("   whole item                       :", stat(w[:, 4] - w[:, 0]))
+# per-CTA busy fraction
+ctas = tr[:, 6]
+busy = np.zeros(int(ctas.max()) + 1)
+for cta in np.unique(ctas):
+    w = tr[ctas == cta]
+    busy[int(cta)] = (w[:, 4] - w[:, 0]).sum()
+span = tr[:, 4].max() - t0
+print(f"per-CTA time inside items / kernel span: mean {busy.mean() / span:.2f}, min {busy.min() / span:.2f}")
