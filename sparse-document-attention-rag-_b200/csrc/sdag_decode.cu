@@ -1,203 +1,238 @@
 // SDAG decode attention for sm_100a (path A5): one new token attends to every cached position — the
 // reference passes no mask after the prefill (SDAG.py:193-197), so decode is dense over the KV cache and
-// HBM-bound.  Split-KV: each CTA streams a contiguous range of cache rows of one kv head for all G = H/Hkv
-// query heads sharing it (K/V bytes are read exactly once), writes an (m, l, acc) partial; a second kernel
-// merges the partials.  CUDA-core arithmetic on purpose: 2*G FLOP per cache byte is far below the tensor
-// ridge.
+// HBM-bound.  Split-KV over a TMA ring: each CTA streams a contiguous range of cache rows of one kv head
+// for all G = H/Hkv query heads sharing it (K/V bytes are read exactly once) and writes an (m, l, acc)
+// partial; a second kernel merges the partials.  The arithmetic rides on warp-level MMAs only to keep the
+// instruction count out of the way of the copy engine: 2*G FLOP per cache byte is far below the tensor ridge.
 #include <math.h>
 
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace {
 
-constexpr int TILE_ROWS = 64;
-constexpr int MAX_G = 8;
-constexpr int MAX_CHUNK = 1024;  // cache rows per CTA
-constexpr int THREADS = 256;
+using namespace sm100;
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  const int sz = pred ? 16 : 0;  // zero-fill when out of range
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
+constexpr int TILE_ROWS = 128;   // cache rows per ring stage (16 per consumer warp)
+constexpr int MAX_G = 8;         // query heads per kv head (the M rows of the warp MMA that are live)
+constexpr int CONSUMERS = 8;     // consumer warps
+constexpr int THREADS = (CONSUMERS + 1) * 32;  // + one TMA producer warp
 
 template <int D>
 struct DecodeSmem {
-  static constexpr int kRowBytes = D * 2 + 16;  // +16 B: conflict-free 16-byte row-strided reads
-  static constexpr int kTile = TILE_ROWS * kRowBytes;
-  static constexpr int kTiles = 2 * kTile;
-  static constexpr int kScores = MAX_CHUNK * MAX_G * 4;
-  static constexpr int kQ = MAX_G * D * 4;
-  static constexpr int kTotal = kTiles + kScores + kQ;
+  static constexpr int kTileBytes = TILE_ROWS * D * 2;           // one K (or V) tile
+  static constexpr int kStageBytes = 2 * kTileBytes;             // K then V
+  static constexpr int kStages = D == 128 ? 3 : 6;               // 192 KiB of ring either way
+  static constexpr int kTotal = kStages * kStageBytes + 1024;    // + alignment slack (128B-swizzle atoms)
 };
 
-template <int D>
-__device__ __forceinline__ void load_tile(uint8_t* dst, const __nv_bfloat16* base, long long s_l, int row0, int row_end) {
-  constexpr int CPR = D / 8;  // 16-byte chunks per row
-  for (int i = threadIdx.x; i < TILE_ROWS * CPR; i += THREADS) {
-    const int r = i / CPR, c = i % CPR;
-    const bool ok = row0 + r < row_end;
-    const __nv_bfloat16* src = base + static_cast<long long>(ok ? row0 + r : row0) * s_l + c * 8;
-    cp_async16(dst + r * DecodeSmem<D>::kRowBytes + c * 16, src, ok);
-  }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+// D(16x8, f32) += A(16x16, bf16, row) * B(16x8, bf16, col).  Only rows 0..7 of A are live here (a1 = a3 = 0).
+__device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Split-KV decode: CTA (split, hkv, b) streams its share of the cache rows of one kv head through a TMA ring
+// (K and V tiles of 128 rows, 128-byte swizzle) exactly once for all G query heads of the group.  The ranges are cut
+// inside the kernel from the device-side cache length, so every CTA of a replayed CUDA graph keeps an equal share as
+// the cache grows.  Each consumer warp owns 16 rows of every tile and runs its own online softmax on warp-level
+// m16n8k16 MMAs (S = Q K^T with the G heads as the M rows, O += P V) — no block-wide synchronisation in the loop;
+// the eight warp states are merged through shared memory at the end and written as one (m, l, acc[D]) partial.
 template <int D>
-__global__ void __launch_bounds__(THREADS)
-decode_split_kernel(const __nv_bfloat16* __restrict__ q, long long sq_b, long long sq_h,
-                    const __nv_bfloat16* __restrict__ k, long long sk_b, long long sk_h, long long sk_l,
-                    const __nv_bfloat16* __restrict__ v, long long sv_b, long long sv_h, long long sv_l,
-                    float* __restrict__ partial, int H, int Hkv, int kv_len_host, int rows_per_split, float scale_log2,
-                    const int32_t* __restrict__ kv_len_dev) {
-  const int kv_len = kv_len_dev ? *kv_len_dev : kv_len_host;  // device value: CUDA-graph replay per token
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint8_t* tiles = smem;
-  float* sp = reinterpret_cast<float*>(smem + DecodeSmem<D>::kTiles);          // [MAX_CHUNK][MAX_G]
-  float* sq = reinterpret_cast<float*>(smem + DecodeSmem<D>::kTiles + DecodeSmem<D>::kScores);  // [MAX_G][D]
-  __shared__ float s_m[MAX_G], s_l[MAX_G];
+__global__ void __launch_bounds__(THREADS, 1)
+decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __nv_bfloat16* __restrict__ q, long long sq_b, long long sq_h, float* __restrict__ partial,
+                    int H, int Hkv, int kv_len_host, float scale_log2, const int32_t* __restrict__ kv_len_dev) {
+  using S = DecodeSmem<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[S::kStages], empty[S::kStages];
 
-  const int split = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
-  const int nsplit = gridDim.x;
+  const int kv_len = kv_len_dev ? min(*kv_len_dev, kv_len_host) : kv_len_host;
+  const int split = blockIdx.x, nsplit = gridDim.x, hkv = blockIdx.y, b = blockIdx.z;
   const int G = H / Hkv;
-  const int tid = threadIdx.x;
-  const int r0 = split * rows_per_split;
-  const int r1 = min(kv_len, r0 + rows_per_split);
-  const int n_rows = max(0, r1 - r0);
-  const int n_tiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_total = (kv_len + TILE_ROWS - 1) / TILE_ROWS;
+  const int tiles_per_split = (tiles_total + nsplit - 1) / nsplit;
+  const int t0 = min(tiles_total, split * tiles_per_split);
+  const int t1 = min(tiles_total, t0 + tiles_per_split);
+  const int n_tiles = t1 - t0;
 
-  for (int i = tid; i < MAX_G * D; i += THREADS) {
-    const int g = i / D, d = i % D;
-    sq[i] = g < G ? __bfloat162float(q[b * sq_b + (hkv * G + g) * sq_h + d]) * scale_log2 : 0.f;
-  }
-  const __nv_bfloat16* kbase = k + b * sk_b + hkv * sk_h;
-  const __nv_bfloat16* vbase = v + b * sv_b + hkv * sv_h;
-
-  // ---------------- pass 1: scores (log2 domain) ----------------
-  if (n_tiles > 0) load_tile<D>(tiles, kbase, sk_l, r0, r1);
-  cp_async_commit();
-  for (int t = 0; t < n_tiles; ++t) {
-    if (t + 1 < n_tiles) load_tile<D>(tiles + ((t + 1) & 1) * DecodeSmem<D>::kTile, kbase, sk_l, r0 + (t + 1) * TILE_ROWS, r1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const uint8_t* tile = tiles + (t & 1) * DecodeSmem<D>::kTile;
-    const int row = tid & (TILE_ROWS - 1);
-    for (int g = tid / TILE_ROWS; g < G; g += THREADS / TILE_ROWS) {
-      const uint4* kr = reinterpret_cast<const uint4*>(tile + row * DecodeSmem<D>::kRowBytes);
-      const float4* qg = reinterpret_cast<const float4*>(sq + g * D);
-      float acc = 0.f;
-#pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
-        const uint4 w = kr[c];
-        const float4 qa = qg[2 * c], qb = qg[2 * c + 1];
-        const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
-        const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
-        const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.z));
-        const float2 f3 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.w));
-        acc = fmaf(f0.x, qa.x, acc);
-        acc = fmaf(f0.y, qa.y, acc);
-        acc = fmaf(f1.x, qa.z, acc);
-        acc = fmaf(f1.y, qa.w, acc);
-        acc = fmaf(f2.x, qb.x, acc);
-        acc = fmaf(f2.y, qb.y, acc);
-        acc = fmaf(f3.x, qb.z, acc);
-        acc = fmaf(f3.y, qb.w, acc);
-      }
-      const int lr = t * TILE_ROWS + row;
-      sp[lr * MAX_G + g] = lr < n_rows ? acc : -INFINITY;
+  if (tid == 0) {
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CONSUMERS);
     }
-    __syncthreads();
+    fence_mbar_init();
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
   }
-  cp_async_wait<0>();
+  __syncthreads();
 
-  // start streaming V while the softmax statistics are computed
-  if (n_tiles > 0) load_tile<D>(tiles, vbase, sv_l, r0, r1);
-  cp_async_commit();
+  if (warp == CONSUMERS) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % S::kStages;
+        if (it >= S::kStages) mbar_wait(&empty[s], ((it / S::kStages) - 1) & 1);
+        uint8_t* stage = smem + s * S::kStageBytes;
+        const int row0 = (t0 + it) * TILE_ROWS;
+        mbar_expect_tx(&full[s], S::kStageBytes);
+        for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(stage + dh * TILE_ROWS * 128, &tmK, &full[s], dh * 64, row0, hkv, b);
+        for (int dh = 0; dh < D / 64; ++dh)
+          tma_load_4d(stage + S::kTileBytes + dh * TILE_ROWS * 128, &tmV, &full[s], dh * 64, row0, hkv, b);
+      }
+    }
+    return;
+  }
 
-  // ---------------- softmax statistics per head: warp g handles head g ----------------
+  // ======================= consumers =======================
+  const int g = lane >> 2, qd = lane & 3;  // MMA row (query head within the group) / quad lane
+  // A fragments of Q for every 16-wide slice of d: a0 = Q[g][16ks + 2qd .. +1], a2 = Q[g][16ks + 8 + 2qd .. +1]
+  uint32_t qa[D / 16][2];
   {
-    const int warp = tid >> 5, lane = tid & 31;
-    if (warp < G) {
-      float mx = -INFINITY;
-      for (int r = lane; r < n_rows; r += 32) mx = fmaxf(mx, sp[r * MAX_G + warp]);
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float m_use = mx == -INFINITY ? 0.f : mx;
-      float sum = 0.f;
-      for (int r = lane; r < n_rows; r += 32) {
-        const float pv = exp2f(sp[r * MAX_G + warp] - m_use);
-        sp[r * MAX_G + warp] = pv;
-        sum += pv;
-      }
-      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      if (lane == 0) {
-        s_m[warp] = mx;
-        s_l[warp] = sum;
-      }
+    const __nv_bfloat16* qrow = q + b * sq_b + static_cast<long long>(hkv * G + g) * sq_h;
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+      qa[ks][0] = g < G ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + qd * 2) : 0u;
+      qa[ks][1] = g < G ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8 + qd * 2) : 0u;
     }
   }
-  __syncthreads();
-
-  // ---------------- pass 2: acc[g][d] = sum_r p[r][g] * V[r][d] ----------------
-  constexpr int TPG = D / 2;            // threads per row group (one bf16 pair each)
-  constexpr int GROUPS = THREADS / TPG;  // row groups
-  const int dp = tid % TPG, rg = tid / TPG;
-  float acc[MAX_G][2];
+  float o[D / 8][4];
 #pragma unroll
-  for (int g = 0; g < MAX_G; ++g) acc[g][0] = acc[g][1] = 0.f;
-  for (int t = 0; t < n_tiles; ++t) {
-    if (t + 1 < n_tiles) load_tile<D>(tiles + ((t + 1) & 1) * DecodeSmem<D>::kTile, vbase, sv_l, r0 + (t + 1) * TILE_ROWS, r1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const uint8_t* tile = tiles + (t & 1) * DecodeSmem<D>::kTile;
-    const int rows_here = min(TILE_ROWS, n_rows - t * TILE_ROWS);
-    for (int r = rg; r < rows_here; r += GROUPS) {
-      const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(tile + r * DecodeSmem<D>::kRowBytes + dp * 4));
-      const float4* pr = reinterpret_cast<const float4*>(sp + (t * TILE_ROWS + r) * MAX_G);
-      const float4 pa = pr[0];
-      acc[0][0] = fmaf(pa.x, vv.x, acc[0][0]), acc[0][1] = fmaf(pa.x, vv.y, acc[0][1]);
-      acc[1][0] = fmaf(pa.y, vv.x, acc[1][0]), acc[1][1] = fmaf(pa.y, vv.y, acc[1][1]);
-      acc[2][0] = fmaf(pa.z, vv.x, acc[2][0]), acc[2][1] = fmaf(pa.z, vv.y, acc[2][1]);
-      acc[3][0] = fmaf(pa.w, vv.x, acc[3][0]), acc[3][1] = fmaf(pa.w, vv.y, acc[3][1]);
-      if (G > 4) {
-        const float4 pb = pr[1];
-        acc[4][0] = fmaf(pb.x, vv.x, acc[4][0]), acc[4][1] = fmaf(pb.x, vv.y, acc[4][1]);
-        acc[5][0] = fmaf(pb.y, vv.x, acc[5][0]), acc[5][1] = fmaf(pb.y, vv.y, acc[5][1]);
-        acc[6][0] = fmaf(pb.z, vv.x, acc[6][0]), acc[6][1] = fmaf(pb.z, vv.y, acc[6][1]);
-        acc[7][0] = fmaf(pb.w, vv.x, acc[7][0]), acc[7][1] = fmaf(pb.w, vv.y, acc[7][1]);
+  for (int n = 0; n < D / 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m = -INFINITY, l = 0.f;  // running maximum of row g (quad-uniform), this thread's share of the row sum
+
+  // ldmatrix source rows inside the warp's 16-row slice of a tile (see the fragment tables of mma.m16n8k16)
+  const int wrow = warp * 16;
+  const int krow = wrow + ((lane >> 4) << 3) + (lane & 7);  // K: matrices (n-tile, d-half) = lane / 8 -> (lane/16, (lane/8)&1)
+  const int kch = (lane >> 3) & 1;
+  const int vrow = wrow + (((lane >> 3) & 1) << 3) + (lane & 7);  // V: matrices (kv-half, d-tile) = ((lane/8)&1, lane/16)
+  const int vch = lane >> 4;
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int s = it % S::kStages;
+    mbar_wait(&full[s], (it / S::kStages) & 1);
+    const uint32_t sK = smem_u32(smem + s * S::kStageBytes);
+    const uint32_t sV = sK + S::kTileBytes;
+    const int row0 = (t0 + it) * TILE_ROWS;
+    if (row0 + TILE_ROWS > kv_len) {
+      // tail tile: rows at or beyond the cache length may hold anything (a preallocated cache): zero this warp's V rows
+      // there so that P = 0 really contributes nothing; their scores are masked below
+      uint8_t* vt = smem + s * S::kStageBytes + S::kTileBytes;
+      for (int e = lane; e < 16 * (D / 8); e += 32) {
+        const int r = wrow + e / (D / 8), c = e % (D / 8);
+        if (row0 + r >= kv_len)
+          *reinterpret_cast<uint4*>(vt + (c >> 3) * TILE_ROWS * 128 + r * 128 + ((c & 7) << 4)) = make_uint4(0, 0, 0, 0);
       }
+      __syncwarp();
     }
-    __syncthreads();
-  }
-  cp_async_wait<0>();
-  __syncthreads();
 
-  // reduce the row groups through shared memory (tile buffers are free now): red[GROUPS][MAX_G][D]
-  float* red = reinterpret_cast<float*>(tiles);
-  static_assert(GROUPS * MAX_G * D * 4 <= DecodeSmem<D>::kTiles, "reduction scratch must fit in the tile buffers");
+    // ---- S[g][kv] for the warp's 16 rows: two n-tiles of 8 ----
+    float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-  for (int g = 0; g < MAX_G; ++g) {
-    red[(rg * MAX_G + g) * D + dp * 2] = acc[g][0];
-    red[(rg * MAX_G + g) * D + dp * 2 + 1] = acc[g][1];
+    for (int ks = 0; ks < D / 16; ++ks) {
+      const int c = ks * 2 + kch;  // 16-byte chunk of the row
+      uint32_t b00, b01, b10, b11;
+      ldmatrix_x4(sK + (c >> 3) * TILE_ROWS * 128 + sw128_offset(krow, c & 7), b00, b01, b10, b11);
+      mma_16816(sc[0], qa[ks][0], qa[ks][1], b00, b01);
+      mma_16816(sc[1], qa[ks][0], qa[ks][1], b10, b11);
+    }
+    // this thread: row g, columns kv = row0 + wrow + 8j + 2qd + {0,1}
+    float p[2][2];
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = row0 + wrow + j * 8 + qd * 2 + e < kv_len;
+        p[j][e] = ok ? sc[j][e] * scale_log2 : -INFINITY;
+        tmax = fmaxf(tmax, p[j][e]);
+      }
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+    const bool grow = tmax > m;
+    if (__any_sync(0xffffffffu, grow)) {
+      const float alpha = grow ? exp2f(m - tmax) : 1.f;  // m = -inf -> 0 (nothing accumulated yet)
+      if (grow) m = tmax;
+      l *= alpha;
+#pragma unroll
+      for (int n = 0; n < D / 8; ++n) o[n][0] *= alpha, o[n][1] *= alpha;
+    }
+    const float mu = m == -INFINITY ? 0.f : m;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        p[j][e] = exp2f(p[j][e] - mu);
+        l += p[j][e];
+      }
+    const uint32_t pa0 = pack_bf16x2(p[0][0], p[0][1]);  // A[g][kv 2qd..]   of the 16 x 16 P block
+    const uint32_t pa2 = pack_bf16x2(p[1][0], p[1][1]);  // A[g][kv 8+2qd..]
+
+    // ---- O[g][d] += P[g][kv] V[kv][d]: V^T fragments straight from the [kv][d] rows (ldmatrix.trans) ----
+#pragma unroll
+    for (int n2 = 0; n2 < D / 16; ++n2) {
+      const int c = n2 * 2 + vch;
+      uint32_t b00, b01, b10, b11;
+      ldmatrix_x4_trans(sV + (c >> 3) * TILE_ROWS * 128 + sw128_offset(vrow, c & 7), b00, b01, b10, b11);
+      mma_16816(o[n2 * 2], pa0, pa2, b00, b01);
+      mma_16816(o[n2 * 2 + 1], pa0, pa2, b10, b11);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
   }
-  __syncthreads();
-  // partial record per (b, hkv, split, g): [m, l, acc[D]]
+
+  // ---- merge the eight warp states: red[w][g] = {m, l}, acc[w][g][d] (the ring is drained: reuse it) ----
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS * 32) : "memory");
+  float* red_ml = reinterpret_cast<float*>(smem);                       // [CONSUMERS][MAX_G][2]
+  float* red_o = red_ml + CONSUMERS * MAX_G * 2;                        // [CONSUMERS][MAX_G][D]
+  if (qd == 0) {
+    red_ml[(warp * MAX_G + g) * 2] = m;
+    red_ml[(warp * MAX_G + g) * 2 + 1] = l;
+  }
+#pragma unroll
+  for (int n = 0; n < D / 8; ++n)
+    *reinterpret_cast<float2*>(red_o + (warp * MAX_G + g) * D + n * 8 + qd * 2) = make_float2(o[n][0], o[n][1]);
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS * 32) : "memory");
+  // partial record per (b, hkv, split, head): [m, l, acc[D]]
   float* out = partial + ((static_cast<long long>(b) * Hkv + hkv) * nsplit + split) * G * (D + 2);
-  for (int i = tid; i < G * D; i += THREADS) {
-    const int g = i / D, d = i % D;
-    float s = 0.f;
+  for (int i = tid; i < G * D; i += CONSUMERS * 32) {
+    const int gg = i / D, d = i % D;
+    float M = -INFINITY;
 #pragma unroll
-    for (int x = 0; x < GROUPS; ++x) s += red[(x * MAX_G + g) * D + d];
-    out[g * (D + 2) + 2 + d] = s;
-  }
-  if (tid < G) {
-    out[tid * (D + 2)] = s_m[tid];
-    out[tid * (D + 2) + 1] = s_l[tid];
+    for (int w = 0; w < CONSUMERS; ++w) M = fmaxf(M, red_ml[(w * MAX_G + gg) * 2]);
+    float acc = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < CONSUMERS; ++w) {
+      const float mw = red_ml[(w * MAX_G + gg) * 2];
+      const float sc = mw == -INFINITY ? 0.f : exp2f(mw - M);
+      acc = fmaf(sc, red_o[(w * MAX_G + gg) * D + d], acc);
+      den = fmaf(sc, red_ml[(w * MAX_G + gg) * 2 + 1], den);
+    }
+    out[gg * (D + 2) + 2 + d] = acc;
+    if (d == 0) {
+      out[gg * (D + 2)] = M;
+      out[gg * (D + 2) + 1] = den;
+    }
   }
 }
 
@@ -220,17 +255,48 @@ decode_merge_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict
   out[(static_cast<long long>(b) * H + h) * D + d] = __float2bfloat16(num / den);
 }
 
-inline void split_plan(int B, int Hkv, int kv_len, int* nsplit, int* rows_per_split) {
-  int want = (2 * 148 + B * Hkv - 1) / (B * Hkv);             // ~2 CTAs per SM in flight
-  int by_len = (kv_len + 4 * TILE_ROWS - 1) / (4 * TILE_ROWS);  // at least 256 rows per CTA
-  int n = want < by_len ? want : by_len;
-  if (n < 1) n = 1;
-  int rows = (kv_len + n - 1) / n;
-  rows = (rows + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
-  if (rows > MAX_CHUNK) rows = MAX_CHUNK;
-  n = (kv_len + rows - 1) / rows;
-  *nsplit = n;
-  *rows_per_split = rows;
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+// One CTA per SM (the ring takes the whole shared memory): as many splits as fill the SMs once, never more than tiles.
+inline int split_count(int B, int Hkv, int kv_len) {
+  int n = sm_count() / (B * Hkv);
+  const int tiles = (kv_len + TILE_ROWS - 1) / TILE_ROWS;
+  if (n > tiles) n = tiles;
+  return n < 1 ? 1 : n;
+}
+
+int make_kv_map(CUtensorMap* m, const void* base, int D, int rows, int heads, int B, int64_t s_l, int64_t s_h, int64_t s_b) {
+  uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(rows), static_cast<uint64_t>(heads),
+                      static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {static_cast<uint64_t>(s_l) * 2, static_cast<uint64_t>(s_h) * 2,
+                         static_cast<uint64_t>(s_b > 0 ? s_b : s_l * rows) * 2};
+  uint32_t box[4] = {64, TILE_ROWS, 1, 1};
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box);
+}
+
+template <int D>
+int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloat16* q, int64_t sq_b, int64_t sq_h,
+                  float* part, __nv_bfloat16* out, int B, int H, int Hkv, int kv_len, int nsplit, float sl2,
+                  const int32_t* kv_len_dev, cudaStream_t st) {
+  static bool cfg = false;
+  if (!cfg) {
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(decode_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       DecodeSmem<D>::kTotal));
+    cfg = true;
+  }
+  decode_split_kernel<D><<<dim3(nsplit, Hkv, B), THREADS, DecodeSmem<D>::kTotal, st>>>(tk, tv, q, sq_b, sq_h, part, H, Hkv,
+                                                                                      kv_len, sl2, kv_len_dev);
+  SDAG_CUDA_TRY(cudaGetLastError());
+  decode_merge_kernel<D><<<dim3(H, B), D, 0, st>>>(part, out, H, Hkv, nsplit);
+  return static_cast<int>(cudaGetLastError());
 }
 
 }  // namespace
@@ -239,8 +305,8 @@ extern "C" {
 
 size_t sdag_decode_workspace_bytes(int B, int H, int D, int kv_len) {
   if (B <= 0 || H <= 0 || D <= 0 || kv_len <= 0) return 0;
-  // worst case over Hkv: nsplit is bounded by kv_len / TILE_ROWS + 1
-  const size_t max_split = static_cast<size_t>(kv_len) / TILE_ROWS + 1;
+  // worst case over Hkv (Hkv = 1 gives the most splits per head): one (m, l, acc[D]) record per head and split
+  const size_t max_split = static_cast<size_t>(split_count(1, 1, kv_len));
   return sizeof(float) * static_cast<size_t>(B) * H * max_split * (D + 2);
 }
 
@@ -252,42 +318,21 @@ int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h, const void* k, in
   if (D != 64 && D != 128) return SDAG_ERR_UNSUPPORTED;
   if (H / Hkv > MAX_G) return SDAG_ERR_UNSUPPORTED;
   if ((sk_l % 8) || (sv_l % 8) || (sk_h % 8) || (sv_h % 8) || (sk_b % 8) || (sv_b % 8)) return SDAG_ERR_INVALID;
+  if ((sq_b % 2) || (sq_h % 2) || (reinterpret_cast<uintptr_t>(q) & 3)) return SDAG_ERR_INVALID;
   if ((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) return SDAG_ERR_INVALID;
-  int nsplit, rows;
-  split_plan(B, Hkv, kv_len, &nsplit, &rows);
+  const int nsplit = split_count(B, Hkv, kv_len);
   const size_t need = sizeof(float) * static_cast<size_t>(B) * H * nsplit * (D + 2);
   if (workspace_bytes < need) return SDAG_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float sl2 = scaling * 1.4426950408889634f;
-  const dim3 grid(nsplit, Hkv, B);
+  CUtensorMap tk, tv;
+  if (make_kv_map(&tk, k, D, kv_len, Hkv, B, sk_l, sk_h, sk_b)) return SDAG_ERR_DRIVER;
+  if (make_kv_map(&tv, v, D, kv_len, Hkv, B, sv_l, sv_h, sv_b)) return SDAG_ERR_DRIVER;
   auto* qq = static_cast<const __nv_bfloat16*>(q);
-  auto* kk = static_cast<const __nv_bfloat16*>(k);
-  auto* vv = static_cast<const __nv_bfloat16*>(v);
   float* part = static_cast<float*>(workspace);
-  if (D == 128) {
-    static bool cfg = false;
-    if (!cfg) {
-      SDAG_CUDA_TRY(cudaFuncSetAttribute(decode_split_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DecodeSmem<128>::kTotal));
-      cfg = true;
-    }
-    decode_split_kernel<128><<<grid, THREADS, DecodeSmem<128>::kTotal, st>>>(qq, sq_b, sq_h, kk, sk_b, sk_h, sk_l, vv, sv_b,
-                                                                             sv_h, sv_l, part, H, Hkv, kv_len, rows, sl2, kv_len_dev);
-    SDAG_CUDA_TRY(cudaGetLastError());
-    decode_merge_kernel<128><<<dim3(H, B), 128, 0, st>>>(part, static_cast<__nv_bfloat16*>(out), H, Hkv, nsplit);
-  } else {
-    static bool cfg = false;
-    if (!cfg) {
-      SDAG_CUDA_TRY(cudaFuncSetAttribute(decode_split_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DecodeSmem<64>::kTotal));
-      cfg = true;
-    }
-    decode_split_kernel<64><<<grid, THREADS, DecodeSmem<64>::kTotal, st>>>(qq, sq_b, sq_h, kk, sk_b, sk_h, sk_l, vv, sv_b,
-                                                                           sv_h, sv_l, part, H, Hkv, kv_len, rows, sl2, kv_len_dev);
-    SDAG_CUDA_TRY(cudaGetLastError());
-    decode_merge_kernel<64><<<dim3(H, B), 64, 0, st>>>(part, static_cast<__nv_bfloat16*>(out), H, Hkv, nsplit);
-  }
-  return static_cast<int>(cudaGetLastError());
+  auto* oo = static_cast<__nv_bfloat16*>(out);
+  if (D == 128) return launch_decode<128>(tk, tv, qq, sq_b, sq_h, part, oo, B, H, Hkv, kv_len, nsplit, sl2, kv_len_dev, st);
+  return launch_decode<64>(tk, tv, qq, sq_b, sq_h, part, oo, B, H, Hkv, kv_len, nsplit, sl2, kv_len_dev, st);
 }
 
 }  // extern "C"

@@ -36,6 +36,29 @@ def test_decode_attention_matches_oracle(S, H, Hkv, D, B):
         np.testing.assert_allclose(out[b, 0].float().cpu().numpy(), ref, atol=1e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("cap,lens,H,Hkv,D,B", [(4096, [1, 127, 128, 129, 2643, 4096], 32, 8, 128, 2),
+                                                (2048, [5, 1000, 2047], 14, 2, 64, 1)])
+def test_decode_attention_device_side_length(cap, lens, H, Hkv, D, B):
+    """CUDA-graph form of the call: the grid is sized for the capacity, the valid length is read from device memory.
+    Rows at or beyond the length hold NaN and must not leak into the result; every length must agree with the oracle."""
+    import sdag_b200.sdag as sdag
+
+    g = torch.Generator(device="cuda").manual_seed(cap)
+    q = torch.randn(B, H, 1, D, generator=g, device="cuda").to(torch.bfloat16)
+    k0 = torch.randn(B, Hkv, cap, D, generator=g, device="cuda").to(torch.bfloat16)
+    v0 = torch.randn(B, Hkv, cap, D, generator=g, device="cuda").to(torch.bfloat16)
+    n_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for n in lens:
+        kc, vc = k0.clone(), v0.clone()
+        kc[:, :, n:] = float("nan")
+        vc[:, :, n:] = float("nan")
+        n_dev.fill_(n)
+        out = sdag.sdag_decode_attention(q, kc, vc, D ** -0.5, kv_len_dev=n_dev)
+        ref = decode_attention_oracle(q[0, :, 0].float().cpu().numpy(), kc[0, :, :n].float().cpu().numpy(),
+                                      vc[0, :, :n].float().cpu().numpy(), D ** -0.5)
+        np.testing.assert_allclose(out[0, 0].float().cpu().numpy(), ref, atol=1e-2, rtol=1e-2, err_msg=f"len {n}")
+
+
 def _records(golden_dir):
     with open(os.path.join(golden_dir, "generation.json")) as f:
         return json.load(f)
