@@ -441,68 +441,85 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int q0 = it.q0;
       const int32_t* map = it.map;
       float m = -INFINITY, l = 0.f;
+      const uint32_t g_item0 = g;  // first sub-step of this item
       // with GQA packing the tile row splits into (head within the group, row within the query tile)
       const int rr = row & (it.R - 1);
       const int wrow0 = (quarter * 32) & (it.R - 1);  // first query-tile row handled by this warp
 
       bool first_sub = true;
+      int4 kt_next = it.kvt[0];
+#pragma unroll 1
       for (int j = 0; j < it.n_kv; ++j) {
-        const int4 kt = it.kvt[j];
+        const int4 kt = kt_next;
+        if (j + 1 < it.n_kv) kt_next = it.kvt[j + 1];  // descriptor of the next tile: off the dependency chain
         const bool bitmask = (kt.w & KV_FLAG_BITMASK) != 0;
-        uint32_t bits[4] = {0, 0, 0, 0};
-        if (bitmask && q0 + rr < p.Lq) {
-          const uint4 w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
-                                                          static_cast<long long>(q0 + rr) * map[7] + (kt.x >> 5));
-          bits[0] = w.x, bits[1] = w.y, bits[2] = w.z, bits[3] = w.w;
+        unsigned long long bits_lo = ~0ull, bits_hi = ~0ull;  // allow bits of columns [0,64) / [64,128) of the tile
+        if (bitmask) {
+          uint4 w = make_uint4(0u, 0u, 0u, 0u);
+          if (q0 + rr < p.Lq)
+            w = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
+                                                static_cast<long long>(q0 + rr) * map[7] + (kt.x >> 5));
+          bits_lo = w.x | (static_cast<unsigned long long>(w.y) << 32);
+          bits_hi = w.z | (static_cast<unsigned long long>(w.w) << 32);
         }
         const int nsub = kt.y > 64 ? 2 : 1;
+#pragma unroll 1
         for (int sub = 0; sub < nsub; ++sub, ++g) {
           const int ncols = min(64, kt.y - sub * 64);  // valid columns of this 64-column sub-step
           const int doff = kt.z - sub * 64;            // allowed: c <= r + doff (c relative to the sub-step)
-          int lim = min(ncols - 1, rr + doff);
-          // warp-uniform bounds of lim over the 32 rows of this warp: chunks at or below wlim_lo need no masking at
-          // all, chunks above wlim_hi hold no allowed column for any lane
-          int wlim_lo = min(ncols - 1, wrow0 + doff);
-          int wlim_hi = min(ncols - 1, wrow0 + 31 + doff);
-          if (bitmask) {
-            lim = ncols - 1;
-            wlim_lo = -1;  // every chunk takes the masked path
-            wlim_hi = ncols - 1;
-          }
-          const int nchunks = (ncols + 31) >> 5;
+          // this row: columns [0, lim] are allowed (lim < 0: none); bit-mask tiles carry no diagonal, only bits
+          const int lim = bitmask ? ncols - 1 : min(ncols - 1, rr + doff);
+          // warp-uniform bounds of lim over the 32 rows of this warp
+          const int wlim_lo = min(ncols - 1, wrow0 + doff);
+          const int wlim_hi = min(ncols - 1, wrow0 + 31 + doff);
+          const bool full = !bitmask && wlim_lo >= 63;   // every row of the warp sees all 64 columns: no masking
+          const bool none = !bitmask && wlim_hi < 0;     // no row of the warp sees any column
+          const bool dead1 = !bitmask && wlim_hi < 32;   // columns [32,64) are masked for every row of the warp
           const uint32_t tS = tmem_S + lane_addr + (g & 1) * 64;
           mbar_wait(&s_full[g & 1], (g >> 1) & 1);
           tc_fence_after();
           if (first_sub) STAMP(i, 1);
+          first_sub = false;
+          if (none) {
+            // P = 0 for these rows (the MMA still spans all 128 rows of the tile)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = 0u;
+            tmem_st_32x32b_x32(tS, r);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_full[g & 1]);
+            continue;
+          }
 
           // Single pass over the 64 scores of this sub-step: maximum over the allowed columns, keep the running
           // reference maximum m unless it is exceeded by more than RESCALE_TAU (then l and O, accumulated against
           // the old reference, are rescaled — rare), and write P = exp2(S*scale - m) as bf16 pairs over the first
-          // 32 columns of the same buffer.
-          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+          // 32 columns of the same buffer.  Columns that are not allowed are replaced by -inf up front, so the
+          // arithmetic below exists once.
           tmem_ld_32x32b_x32(tS, r);
-          if (nchunks > 1) tmem_ld_32x32b_x32(tS + 32, r2);
+          if (!dead1) tmem_ld_32x32b_x32(tS + 32, r2);
           tmem_ld_wait();
+          if (!full) {
+            unsigned long long allow = lim < 0 ? 0ull : (lim >= 63 ? ~0ull : ((2ull << lim) - 1ull));
+            allow &= sub ? bits_hi : bits_lo;
+            const uint32_t alo = static_cast<uint32_t>(allow), ahi = static_cast<uint32_t>(allow >> 32);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              r[e] = (alo >> e) & 1u ? r[e] : 0xff800000u;
+              r2[e] = (ahi >> e) & 1u ? r2[e] : 0xff800000u;
+            }
+          }
           float mxa = -INFINITY, mxb = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t* cur = c ? r2 : r;
-            if (c < nchunks && wlim_hi >= c * 32) {
-              if (wlim_lo >= c * 32 + 31) {
+          for (int e = 0; e < 32; e += 4) {
+            mxa = fmax3(mxa, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+            mxb = fmax3(mxb, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+          }
+          if (!dead1) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                  mxa = fmax3(mxa, __uint_as_float(cur[e]), __uint_as_float(cur[e + 1]));
-                  mxb = fmax3(mxb, __uint_as_float(cur[e + 2]), __uint_as_float(cur[e + 3]));
-                }
-              } else {
-                const uint32_t bw = bitmask ? bits[sub * 2 + c] : 0xffffffffu;
-                const int rel = lim - c * 32;  // columns e <= rel are allowed
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                  const bool ok = (e <= rel) && ((bw >> e) & 1u);
-                  mxa = fmaxf(mxa, ok ? __uint_as_float(cur[e]) : -INFINITY);
-                }
-              }
+            for (int e = 0; e < 32; e += 4) {
+              mxa = fmax3(mxa, __uint_as_float(r2[e]), __uint_as_float(r2[e + 1]));
+              mxb = fmax3(mxb, __uint_as_float(r2[e + 2]), __uint_as_float(r2[e + 3]));
             }
           }
           const float mx = fmaxf(mxa, mxb) * p.scale_log2;
@@ -511,11 +528,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const float alpha = need ? exp2f(m - mx) : 1.f;
             if (need) m = mx;
             l *= alpha;
-            if (!first_sub) {
-              // O holds the P.V of every earlier sub-step; the latest one may still be in flight
+            if (g != g_item0) {
+              // O holds the P.V of every earlier sub-step of this item; the latest one may still be in flight
               mbar_wait(&pv_done, (g - 1) & 1);
               tc_fence_after();
               uint32_t t[32];
+#pragma unroll 1
               for (int oc = 0; oc < D / 32; ++oc) {
                 tmem_ld_32x32b_x32(tmem_O + lane_addr + oc * 32, t);
                 tmem_ld_wait();
@@ -528,52 +546,43 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float neg_m = (m == -INFINITY) ? 0.f : -m;
           const unsigned long long scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(neg_m, neg_m);
           unsigned long long lsA = pack2(0.f, 0.f), lsB = lsA;
+          uint32_t pk[32];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const uint32_t* cur = c ? r2 : r;
-            if (c < nchunks) {
-              uint32_t pk[16];
-              if (wlim_hi < c * 32) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) pk[e] = 0u;
-              } else if (wlim_lo >= c * 32 + 31) {
-#pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                  float x0, x1, x2, x3;
-                  unpack2(fma2(pack2u(cur[e], cur[e + 1]), scale2, negm2), x0, x1);
-                  unpack2(fma2(pack2u(cur[e + 2], cur[e + 3]), scale2, negm2), x2, x3);
-                  const float p0 = exp2f(x0), p1 = exp2f(x1), p2 = exp2f(x2), p3 = exp2f(x3);
-                  lsA = add2(lsA, pack2(p0, p1));
-                  lsB = add2(lsB, pack2(p2, p3));
-                  pk[e >> 1] = pack_bf16x2(p0, p1);
-                  pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
-                }
-              } else {
-                const uint32_t bw = bitmask ? bits[sub * 2 + c] : 0xffffffffu;
-                const int rel = lim - c * 32;
-#pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                  const bool ok0 = (e <= rel) && ((bw >> e) & 1u);
-                  const bool ok1 = (e + 1 <= rel) && ((bw >> (e + 1)) & 1u);
-                  const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(cur[e]), p.scale_log2, neg_m)) : 0.f;
-                  const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(cur[e + 1]), p.scale_log2, neg_m)) : 0.f;
-                  l0 += p0, l1 += p1;
-                  pk[e >> 1] = pack_bf16x2(p0, p1);
-                }
-              }
-              tmem_st_32x32b_x16(tS + c * 16, pk);  // both S chunks are already in registers
-            }
+          for (int e = 0; e < 32; e += 4) {
+            float x0, x1, x2, x3;
+            unpack2(fma2(pack2u(r[e], r[e + 1]), scale2, negm2), x0, x1);
+            unpack2(fma2(pack2u(r[e + 2], r[e + 3]), scale2, negm2), x2, x3);
+            const float p0 = exp2f(x0), p1 = exp2f(x1), p2 = exp2f(x2), p3 = exp2f(x3);
+            lsA = add2(lsA, pack2(p0, p1));
+            lsB = add2(lsB, pack2(p2, p3));
+            pk[e >> 1] = pack_bf16x2(p0, p1);
+            pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
           }
+          if (!dead1) {
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              float x0, x1, x2, x3;
+              unpack2(fma2(pack2u(r2[e], r2[e + 1]), scale2, negm2), x0, x1);
+              unpack2(fma2(pack2u(r2[e + 2], r2[e + 3]), scale2, negm2), x2, x3);
+              const float p0 = exp2f(x0), p1 = exp2f(x1), p2 = exp2f(x2), p3 = exp2f(x3);
+              lsA = add2(lsA, pack2(p0, p1));
+              lsB = add2(lsB, pack2(p2, p3));
+              pk[16 + (e >> 1)] = pack_bf16x2(p0, p1);
+              pk[16 + (e >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+          } else {
+#pragma unroll
+            for (int e = 16; e < 32; ++e) pk[e] = 0u;
+          }
+          tmem_st_32x32b_x32(tS, pk);
           {
-            float a0, a1, b0, b1;
+            float a0, a1;
             unpack2(add2(lsA, lsB), a0, a1);
-            (void)b0, (void)b1;
-            l += (l0 + l1) + (l2 + l3) + (a0 + a1);
+            l += a0 + a1;
           }
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&p_full[g & 1]);
-          first_sub = false;
         }
       }
 

@@ -89,11 +89,13 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  const long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity, 20000u)) {
     if (clock64() - t0 > SDAG_SPIN_TRAP_CYCLES) {
+#ifdef SDAG_DEBUG_WAITS
       printf("sdag_b200: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
