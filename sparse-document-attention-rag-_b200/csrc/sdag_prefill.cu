@@ -107,6 +107,39 @@ __device__ __forceinline__ unsigned long long gtime() {
 #endif
 
 #ifdef SDAG_DEBUG_TIMING
+// Sub-step trace (bring-up only): the first TRACE_CTAS CTAs record (clock64 << 8 | event) for softmax warp 0
+// (role 0) and the MMA issuer (role 1); slot 0 of each role holds %smid.
+constexpr int TRACE_CTAS = 8, TRACE_EV = 8192;
+__device__ unsigned long long* g_trace = nullptr;
+struct Tracer {
+  unsigned long long* base;
+  int n;
+  __device__ __forceinline__ void init(int role, bool on) {
+    base = (g_trace && on && blockIdx.x < TRACE_CTAS) ? g_trace + (blockIdx.x * 2 + role) * static_cast<long long>(TRACE_EV) : nullptr;
+    n = 1;
+    if (base) {
+      uint32_t sm;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(sm));
+      base[0] = sm;
+    }
+  }
+  __device__ __forceinline__ void ev(int e) {
+    if (base && n < TRACE_EV) base[n++] = (static_cast<unsigned long long>(clock64()) << 8) | static_cast<unsigned>(e);
+  }
+};
+#define TRACE_INIT(tr, role, on) tr.init(role, on)
+#define TRACE(tr, e) tr.ev(e)
+#else
+struct Tracer {};
+#define TRACE_INIT(tr, role, on) \
+  do {                          \
+  } while (0)
+#define TRACE(tr, e) \
+  do {               \
+  } while (0)
+#endif
+
+#ifdef SDAG_DEBUG_TIMING
 __device__ __forceinline__ bool g_timing_enabled() { return g_timing != nullptr; }
 __device__ __forceinline__ void g_timing_write(long long item, int slot, long long v) { g_timing[item * 8ull + slot] = v; }
 #else
@@ -172,7 +205,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = sQ + Smem<D>::kQ;
   uint8_t* sV = sK + Smem<D>::kK;
   uint8_t* sStage = sV + Smem<D>::kV;
-  __shared__ uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done, o_full, o_empty;
+  __shared__ uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_free, p_full[2], p_empty[2], pv_done, o_full, o_empty;
   __shared__ uint64_t sched_full[2], sched_empty[2];
   __shared__ long long sched_item[2];
   __shared__ uint32_t tmem_base_s;
@@ -188,9 +221,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&v_full[x], 1);
       mbar_init(&v_empty[x], 1);
     }
+    mbar_init(&s_full, 1);
+    mbar_init(&s_free, 4);  // one arrival per softmax warp once its rows of S are in registers
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1);
       mbar_init(&p_full[x], 128);
+      mbar_init(&p_empty[x], 1);
     }
     mbar_init(&pv_done, 1);
     mbar_init(&o_full, 1);
@@ -214,9 +249,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  // TMEM columns: two 64-column score buffers S0 / S1 (P, as bf16 pairs, is written over the first 32 columns of
-  // the buffer it came from), then the fp32 output accumulator (D columns).
+  // TMEM columns: one 64-column score buffer S, two 32-column probability buffers P0 / P1 (bf16 pairs), then the
+  // fp32 output accumulator (D columns).  S is free again as soon as the softmax warps hold it in registers, so the
+  // next Q.K^T never waits for a P.V.
   const uint32_t tmem_S = tmem;
+  const uint32_t tmem_P = tmem + 64;
   const uint32_t tmem_O = tmem + 128;
 
   if (warp >= 4) {
@@ -317,11 +354,13 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 5) {
     // ======================= MMA issuer =======================
-    // Each 128-column kv tile is processed as one or two 64-column sub-steps.  Scores of sub-step g go to S[g & 1],
-    // so QK^T of sub-steps g+1 / g+2 is issued before the softmax of g has finished: issue order is
-    //   QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...   (QK(g+2) overwrites the buffer whose P was consumed by PV(g)).
+    // Each 128-column kv tile is processed as one or two 64-column sub-steps.  QK^T of sub-step g+1 is issued as soon
+    // as the softmax warps have pulled S(g) into registers (s_free), i.e. it runs underneath the softmax of g; P(g)
+    // goes to P[g & 1] and P.V(g) follows when it is complete:   QK(0) | QK(1) PV(0) | QK(2) PV(1) | ...
     uint32_t nq = 0;           // items with tensor work done so far
     uint32_t gq = 0, gp = 0;   // QK / PV sub-steps issued so far (S-buffer index and phases)
+    Tracer tr;
+    TRACE_INIT(tr, 1, lane == 0);
     for (uint32_t ns = 0;; ++ns) {
       const uint32_t slot = ns & 1;
       mbar_wait(&sched_full[slot], (ns >> 1) & 1);
@@ -333,27 +372,35 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&q_full, nq & 1);
       int qj = 0, qs = 0, pj = 0, ps = 0;  // cursors: (tile, sub-step) of the next QK / PV to issue
       bool first_pv = true;
+      const uint64_t descQ0 = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t descK0 = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t descV0 = umma_smem_desc_sw128(smem_u32(sV), 64 * 128, 1024);
 
       auto issue_qk = [&]() {
         const int ncols = it.kvt[qj].y;
         const int nsub = ncols > 64 ? 2 : 1;
         const int sub_cols = min(64, ncols - qs * 64);
-        const uint32_t slot = gq & 1;  // K ring slot == S buffer index: both advance once per sub-step
-        mbar_wait(&k_full[slot], (gq >> 1) & 1);
+        const uint32_t slot = gq & 1;  // K ring slot
+        TRACE(tr, 10);
+        if (gq > 0) mbar_wait_spin(&s_free, (gq - 1) & 1);
+        TRACE(tr, 11);
+        mbar_wait_spin(&k_full[slot], (gq >> 1) & 1);
+        TRACE(tr, 12);
         tc_fence_after();
         const bool last_sub = qs == nsub - 1;
-        if (lane == 0) {
-          const uint32_t idesc = umma_idesc_bf16_f32(BM, static_cast<uint32_t>((sub_cols + 15) & ~15), 0, 0);
+        // descriptors are built in warp-uniform code (uniform registers); only the issue itself is single-lane
+        const uint32_t idesc = umma_idesc_bf16_f32(BM, static_cast<uint32_t>((sub_cols + 15) & ~15), 0, 0);
+        const uint64_t dk = descK0 + ((slot * (Smem<D>::kK / 2)) >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t off = (ks >> 2) * (BM * 128) + (ks & 3) * 32;
-            const uint32_t offk = slot * (Smem<D>::kK / 2) + (ks >> 2) * (64 * 128) + (ks & 3) * 32;
-            umma_ss(tmem_S + slot * 64, umma_smem_desc_sw128(smem_u32(sQ) + off, 16, 1024),
-                    umma_smem_desc_sw128(smem_u32(sK) + offk, 16, 1024), idesc, ks > 0);
+            const uint32_t offk = (ks >> 2) * (64 * 128) + (ks & 3) * 32;
+            umma_ss(tmem_S, descQ0 + (off >> 4), dk + (offk >> 4), idesc, ks > 0);
           }
           umma_commit(&k_empty[slot]);                               // K half consumed -> producer may refill the slot
           if (last_sub && qj == it.n_kv - 1) umma_commit(&q_empty);  // Q consumed -> next item's Q may load
-          umma_commit(&s_full[slot]);
+          umma_commit(&s_full);
         }
         __syncwarp();
         ++gq;
@@ -369,20 +416,24 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int nsub = ncols > 64 ? 2 : 1;
         const int sub_cols = min(64, ncols - ps * 64);
         const uint32_t slot = gp & 1;
-        mbar_wait(&p_full[slot], (gp >> 1) & 1);
-        mbar_wait(&v_full[slot], (gp >> 1) & 1);
+        TRACE(tr, 20);
+        mbar_wait_spin(&p_full[slot], (gp >> 1) & 1);
+        TRACE(tr, 21);
+        mbar_wait_spin(&v_full[slot], (gp >> 1) & 1);
+        TRACE(tr, 22);
         if (first_pv && nq > 0) mbar_wait(&o_empty, (nq - 1) & 1);  // previous item's epilogue has read O out of TMEM
         tc_fence_after();
         const bool last_sub = ps == nsub - 1;
-        if (lane == 0) {
-          const uint32_t idesc = umma_idesc_bf16_f32(BM, D, 0, 1);  // B = V, MN-major
-          const int pv_steps = (sub_cols + 15) >> 4;
-          for (int ks = 0; ks < pv_steps; ++ks) {
-            umma_ts(tmem_O, tmem_S + slot * 64 + ks * 8,
-                    umma_smem_desc_sw128(smem_u32(sV) + slot * (Smem<D>::kV / 2) + ks * 16 * 128, 64 * 128, 1024), idesc,
-                    (!first_pv || ks > 0) ? 1u : 0u);
-          }
+        constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, D, 0, 1);  // B = V, MN-major
+        const int pv_steps = (sub_cols + 15) >> 4;
+        const uint64_t dv = descV0 + ((slot * (Smem<D>::kV / 2)) >> 4);
+        const uint32_t tP = tmem_P + slot * 32;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            if (ks < pv_steps) umma_ts(tmem_O, tP + ks * 8, dv + ((ks * 16 * 128) >> 4), idesc, (!first_pv || ks > 0) ? 1u : 0u);
           umma_commit(&v_empty[slot]);
+          umma_commit(&p_empty[slot]);
           umma_commit(&pv_done);
           if (last_sub && pj == it.n_kv - 1) umma_commit(&o_full);
         }
@@ -398,10 +449,9 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       };
 
       issue_qk();
-      if (qj < it.n_kv) issue_qk();
       while (pj < it.n_kv) {
-        issue_pv();
         if (qj < it.n_kv) issue_qk();
+        issue_pv();
       }
       ++nq;
     }
@@ -415,6 +465,8 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t r[32], r2[32];
     uint32_t nq = 0, g = 0;  // items with tensor work / 64-column sub-steps processed so far
+    Tracer tr;
+    TRACE_INIT(tr, 0, tid == 0);
 
     for (uint32_t ns = 0;; ++ns) {
       const uint32_t slot = ns & 1;
@@ -475,16 +527,23 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const bool full = !bitmask && wlim_lo >= 63;   // every row of the warp sees all 64 columns: no masking
           const bool none = !bitmask && wlim_hi < 0;     // no row of the warp sees any column
           const bool dead1 = !bitmask && wlim_hi < 32;   // columns [32,64) are masked for every row of the warp
-          const uint32_t tS = tmem_S + lane_addr + (g & 1) * 64;
-          mbar_wait(&s_full[g & 1], (g >> 1) & 1);
+          const uint32_t tS = tmem_S + lane_addr;
+          const uint32_t tP = tmem_P + lane_addr + (g & 1) * 32;
+          TRACE(tr, 1);
+          mbar_wait_spin(&s_full, g & 1);
+          TRACE(tr, 2);
           tc_fence_after();
           if (first_sub) STAMP(i, 1);
           first_sub = false;
           if (none) {
             // P = 0 for these rows (the MMA still spans all 128 rows of the tile)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free);
 #pragma unroll
             for (int e = 0; e < 32; ++e) r[e] = 0u;
-            tmem_st_32x32b_x32(tS, r);
+            if (g >= 2) mbar_wait(&p_empty[g & 1], ((g >> 1) - 1) & 1);
+            tc_fence_after();
+            tmem_st_32x32b_x32(tP, r);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_full[g & 1]);
@@ -499,6 +558,10 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_ld_32x32b_x32(tS, r);
           if (!dead1) tmem_ld_32x32b_x32(tS + 32, r2);
           tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free);  // S is in registers: the next Q.K^T may overwrite it
+          TRACE(tr, 3);
           if (!full) {
             unsigned long long allow = lim < 0 ? 0ull : (lim >= 63 ? ~0ull : ((2ull << lim) - 1ull));
             allow &= sub ? bits_hi : bits_lo;
@@ -574,7 +637,9 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int e = 16; e < 32; ++e) pk[e] = 0u;
           }
-          tmem_st_32x32b_x32(tS, pk);
+          if (g >= 2) mbar_wait(&p_empty[g & 1], ((g >> 1) - 1) & 1);  // P.V(g - 2) has consumed this buffer (long ago)
+          tc_fence_after();
+          tmem_st_32x32b_x32(tP, pk);
           {
             float a0, a1;
             unpack2(add2(lsA, lsB), a0, a1);
@@ -583,6 +648,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&p_full[g & 1]);
+          TRACE(tr, 4);
         }
       }
 
@@ -740,6 +806,9 @@ extern "C" {
 #ifdef SDAG_DEBUG_TIMING
 int sdag_debug_set_timing(unsigned long long* buf) {
   return static_cast<int>(cudaMemcpyToSymbol(g_timing, &buf, sizeof(buf)));
+}
+int sdag_debug_set_trace(unsigned long long* buf) {  // TRACE_CTAS * 2 * TRACE_EV entries
+  return static_cast<int>(cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)));
 }
 #endif
 

@@ -101,6 +101,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Latency-critical handoffs (the S / P ping-pong between the MMA issuer and the softmax warps): poll with the plain
+// try_wait, which the hardware already blocks for a bounded time, instead of suspending on a timer.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+#ifdef SDAG_NO_SPIN_WAITS
+  mbar_wait(bar, parity);
+#else
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > SDAG_SPIN_TRAP_CYCLES) __trap();
+  }
+#endif
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
