@@ -259,18 +259,27 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp >= 4) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
    if (warp == 4) {
-    // ======================= TMA producer =======================
-    if (lane == 0) {
+    // ======================= TMA producer (Q, K) + scheduler =======================
+    // The whole warp walks the loop (uniform control flow, uniform registers); single lanes are elected only to issue.
+    {
       uint32_t nq = 0, nk = 0;  // loads issued so far per buffer
       // Dynamic longest-first scheduling: the first item is blockIdx.x, later ones come from a global counter; the
       // producer publishes each item index to the other roles through a two-slot ring (so it can run one item ahead).
+      auto next_index = [&]() {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(p.next_item, 1);
+        return static_cast<long long>(gridDim.x) + __shfl_sync(0xffffffffu, t, 0);
+      };
       long long i = blockIdx.x;
-      long long i_next = static_cast<long long>(gridDim.x) + atomicAdd(p.next_item, 1);
+      long long i_next = next_index();
       for (uint32_t ns = 0;; ++ns) {
         const uint32_t slot = ns & 1;
         mbar_wait(&sched_empty[slot], ((ns >> 1) & 1) ^ 1);
-        sched_item[slot] = i < n_items ? i : -1;
-        mbar_arrive(&sched_full[slot]);
+        if (lane == 0) {
+          sched_item[slot] = i < n_items ? i : -1;
+          mbar_arrive(&sched_full[slot]);
+        }
+        __syncwarp();
         if (i >= n_items) break;
         const Item it = fetch_item(p, i);
         // The item after this one is already known: pull its Q and its first K / V halves into L2 now, so that the
@@ -278,35 +287,42 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (i_next < n_items) {
           const Item nx = fetch_item(p, i_next);
           if (nx.valid && nx.n_kv > 0) {
-            for (int g = 0; g < nx.pack; ++g)
-              for (int dh = 0; dh < D / 64; ++dh)
-                tma_prefetch_l2_4d(nx.pack == 1 ? &tmQ : (nx.pack == 2 ? &tmQ64 : &tmQ32), dh * 64, nx.q0, nx.h + g, nx.b);
+            const CUtensorMap* tmq = nx.pack == 1 ? &tmQ : (nx.pack == 2 ? &tmQ64 : &tmQ32);
+            if (elect_one()) {
+              for (int g = 0; g < nx.pack; ++g)
+                for (int dh = 0; dh < D / 64; ++dh) tma_prefetch_l2_4d(tmq, dh * 64, nx.q0, nx.h + g, nx.b);
+            }
             int halves = 0;
             for (int j = 0; j < nx.n_kv && halves < 6; ++j) {
               const int4 kt = nx.kvt[j];
-              for (int sub = 0; sub < (kt.y > 64 ? 2 : 1) && halves < 6; ++sub, ++halves)
-                for (int dh = 0; dh < D / 64; ++dh) {
-                  tma_prefetch_l2_4d(&tmK, dh * 64, kt.x + sub * 64, nx.hkv, nx.b);
-                  tma_prefetch_l2_4d(&tmV, dh * 64, kt.x + sub * 64, nx.hkv, nx.b);
+              for (int sub = 0; sub < (kt.y > 64 ? 2 : 1) && halves < 6; ++sub, ++halves) {
+                if (elect_one()) {
+                  for (int dh = 0; dh < D / 64; ++dh) {
+                    tma_prefetch_l2_4d(&tmK, dh * 64, kt.x + sub * 64, nx.hkv, nx.b);
+                    tma_prefetch_l2_4d(&tmV, dh * 64, kt.x + sub * 64, nx.hkv, nx.b);
+                  }
                 }
+              }
             }
           }
         }
         i = i_next;
-        i_next = static_cast<long long>(gridDim.x) + atomicAdd(p.next_item, 1);
+        i_next = next_index();
         if (!it.valid || it.n_kv == 0) continue;
         mbar_wait(&q_empty, (nq & 1) ^ 1);
-        mbar_expect_tx(&q_full, Smem<D>::kQ);
-        if (it.pack == 1) {
-          for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(sQ + dh * BM * 128, &tmQ, &q_full, dh * 64, it.q0, it.h, it.b);
-        } else {
-          const CUtensorMap* tm = it.pack == 2 ? &tmQ64 : &tmQ32;
-          for (int g = 0; g < it.pack; ++g)
-            for (int dh = 0; dh < D / 64; ++dh)
-              tma_load_4d(sQ + dh * BM * 128 + g * it.R * 128, tm, &q_full, dh * 64, it.q0, it.h + g, it.b);
+        {
+          const CUtensorMap* tm = it.pack == 1 ? &tmQ : (it.pack == 2 ? &tmQ64 : &tmQ32);
+          if (elect_one()) {
+            mbar_expect_tx(&q_full, Smem<D>::kQ);
+            for (int g = 0; g < it.pack; ++g)
+              for (int dh = 0; dh < D / 64; ++dh)
+                tma_load_4d(sQ + dh * BM * 128 + g * it.R * 128, tm, &q_full, dh * 64, it.q0, it.h + g, it.b);
+          }
         }
+        int4 kt_next = it.kvt[0];
         for (int j = 0; j < it.n_kv; ++j) {
-          const int4 kt = it.kvt[j];
+          const int4 kt = kt_next;
+          if (j + 1 < it.n_kv) kt_next = it.kvt[j + 1];
           const int nsub = kt.y > 64 ? 2 : 1;
           for (int sub = 0; sub < nsub; ++sub) {
             // K travels as 64-row halves through a two-slot ring, so the load of sub-step u+1 is in flight while
@@ -315,9 +331,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int k0 = kt.x + sub * 64;
             const uint32_t ks = nk & 1;
             mbar_wait(&k_empty[ks], ((nk >> 1) & 1) ^ 1);
-            mbar_expect_tx(&k_full[ks], Smem<D>::kK / 2);
-            for (int dh = 0; dh < D / 64; ++dh)
-              tma_load_4d(sK + ks * (Smem<D>::kK / 2) + dh * 64 * 128, &tmK, &k_full[ks], dh * 64, k0, it.hkv, it.b);
+            if (elect_one()) {
+              mbar_expect_tx(&k_full[ks], Smem<D>::kK / 2);
+              for (int dh = 0; dh < D / 64; ++dh)
+                tma_load_4d(sK + ks * (Smem<D>::kK / 2) + dh * 64 * 128, &tmK, &k_full[ks], dh * 64, k0, it.hkv, it.b);
+            }
             ++nk;
           }
         }
@@ -326,30 +344,33 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 6) {
     // ======================= TMA producer for V =======================
-    if (lane == 0) {
-      uint32_t nq = 0, nv = 0;
+    {
+      uint32_t nv = 0;
       for (uint32_t ns = 0;; ++ns) {
         const uint32_t slot = ns & 1;
         mbar_wait(&sched_full[slot], (ns >> 1) & 1);
         const long long i = sched_item[slot];
-        mbar_arrive(&sched_empty[slot]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sched_empty[slot]);
         if (i < 0) break;
         const Item it = fetch_item(p, i);
         if (!it.valid || it.n_kv == 0) continue;
-        int sub_in_item = 0;
+        int4 kt_next = it.kvt[0];
         for (int j = 0; j < it.n_kv; ++j) {
-          const int4 kt = it.kvt[j];
+          const int4 kt = kt_next;
+          if (j + 1 < it.n_kv) kt_next = it.kvt[j + 1];
           const int nsub = kt.y > 64 ? 2 : 1;
-          for (int sub = 0; sub < nsub; ++sub, ++sub_in_item) {
+          for (int sub = 0; sub < nsub; ++sub) {
             const uint32_t vs = nv & 1;
             mbar_wait(&v_empty[vs], ((nv >> 1) & 1) ^ 1);
-            mbar_expect_tx(&v_full[vs], Smem<D>::kV / 2);
-            for (int dh = 0; dh < D / 64; ++dh)
-              tma_load_4d(sV + vs * (Smem<D>::kV / 2) + dh * 64 * 128, &tmV, &v_full[vs], dh * 64, kt.x + sub * 64, it.hkv, it.b);
+            if (elect_one()) {
+              mbar_expect_tx(&v_full[vs], Smem<D>::kV / 2);
+              for (int dh = 0; dh < D / 64; ++dh)
+                tma_load_4d(sV + vs * (Smem<D>::kV / 2) + dh * 64 * 128, &tmV, &v_full[vs], dh * 64, kt.x + sub * 64, it.hkv, it.b);
+            }
             ++nv;
           }
         }
-        ++nq;
       }
     }
   } else if (warp == 5) {
