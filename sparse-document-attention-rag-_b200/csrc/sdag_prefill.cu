@@ -205,7 +205,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = sQ + Smem<D>::kQ;
   uint8_t* sV = sK + Smem<D>::kK;
   uint8_t* sStage = sV + Smem<D>::kV;
-  __shared__ uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_free, p_full[2], p_empty[2], pv_done, o_full, o_empty;
+  __shared__ uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done, o_full, o_empty;
   __shared__ uint64_t sched_full[2], sched_empty[2];
   __shared__ long long sched_item[2];
   __shared__ uint32_t tmem_base_s;
@@ -221,11 +221,9 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&v_full[x], 1);
       mbar_init(&v_empty[x], 1);
     }
-    mbar_init(&s_full, 1);
-    mbar_init(&s_free, 4);  // one arrival per softmax warp once its rows of S are in registers
     for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1);
       mbar_init(&p_full[x], 128);
-      mbar_init(&p_empty[x], 1);
     }
     mbar_init(&pv_done, 1);
     mbar_init(&o_full, 1);
@@ -249,11 +247,9 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  // TMEM columns: one 64-column score buffer S, two 32-column probability buffers P0 / P1 (bf16 pairs), then the
-  // fp32 output accumulator (D columns).  S is free again as soon as the softmax warps hold it in registers, so the
-  // next Q.K^T never waits for a P.V.
+  // TMEM columns: two 64-column score buffers S0 / S1 (P, as bf16 pairs, is written over the first 32 columns of
+  // the buffer it came from), then the fp32 output accumulator (D columns).
   const uint32_t tmem_S = tmem;
-  const uint32_t tmem_P = tmem + 64;
   const uint32_t tmem_O = tmem + 128;
 
   if (warp >= 4) {
@@ -328,13 +324,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // K travels as 64-row halves through a two-slot ring, so the load of sub-step u+1 is in flight while
             // sub-step u is being computed — also across tile and item boundaries.  (V has its own producer warp:
             // its slots free up later, after P.V, and must not hold back the K loads.)
-            const int k0 = kt.x + sub * 64;
             const uint32_t ks = nk & 1;
             mbar_wait(&k_empty[ks], ((nk >> 1) & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(&k_full[ks], Smem<D>::kK / 2);
               for (int dh = 0; dh < D / 64; ++dh)
-                tma_load_4d(sK + ks * (Smem<D>::kK / 2) + dh * 64 * 128, &tmK, &k_full[ks], dh * 64, k0, it.hkv, it.b);
+                tma_load_4d(sK + ks * (Smem<D>::kK / 2) + dh * 64 * 128, &tmK, &k_full[ks], dh * 64, kt.x + sub * 64, it.hkv, it.b);
             }
             ++nk;
           }
@@ -375,9 +370,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else if (warp == 5) {
     // ======================= MMA issuer =======================
-    // Each 128-column kv tile is processed as one or two 64-column sub-steps.  QK^T of sub-step g+1 is issued as soon
-    // as the softmax warps have pulled S(g) into registers (s_free), i.e. it runs underneath the softmax of g; P(g)
-    // goes to P[g & 1] and P.V(g) follows when it is complete:   QK(0) | QK(1) PV(0) | QK(2) PV(1) | ...
+    // Each 128-column kv tile is processed as one or two 64-column sub-steps.  Scores of sub-step g go to S[g & 1],
+    // so Q.K^T of sub-steps g+1 / g+2 is issued before the softmax of g has finished: issue order is
+    //   QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...   (QK(g+2) overwrites the buffer whose P was consumed by PV(g);
+    // the tensor pipe executes in issue order).  Issue is cheap (uniform descriptors, elect.sync), so PV(g) + QK(g+2)
+    // fit underneath the softmax of g+1.
     uint32_t nq = 0;           // items with tensor work done so far
     uint32_t gq = 0, gp = 0;   // QK / PV sub-steps issued so far (S-buffer index and phases)
     Tracer tr;
@@ -393,18 +390,22 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&q_full, nq & 1);
       int qj = 0, qs = 0, pj = 0, ps = 0;  // cursors: (tile, sub-step) of the next QK / PV to issue
       bool first_pv = true;
+      int4 kt_q = make_int4(0, 0, 0, 0), kt_p = kt_q;
+      int4 kt_qnext = it.kvt[0], kt_pnext = kt_qnext;
       const uint64_t descQ0 = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t descK0 = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t descV0 = umma_smem_desc_sw128(smem_u32(sV), 64 * 128, 1024);
 
       auto issue_qk = [&]() {
-        const int ncols = it.kvt[qj].y;
+        if (qs == 0) {
+          kt_q = kt_qnext;
+          if (qj + 1 < it.n_kv) kt_qnext = it.kvt[qj + 1];
+        }
+        const int ncols = kt_q.y;
         const int nsub = ncols > 64 ? 2 : 1;
         const int sub_cols = min(64, ncols - qs * 64);
-        const uint32_t slot = gq & 1;  // K ring slot
+        const uint32_t slot = gq & 1;  // K ring slot == S buffer index: both advance once per sub-step
         TRACE(tr, 10);
-        if (gq > 0) mbar_wait_spin(&s_free, (gq - 1) & 1);
-        TRACE(tr, 11);
         mbar_wait_spin(&k_full[slot], (gq >> 1) & 1);
         TRACE(tr, 12);
         tc_fence_after();
@@ -412,16 +413,18 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // descriptors are built in warp-uniform code (uniform registers); only the issue itself is single-lane
         const uint32_t idesc = umma_idesc_bf16_f32(BM, static_cast<uint32_t>((sub_cols + 15) & ~15), 0, 0);
         const uint64_t dk = descK0 + ((slot * (Smem<D>::kK / 2)) >> 4);
+        const uint32_t tS = tmem_S + slot * 64;
+        const bool last_qk = last_sub && qj == it.n_kv - 1;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t off = (ks >> 2) * (BM * 128) + (ks & 3) * 32;
             const uint32_t offk = (ks >> 2) * (64 * 128) + (ks & 3) * 32;
-            umma_ss(tmem_S, descQ0 + (off >> 4), dk + (offk >> 4), idesc, ks > 0);
+            umma_ss(tS, descQ0 + (off >> 4), dk + (offk >> 4), idesc, ks > 0);
           }
-          umma_commit(&k_empty[slot]);                               // K half consumed -> producer may refill the slot
-          if (last_sub && qj == it.n_kv - 1) umma_commit(&q_empty);  // Q consumed -> next item's Q may load
-          umma_commit(&s_full);
+          umma_commit(&k_empty[slot]);         // K half consumed -> producer may refill the slot
+          if (last_qk) umma_commit(&q_empty);  // Q consumed -> next item's Q may load
+          umma_commit(&s_full[slot]);
         }
         __syncwarp();
         ++gq;
@@ -433,7 +436,11 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       };
       auto issue_pv = [&]() {
-        const int ncols = it.kvt[pj].y;
+        if (ps == 0) {
+          kt_p = kt_pnext;
+          if (pj + 1 < it.n_kv) kt_pnext = it.kvt[pj + 1];
+        }
+        const int ncols = kt_p.y;
         const int nsub = ncols > 64 ? 2 : 1;
         const int sub_cols = min(64, ncols - ps * 64);
         const uint32_t slot = gp & 1;
@@ -448,13 +455,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, D, 0, 1);  // B = V, MN-major
         const int pv_steps = (sub_cols + 15) >> 4;
         const uint64_t dv = descV0 + ((slot * (Smem<D>::kV / 2)) >> 4);
-        const uint32_t tP = tmem_P + slot * 32;
+        const uint32_t tP = tmem_S + slot * 64;
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
             if (ks < pv_steps) umma_ts(tmem_O, tP + ks * 8, dv + ((ks * 16 * 128) >> 4), idesc, (!first_pv || ks > 0) ? 1u : 0u);
           umma_commit(&v_empty[slot]);
-          umma_commit(&p_empty[slot]);
           umma_commit(&pv_done);
           if (last_sub && pj == it.n_kv - 1) umma_commit(&o_full);
         }
@@ -470,9 +476,10 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       };
 
       issue_qk();
+      if (qj < it.n_kv) issue_qk();
       while (pj < it.n_kv) {
-        if (qj < it.n_kv) issue_qk();
         issue_pv();
+        if (qj < it.n_kv) issue_qk();
       }
       ++nq;
     }
@@ -548,22 +555,18 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const bool full = !bitmask && wlim_lo >= 63;   // every row of the warp sees all 64 columns: no masking
           const bool none = !bitmask && wlim_hi < 0;     // no row of the warp sees any column
           const bool dead1 = !bitmask && wlim_hi < 32;   // columns [32,64) are masked for every row of the warp
-          const uint32_t tS = tmem_S + lane_addr;
-          const uint32_t tP = tmem_P + lane_addr + (g & 1) * 32;
+          const uint32_t tS = tmem_S + lane_addr + (g & 1) * 64;
+          const uint32_t tP = tS;
           TRACE(tr, 1);
-          mbar_wait_spin(&s_full, g & 1);
+          mbar_wait_spin(&s_full[g & 1], (g >> 1) & 1);
           TRACE(tr, 2);
           tc_fence_after();
           if (first_sub) STAMP(i, 1);
           first_sub = false;
           if (none) {
             // P = 0 for these rows (the MMA still spans all 128 rows of the tile)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free);
 #pragma unroll
             for (int e = 0; e < 32; ++e) r[e] = 0u;
-            if (g >= 2) mbar_wait(&p_empty[g & 1], ((g >> 1) - 1) & 1);
-            tc_fence_after();
             tmem_st_32x32b_x32(tP, r);
             tmem_st_wait();
             tc_fence_before();
@@ -579,9 +582,6 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_ld_32x32b_x32(tS, r);
           if (!dead1) tmem_ld_32x32b_x32(tS + 32, r2);
           tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free);  // S is in registers: the next Q.K^T may overwrite it
           TRACE(tr, 3);
           if (!full) {
             unsigned long long allow = lim < 0 ? 0ull : (lim >= 63 ? ~0ull : ((2ull << lim) - 1ull));
@@ -658,8 +658,6 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int e = 16; e < 32; ++e) pk[e] = 0u;
           }
-          if (g >= 2) mbar_wait(&p_empty[g & 1], ((g >> 1) - 1) & 1);  // P.V(g - 2) has consumed this buffer (long ago)
-          tc_fence_after();
           tmem_st_32x32b_x32(tP, pk);
           {
             float a0, a1;
