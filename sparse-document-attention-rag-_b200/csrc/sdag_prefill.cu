@@ -159,9 +159,9 @@ struct Item {
 // first and the G heads of a kv group run side by side (K/V shared through L2).
 __device__ __forceinline__ Item fetch_item(const PrefillParams& p, long long i) {
   Item it;
-  const int per_tile = p.H * p.B;
-  const int t = static_cast<int>(i / per_tile);
-  const int rem = static_cast<int>(i - static_cast<long long>(t) * per_tile);
+  const unsigned per_tile = static_cast<unsigned>(p.H * p.B), iu = static_cast<unsigned>(i);  // n_items < 2^31
+  const int t = static_cast<int>(iu / per_tile);
+  const int rem = static_cast<int>(iu - static_cast<unsigned>(t) * per_tile);
   it.b = rem / p.H;
   it.h = rem - it.b * p.H;
   it.hkv = it.h / (p.H / p.Hkv);
@@ -181,9 +181,30 @@ __device__ __forceinline__ Item fetch_item(const PrefillParams& p, long long i) 
       if (it.nrows <= 32 && (G % 4) == 0) it.pack = 4;
       else if (it.nrows <= 64 && (G % 2) == 0) it.pack = 2;
     }
-    it.R = BM / it.pack;
+    it.R = BM >> (it.pack >> 1);
     if (it.h % it.pack) it.valid = false;  // handled by the item of the group's first head
   }
+  return it;
+}
+
+// What the scheduler (producer warp) publishes per item: the decoded item and its first two kv tile descriptors, so
+// that the other roles start from shared memory instead of a chain of dependent global loads.
+struct __align__(16) SchedSlot {
+  int4 a;  // q0, nrows, n_kv, h
+  int4 b;  // b, hkv, pack, state (1 = valid item, 0 = nothing to do, -1 = stop)
+  int4 kv0, kv1;
+  const int4* kvt;
+  long long i;
+};
+
+__device__ __forceinline__ Item item_from_slot(const PrefillParams& p, const SchedSlot& sl) {
+  const int4 a = sl.a, b = sl.b;
+  Item it;
+  it.q0 = a.x, it.nrows = a.y, it.n_kv = a.z, it.h = a.w;
+  it.b = b.x, it.hkv = b.y, it.pack = b.z, it.valid = b.w == 1;
+  it.R = BM >> (it.pack >> 1);
+  it.kvt = sl.kvt;
+  it.map = p.blockmaps + static_cast<long long>(it.b) * p.bm_stride_ints;
   return it;
 }
 
@@ -207,7 +228,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sStage = sV + Smem<D>::kV;
   __shared__ uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done, o_full, o_empty;
   __shared__ uint64_t sched_full[2], sched_empty[2];
-  __shared__ long long sched_item[2];
+  __shared__ SchedSlot sched[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -270,14 +291,24 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       long long i_next = next_index();
       for (uint32_t ns = 0;; ++ns) {
         const uint32_t slot = ns & 1;
+        Item it;
+        it.valid = false, it.n_kv = 0, it.q0 = it.nrows = it.h = it.b = it.hkv = 0, it.pack = 1, it.R = BM, it.kvt = nullptr;
+        if (i < n_items) it = fetch_item(p, i);
+        int4 kv0 = make_int4(0, 0, 0, 0), kv1 = kv0;
+        if (it.valid && it.n_kv > 0) kv0 = it.kvt[0];
+        if (it.valid && it.n_kv > 1) kv1 = it.kvt[1];
         mbar_wait(&sched_empty[slot], ((ns >> 1) & 1) ^ 1);
         if (lane == 0) {
-          sched_item[slot] = i < n_items ? i : -1;
+          SchedSlot& sl = sched[slot];
+          sl.a = make_int4(it.q0, it.nrows, it.n_kv, it.h);
+          sl.b = make_int4(it.b, it.hkv, it.pack, i < n_items ? (it.valid ? 1 : 0) : -1);
+          sl.kv0 = kv0, sl.kv1 = kv1;
+          sl.kvt = it.kvt;
+          sl.i = i;
           mbar_arrive(&sched_full[slot]);
         }
         __syncwarp();
         if (i >= n_items) break;
-        const Item it = fetch_item(p, i);
         // The item after this one is already known: pull its Q and its first K / V halves into L2 now, so that the
         // ring loads issued a few microseconds from now do not pay HBM latency (short items are latency-bound).
         if (i_next < n_items) {
@@ -315,10 +346,10 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 tma_load_4d(sQ + dh * BM * 128 + g * it.R * 128, tm, &q_full, dh * 64, it.q0, it.h + g, it.b);
           }
         }
-        int4 kt_next = it.kvt[0];
+        int4 kt_next = kv0;
         for (int j = 0; j < it.n_kv; ++j) {
           const int4 kt = kt_next;
-          if (j + 1 < it.n_kv) kt_next = it.kvt[j + 1];
+          if (j + 1 < it.n_kv) kt_next = j == 0 ? kv1 : it.kvt[j + 1];
           const int nsub = kt.y > 64 ? 2 : 1;
           for (int sub = 0; sub < nsub; ++sub) {
             // K travels as 64-row halves through a two-slot ring, so the load of sub-step u+1 is in flight while
@@ -344,16 +375,17 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (uint32_t ns = 0;; ++ns) {
         const uint32_t slot = ns & 1;
         mbar_wait(&sched_full[slot], (ns >> 1) & 1);
-        const long long i = sched_item[slot];
+        const Item it = item_from_slot(p, sched[slot]);
+        const int state = sched[slot].b.w;
+        int4 kt_next = sched[slot].kv0;
+        const int4 kv1 = sched[slot].kv1;
         __syncwarp();
         if (lane == 0) mbar_arrive(&sched_empty[slot]);
-        if (i < 0) break;
-        const Item it = fetch_item(p, i);
+        if (state < 0) break;
         if (!it.valid || it.n_kv == 0) continue;
-        int4 kt_next = it.kvt[0];
         for (int j = 0; j < it.n_kv; ++j) {
           const int4 kt = kt_next;
-          if (j + 1 < it.n_kv) kt_next = it.kvt[j + 1];
+          if (j + 1 < it.n_kv) kt_next = j == 0 ? kv1 : it.kvt[j + 1];
           const int nsub = kt.y > 64 ? 2 : 1;
           for (int sub = 0; sub < nsub; ++sub) {
             const uint32_t vs = nv & 1;
@@ -382,16 +414,17 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (uint32_t ns = 0;; ++ns) {
       const uint32_t slot = ns & 1;
       mbar_wait(&sched_full[slot], (ns >> 1) & 1);
-      const long long i = sched_item[slot];
+      const Item it = item_from_slot(p, sched[slot]);
+      const int state = sched[slot].b.w;
+      const int4 kv0 = sched[slot].kv0, kv1 = sched[slot].kv1;
       mbar_arrive(&sched_empty[slot]);
-      if (i < 0) break;
-      const Item it = fetch_item(p, i);
+      if (state < 0) break;
       if (!it.valid || it.n_kv == 0) continue;
       mbar_wait(&q_full, nq & 1);
       int qj = 0, qs = 0, pj = 0, ps = 0;  // cursors: (tile, sub-step) of the next QK / PV to issue
       bool first_pv = true;
       int4 kt_q = make_int4(0, 0, 0, 0), kt_p = kt_q;
-      int4 kt_qnext = it.kvt[0], kt_pnext = kt_qnext;
+      int4 kt_qnext = kv0, kt_pnext = kv0;
       const uint64_t descQ0 = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t descK0 = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t descV0 = umma_smem_desc_sw128(smem_u32(sV), 64 * 128, 1024);
@@ -399,7 +432,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto issue_qk = [&]() {
         if (qs == 0) {
           kt_q = kt_qnext;
-          if (qj + 1 < it.n_kv) kt_qnext = it.kvt[qj + 1];
+          if (qj + 1 < it.n_kv) kt_qnext = qj == 0 ? kv1 : it.kvt[qj + 1];
         }
         const int ncols = kt_q.y;
         const int nsub = ncols > 64 ? 2 : 1;
@@ -438,7 +471,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       auto issue_pv = [&]() {
         if (ps == 0) {
           kt_p = kt_pnext;
-          if (pj + 1 < it.n_kv) kt_pnext = it.kvt[pj + 1];
+          if (pj + 1 < it.n_kv) kt_pnext = pj == 0 ? kv1 : it.kvt[pj + 1];
         }
         const int ncols = kt_p.y;
         const int nsub = ncols > 64 ? 2 : 1;
@@ -499,10 +532,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (uint32_t ns = 0;; ++ns) {
       const uint32_t slot = ns & 1;
       mbar_wait(&sched_full[slot], (ns >> 1) & 1);
-      const long long i = sched_item[slot];
+      const Item it = item_from_slot(p, sched[slot]);
+      const int state = sched[slot].b.w;
+      const long long i = sched[slot].i;
+      int4 kt_next = sched[slot].kv0;
       mbar_arrive(&sched_empty[slot]);
-      if (i < 0) break;
-      const Item it = fetch_item(p, i);
+      if (state < 0) break;
       if (!it.valid) continue;
       STAMP(i, 0);
       const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(it.b) * p.Hkv + it.hkv) * D;
@@ -527,7 +562,6 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int wrow0 = (quarter * 32) & (it.R - 1);  // first query-tile row handled by this warp
 
       bool first_sub = true;
-      int4 kt_next = it.kvt[0];
 #pragma unroll 1
       for (int j = 0; j < it.n_kv; ++j) {
         const int4 kt = kt_next;
@@ -673,6 +707,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
       // ---- epilogue: O / l -> bf16 -> staging rows in the (now idle) V buffer -> one bulk copy per row ----
       STAMP(i, 2);
+      TRACE(tr, 8);
       mbar_wait(&o_full, nq & 1);
       tc_fence_after();
       STAMP(i, 3);
@@ -684,6 +719,20 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint8_t* wbase = sStage + quarter * 32 * SROW;
       uint8_t* srow = wbase + lane * SROW;
       const int wr = lane >> 2, ch = lane & 3;  // write-out role: row within a group of 8, 16-byte chunk of the row
+      // destination of the four rows this lane writes out per 32-column round (nullptr: beyond the query tile)
+      __nv_bfloat16* orow[4];
+      {
+        const int rshift = 7 - (it.pack >> 1);  // log2(R)
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int trow = quarter * 32 + g8 * 8 + wr;  // tile row
+          const int orr = trow & (it.R - 1);
+          orow[g8] = orr < it.nrows ? p.out + it.b * p.so_b + static_cast<long long>(q0 + orr) * p.so_l +
+                                          (it.h + (trow >> rshift)) * p.so_h + ch * 8
+                                    : nullptr;
+        }
+      }
+      TRACE(tr, 5);
       tmem_ld_32x32b_x32(tmem_O + lane_addr, r);
 #pragma unroll
       for (int c = 0; c < D / 32; ++c) {
@@ -710,6 +759,7 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             o[(e >> 1) + 1] = pack_bf16x2(f.z, f.w);
           }
         }
+        TRACE(tr, 6);
         uint4* dst = reinterpret_cast<uint4*>(srow);
         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -718,16 +768,13 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
-          const int trow = quarter * 32 + g8 * 8 + wr;  // tile row
-          const int orr = trow & (it.R - 1);
-          if (orr < it.nrows) {
+          if (orow[g8]) {
             const uint4 val = *reinterpret_cast<const uint4*>(wbase + (g8 * 8 + wr) * SROW + ch * 16);
-            __nv_bfloat16* gp = p.out + it.b * p.so_b + static_cast<long long>(q0 + orr) * p.so_l +
-                                (it.h + trow / it.R) * p.so_h + c * 32 + ch * 8;
-            *reinterpret_cast<uint4*>(gp) = val;
+            *reinterpret_cast<uint4*>(orow[g8] + c * 32) = val;
           }
         }
         __syncwarp();
+        TRACE(tr, 7);
       }
       STAMP(i, 4);
       if (g_timing_enabled() && threadIdx.x == 0) g_timing_write(i, 5, it.n_kv), g_timing_write(i, 6, blockIdx.x);
