@@ -42,3 +42,16 @@ def inject_malicious_docs_into_ranked_list(
         if p == -1:
             out.insert(random.randint(0, len(out)), doc)
     return out
+
+
+def apply_ranked_list_order(ranked_docs: List[str], order_mode: str) -> List[str]:
+    """Presentation order of the ranked list in the prompt (src/pipeline/utils/ranked_list.py:113-139):
+    ``"bottom_up"`` reverses, ``"random"`` shuffles a copy with the global ``random`` state, anything else
+    (``"top_down"``) returns the list object itself."""
+    if order_mode == "bottom_up":
+        return ranked_docs[::-1]
+    if order_mode == "random":
+        shuffled = list(ranked_docs)
+        random.shuffle(shuffled)
+        return shuffled
+    return ranked_docs

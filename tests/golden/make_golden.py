@@ -14,7 +14,7 @@ that are not installable here are replaced by stubs *before* import:
   (so the search arithmetic itself stays "parity unpinned", see oracle/__init__.py).
 
 Outputs (all small): masks.npz, attention.npz, generation.json, knn.json, selector.json, retrieval.json,
-ranked_list.json, pipeline.json.
+ranked_list.json, hybrid.json, pipeline.json.
 """
 from __future__ import annotations
 
@@ -282,7 +282,46 @@ def gen_ranked_list():
         json.dump(recs, f, indent=1)
 
 
+def gen_hybrid():
+    """Reference RRF fusion (retrieval/hybrid.py) and ranked-list ordering on seeded synthetic lists."""
+    from src.pipeline.retrieval import hybrid as ref_hybrid
+
+    rnd = random.Random(11)
+    pool = [f"doc {i} text" for i in range(30)]
+    cases = []
+    for top_k in (1, 4, 5, 10, 11):
+        sp_t, sp_i, de_t, de_i = [], [], [], []
+        for _q in range(4):
+            s_idx = rnd.sample(range(30), 12)
+            d_idx = rnd.sample(range(30), 12)
+            sp_t.append([pool[i] for i in s_idx])
+            de_t.append([pool[i] for i in d_idx])
+            # ids: mostly real, some "NA" / "" (fall back to text keys), one duplicated id inside a list
+            sp_i.append([("NA" if i % 7 == 0 else "" if i % 11 == 0 else f"id{i}") for i in s_idx])
+            de_i.append([("NA" if i % 7 == 0 else "" if i % 11 == 0 else f"id{i}") for i in d_idx])
+            sp_i[-1][3] = sp_i[-1][1]
+        t, i, sc = ref_hybrid.fuse_sparse_and_dense_batch(sp_t, sp_i, de_t, de_i, top_k=top_k, seed=42, k0=60)
+        cases.append(dict(top_k=top_k, seed=42, k0=60, sparse_texts=sp_t, sparse_ids=sp_i, dense_texts=de_t, dense_ids=de_i,
+                          fused_texts=t, fused_ids=i, fused_scores=sc))
+    splits = []
+    rng = random.Random(5)
+    for top_k in (0, 1, 2, 3, 7, 10, 11):
+        splits.append(dict(top_k=top_k, split=list(ref_hybrid.split_k_between_sparse_and_dense(top_k, rng))))
+    orders = []
+    for mode in ("top_down", "bottom_up", "random", "other"):
+        random.seed(3)
+        orders.append(dict(mode=mode, seed=3, docs=list("abcdefg"), out=ref_rl.apply_ranked_list_order(list("abcdefg"), mode)))
+    with open(os.path.join(HERE, "hybrid.json"), "w") as f:
+        json.dump(dict(cases=cases, splits=splits, split_seed=5, orders=orders), f, indent=1)
+    print("hybrid:", len(cases), "cases")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # regenerate selected fixtures only: make_golden.py hybrid ...
+        torch.manual_seed(0)
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
     torch.manual_seed(0)
     gen_masks()
     gen_attention()
@@ -291,5 +330,6 @@ if __name__ == "__main__":
     gen_selector()
     gen_retrieval()
     gen_ranked_list()
+    gen_hybrid()
     gen_pipeline()
     print("golden fixtures written to", HERE)
