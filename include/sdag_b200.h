@@ -99,13 +99,16 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l,
 /* One decode step, dense over the cache (SDAG.py:193-197 passes no mask): q [B,H,D] (stride sq_b,
  * sq_h), k/v cache [B,Hkv,S_cap,D], kv_len valid positions, out [B,H,D] contiguous.  When kv_len_dev is
  * not NULL the kernel reads the valid length from device memory (kv_len is then the upper bound used to
- * size the grid), so a captured CUDA graph can be replayed for every generated token. */
+ * size the grid), so a captured CUDA graph can be replayed for every generated token; kv_len_dev_stride
+ * = 1 reads one length per prompt (ragged batches, e.g. generate_batch_seq2seq,
+ * attack/content_generation.py:44-94), 0 one value for the whole batch. */
 size_t sdag_decode_workspace_bytes(int B, int H, int D, int kv_len);
 int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h,
                     const void* k, int64_t sk_b, int64_t sk_h, int64_t sk_l,
                     const void* v, int64_t sv_b, int64_t sv_h, int64_t sv_l,
                     void* out, int B, int H, int Hkv, int kv_len, int D, float scaling,
-                    void* workspace, size_t workspace_bytes, const int32_t* kv_len_dev, void* stream);
+                    void* workspace, size_t workspace_bytes, const int32_t* kv_len_dev, int kv_len_dev_stride,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Path B — exact max-inner-product top-k.  Replaces faiss IndexFlatIP.search as called by
@@ -169,10 +172,11 @@ int llm_rmsnorm(const void* x, const void* residual, const void* weight, void* s
 /* apply_rotary_pos_emb + KV-cache write: qkv [B*L, (H + 2*Hkv)*D] -> q_out [B,L,H,D], k_out / v_out
  * [B,Hkv,S_cap,D] at positions pos0..pos0+L-1 (element strides kv_stride_b / kv_stride_h);
  * cos / sin: bf16 tables [>= pos0+L, D] indexed by absolute position.  pos0_dev != NULL: read pos0
- * from device memory (CUDA-graph replay). */
+ * from device memory (CUDA-graph replay), one value per prompt when pos0_dev_stride = 1 (ragged
+ * batches), one for the batch when 0. */
 int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out, void* k_out, void* v_out,
                  int B, int L, int H, int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0,
-                 const int32_t* pos0_dev, void* stream);
+                 const int32_t* pos0_dev, int pos0_dev_stride, void* stream);
 /* LlamaMLP activation: gate_up [rows, 2*inter] (gate first) -> out [rows, inter] = silu(gate) * up. */
 int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* stream);
 

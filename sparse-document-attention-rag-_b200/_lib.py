@@ -39,7 +39,7 @@ SIGNATURES = {
                                 _vp, _sz, _i32, _vp, _sz, _vp]),
     "sdag_decode_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "sdag_decode_fwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp,
-                               _i32, _i32, _i32, _i32, _i32, _f32, _vp, _sz, _vp, _vp]),
+                               _i32, _i32, _i32, _i32, _i32, _f32, _vp, _sz, _vp, _i32, _vp]),
     "ip_cast_rows_bf16": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "ip_search_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ip_search": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
@@ -47,7 +47,7 @@ SIGNATURES = {
     "centroid_select": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "doc_knn": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "llm_rmsnorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
-    "llm_rope_qkv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _vp]),
+    "llm_rope_qkv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _i32, _vp]),
     "llm_swiglu": (_i32, [_vp, _vp, _i64, _i32, _vp]),
 }
 

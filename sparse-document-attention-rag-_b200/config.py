@@ -8,9 +8,11 @@ SEED = 42
 TOP_K = [5]
 ADD_ATTACK_IN_RANK = [1]
 BATCH_SIZE_EMBED_Q = 32
+LLM_BATCH_SIZE = 4
 RANKER_MODEL_NAME = "intfloat/e5-large-v2"
 MAX_GEN_TOKENS_RAG = 500
 TEMPERATURE = 0.1
+TOP_P = 1.0
 DOC_NEIGHBORS_K = 0
 MALICIOUS_DOC_SELECTION_STRATEGY = "random"
 MAX_MALICIOUS_DOCS_PER_QUERY = 1

@@ -78,14 +78,14 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restr
 
 // qkv [T, (H + 2*Hkv) * D] (row = token t = b * L + l) -> q_out [B, L, H, D] (RoPE applied), k_out / v_out
 // [B, Hkv, S_cap, D] written at positions pos0 + l (RoPE on k).  cos / sin: bf16 tables indexed by ABSOLUTE position
-// (row pos0 + l).  pos0 may come from device memory (pos0_dev) so a captured CUDA graph can be replayed per token.
+// (row pos0 + l).  pos0 may come from device memory (pos0_dev) so a captured CUDA graph can be replayed per token;
+// pos0_dev_stride = 1 gives every prompt of a ragged batch its own position (0: one value shared by the batch).
 // One thread per 8 consecutive elements of the first half of a head; it also owns the partner elements d + D/2.
 __global__ void __launch_bounds__(256)
 rope_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ cosb,
                 const __nv_bfloat16* __restrict__ sinb, __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_out,
                 __nv_bfloat16* __restrict__ v_out, int B, int L, int H, int Hkv, int D, long long kv_stride_b,
-                long long kv_stride_h, int pos0_host, const int32_t* __restrict__ pos0_dev) {
-  const int pos0 = pos0_dev ? *pos0_dev : pos0_host;
+                long long kv_stride_h, int pos0_host, const int32_t* __restrict__ pos0_dev, int pos0_dev_stride) {
   const int heads = H + 2 * Hkv;
   const int vec_per_head = D / 16;  // threads per head (each handles 8 + 8 elements)
   const long long total = static_cast<long long>(B) * L * heads * vec_per_head;
@@ -96,6 +96,7 @@ rope_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
     const int head = static_cast<int>(r % heads);
     const long long t = r / heads;
     const int l = static_cast<int>(t % L), b = static_cast<int>(t / L);
+    const int pos0 = pos0_dev ? pos0_dev[b * pos0_dev_stride] : pos0_host;
     const __nv_bfloat16* src = qkv + (t * heads + head) * D;
     const uint4 lo = reinterpret_cast<const uint4*>(src)[vh];
     const uint4 hi = reinterpret_cast<const uint4*>(src + D / 2)[vh];
@@ -173,16 +174,17 @@ int llm_rmsnorm(const void* x, const void* residual, const void* weight, void* s
 
 int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out, void* k_out, void* v_out, int B, int L,
                  int H, int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0, const int32_t* pos0_dev,
-                 void* stream) {
+                 int pos0_dev_stride, void* stream) {
   if (!qkv || !cos || !sin || !q_out || !k_out || !v_out) return SDAG_ERR_INVALID;
   if (B <= 0 || L <= 0 || H <= 0 || Hkv <= 0 || D <= 0 || (D % 16) || pos0 < 0) return SDAG_ERR_INVALID;
+  if (pos0_dev_stride != 0 && pos0_dev_stride != 1) return SDAG_ERR_INVALID;
   const long long total = static_cast<long long>(B) * L * (H + 2 * Hkv) * (D / 16);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   rope_qkv_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(cos), static_cast<const __nv_bfloat16*>(sin),
       static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(k_out), static_cast<__nv_bfloat16*>(v_out), B, L, H, Hkv,
-      D, kv_stride_b, kv_stride_h, pos0, pos0_dev);
+      D, kv_stride_b, kv_stride_h, pos0, pos0_dev, pos0_dev_stride);
   return static_cast<int>(cudaGetLastError());
 }
 

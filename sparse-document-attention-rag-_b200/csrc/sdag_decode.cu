@@ -58,14 +58,16 @@ template <int D>
 __global__ void __launch_bounds__(THREADS, 1)
 decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __nv_bfloat16* __restrict__ q, long long sq_b, long long sq_h, float* __restrict__ partial,
-                    int H, int Hkv, int kv_len_host, float scale_log2, const int32_t* __restrict__ kv_len_dev) {
+                    int H, int Hkv, int kv_len_host, float scale_log2, const int32_t* __restrict__ kv_len_dev,
+                    int kv_len_dev_stride) {
   using S = DecodeSmem<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full[S::kStages], empty[S::kStages];
 
-  const int kv_len = kv_len_dev ? min(*kv_len_dev, kv_len_host) : kv_len_host;
   const int split = blockIdx.x, nsplit = gridDim.x, hkv = blockIdx.y, b = blockIdx.z;
+  // device-side length: one value for the batch (stride 0) or one per prompt of a ragged batch (stride 1)
+  const int kv_len = kv_len_dev ? max(0, min(kv_len_dev[b * kv_len_dev_stride], kv_len_host)) : kv_len_host;
   const int G = H / Hkv;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_total = (kv_len + TILE_ROWS - 1) / TILE_ROWS;
@@ -285,7 +287,7 @@ int make_kv_map(CUtensorMap* m, const void* base, int D, int rows, int heads, in
 template <int D>
 int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloat16* q, int64_t sq_b, int64_t sq_h,
                   float* part, __nv_bfloat16* out, int B, int H, int Hkv, int kv_len, int nsplit, float sl2,
-                  const int32_t* kv_len_dev, cudaStream_t st) {
+                  const int32_t* kv_len_dev, int kv_len_dev_stride, cudaStream_t st) {
   static bool cfg = false;
   if (!cfg) {
     SDAG_CUDA_TRY(cudaFuncSetAttribute(decode_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -293,7 +295,7 @@ int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloa
     cfg = true;
   }
   decode_split_kernel<D><<<dim3(nsplit, Hkv, B), THREADS, DecodeSmem<D>::kTotal, st>>>(tk, tv, q, sq_b, sq_h, part, H, Hkv,
-                                                                                      kv_len, sl2, kv_len_dev);
+                                                                                      kv_len, sl2, kv_len_dev, kv_len_dev_stride);
   SDAG_CUDA_TRY(cudaGetLastError());
   decode_merge_kernel<D><<<dim3(H, B), D, 0, st>>>(part, out, H, Hkv, nsplit);
   return static_cast<int>(cudaGetLastError());
@@ -312,8 +314,10 @@ size_t sdag_decode_workspace_bytes(int B, int H, int D, int kv_len) {
 
 int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h, const void* k, int64_t sk_b, int64_t sk_h, int64_t sk_l,
                     const void* v, int64_t sv_b, int64_t sv_h, int64_t sv_l, void* out, int B, int H, int Hkv, int kv_len,
-                    int D, float scaling, void* workspace, size_t workspace_bytes, const int32_t* kv_len_dev, void* stream) {
+                    int D, float scaling, void* workspace, size_t workspace_bytes, const int32_t* kv_len_dev, int kv_len_dev_stride,
+                    void* stream) {
   if (!q || !k || !v || !out || !workspace) return SDAG_ERR_INVALID;
+  if (kv_len_dev_stride != 0 && kv_len_dev_stride != 1) return SDAG_ERR_INVALID;
   if (B <= 0 || H <= 0 || Hkv <= 0 || kv_len <= 0 || H % Hkv) return SDAG_ERR_INVALID;
   if (D != 64 && D != 128) return SDAG_ERR_UNSUPPORTED;
   if (H / Hkv > MAX_G) return SDAG_ERR_UNSUPPORTED;
@@ -331,8 +335,9 @@ int sdag_decode_fwd(const void* q, int64_t sq_b, int64_t sq_h, const void* k, in
   auto* qq = static_cast<const __nv_bfloat16*>(q);
   float* part = static_cast<float*>(workspace);
   auto* oo = static_cast<__nv_bfloat16*>(out);
-  if (D == 128) return launch_decode<128>(tk, tv, qq, sq_b, sq_h, part, oo, B, H, Hkv, kv_len, nsplit, sl2, kv_len_dev, st);
-  return launch_decode<64>(tk, tv, qq, sq_b, sq_h, part, oo, B, H, Hkv, kv_len, nsplit, sl2, kv_len_dev, st);
+  if (D == 128)
+    return launch_decode<128>(tk, tv, qq, sq_b, sq_h, part, oo, B, H, Hkv, kv_len, nsplit, sl2, kv_len_dev, kv_len_dev_stride, st);
+  return launch_decode<64>(tk, tv, qq, sq_b, sq_h, part, oo, B, H, Hkv, kv_len, nsplit, sl2, kv_len_dev, kv_len_dev_stride, st);
 }
 
 }  // extern "C"

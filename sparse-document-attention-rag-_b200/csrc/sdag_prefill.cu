@@ -794,6 +794,8 @@ __global__ void __launch_bounds__(256) v_colsum_kernel(const __nv_bfloat16* __re
                                                        const int32_t* __restrict__ blockmaps, long long bm_stride_ints) {
   const int chunk = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
   if (blockmaps && blockmaps[static_cast<long long>(b) * bm_stride_ints + 3] == 0) return;  // no gap rows
+  // ragged batches: a prompt's uniform rows average over its own L keys (header word 4), not the padded length
+  if (blockmaps) Skv = min(Skv, blockmaps[static_cast<long long>(b) * bm_stride_ints + 4]);
   constexpr int TPR = D / 8;        // threads per row (16 B each)
   constexpr int RPI = 256 / TPR;    // rows per iteration
   const int tr = threadIdx.x / TPR, tc = threadIdx.x % TPR;
@@ -830,6 +832,7 @@ __global__ void __launch_bounds__(D) v_mean_kernel(float* __restrict__ vsum, int
   if (hkv == 0 && b == 0 && d == 0)  // work-stealing counter of the attention kernel that follows on the stream
     *reinterpret_cast<int*>(vsum + static_cast<long long>(B) * Hkv * (VSUM_CHUNKS + 1) * D) = 0;
   if (blockmaps && blockmaps[static_cast<long long>(b) * bm_stride_ints + 3] == 0) return;
+  if (blockmaps) Skv = min(Skv, blockmaps[static_cast<long long>(b) * bm_stride_ints + 4]);
   const float* part = vsum + (static_cast<long long>(b) * Hkv + hkv) * VSUM_CHUNKS * D;
   float s = 0.f;
   for (int ch = 0; ch < VSUM_CHUNKS; ++ch) s += part[ch * D + d];

@@ -92,8 +92,12 @@ class FusedPrefill:
         return cos[0].contiguous(), sin[0].contiguous()
 
     @torch.no_grad()
-    def prefill(self, input_ids: torch.Tensor, blockmap, want_cache: bool = True, kv=None):
+    def prefill(self, input_ids: torch.Tensor, blockmap, want_cache: bool = True, kv=None, lengths=None):
         """input_ids int64 [B, L] on the model's device -> (last-position logits [B, vocab], DynamicCache | None).
+
+        ``lengths`` (int64 ``[B]`` on the device) marks a ragged batch: prompt b occupies columns ``[0, lengths[b])``
+        (right-padded), its block map was built for that length, and its logits are taken at ``lengths[b] - 1``.
+        Rows past a prompt's end are computed but never read (every op between attention calls is row-wise).
 
         ``kv = (k_cache, v_cache, cos, sin)`` with caches ``[n_layers, B, Hkv, S_cap, D]`` makes the prefill write K/V
         straight into a preallocated cache (the decode engine's) instead of building a ``DynamicCache``."""
@@ -118,7 +122,7 @@ class FusedPrefill:
             from transformers import DynamicCache
 
             cache = DynamicCache(config=model.config) if _accepts_config(DynamicCache) else DynamicCache()
-        last_rows = torch.arange(B, device=dev) * L + (L - 1)
+        last_rows = torch.arange(B, device=dev) * L + ((lengths - 1) if lengths is not None else (L - 1))
         n_layers = len(self.layers)
         for i, ly in enumerate(self.layers):
             qkv = F.linear(normed, ly["wqkv"], ly["bqkv"])
@@ -131,7 +135,7 @@ class FusedPrefill:
                 vbuf = v = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
             _lib.count_launches(1)
             _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kbuf.data_ptr(),
-                                        vbuf.data_ptr(), B, L, H, Hkv, D, kbuf.stride(0), kbuf.stride(1), 0, 0, stream),
+                                        vbuf.data_ptr(), B, L, H, Hkv, D, kbuf.stride(0), kbuf.stride(1), 0, 0, 0, stream),
                        "llm_rope_qkv")
             del qkv
             if cache is not None:
@@ -167,14 +171,14 @@ class FusedPrefill:
     # ------------------------------------------------------------------------------------------------
     # generation: prefill into a preallocated cache, then a CUDA-graph-captured decode step replayed per token
     # ------------------------------------------------------------------------------------------------
-    def _decode_context(self, B: int, need_cap: int, temperature: float, dev, use_graph: bool):
+    def _decode_context(self, B: int, need_cap: int, temperature: float, dev, use_graph: bool, nucleus: bool = False):
         """Preallocated KV cache + device-side step state + captured decode graph, cached per (batch, capacity bucket,
         sampling mode).  Capturing costs a few hundred ms, so it is done once per bucket and replayed across calls."""
         from . import sdag
 
         lib = _lib.load()
         S_cap = max(2048, (need_cap + 2047) // 2048 * 2048)
-        key = (B, S_cap, temperature > 0, use_graph, str(dev))
+        key = (B, S_cap, temperature > 0, nucleus, use_graph, str(dev))
         ctxs = self.__dict__.setdefault("_ctx", {})
         ctx = ctxs.get(key)
         if ctx is not None:
@@ -191,10 +195,12 @@ class FusedPrefill:
         c["cos"], c["sin"] = self.rope_tables(S_cap, dev)
         c["gen"] = torch.zeros((B, S_cap), dtype=torch.int64, device=dev)
         c["tok"] = torch.zeros((B, 1), dtype=torch.int64, device=dev)
-        c["pos"] = torch.zeros((1,), dtype=torch.int32, device=dev)    # position of the token being fed
-        c["len"] = torch.ones((1,), dtype=torch.int32, device=dev)     # cache length once its K/V are written
+        # per prompt (ragged batches): position of the token being fed / cache length once its K and V are written
+        c["pos"] = torch.zeros((B,), dtype=torch.int32, device=dev)
+        c["len"] = torch.ones((B,), dtype=torch.int32, device=dev)
         c["slot"] = torch.ones((B, 1), dtype=torch.int64, device=dev)  # output column
         c["temp"] = torch.ones((1,), dtype=torch.float32, device=dev)
+        c["top_p"] = torch.ones((1,), dtype=torch.float32, device=dev)
         q = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=dev)
         attn_out = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=dev)
         kc, vc, cos, sin = c["kc"], c["vc"], c["cos"], c["sin"]
@@ -209,12 +215,12 @@ class FusedPrefill:
                 _lib.count_launches(1)
                 _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kc[i].data_ptr(),
                                             vc[i].data_ptr(), B, 1, H, Hkv, D, kc[i].stride(0), kc[i].stride(1), 0,
-                                            c["pos"].data_ptr(), _lib.stream_ptr(dev)), "llm_rope_qkv")
+                                            c["pos"].data_ptr(), 1, _lib.stream_ptr(dev)), "llm_rope_qkv")
                 sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out)
                 normed, resid = self._mlp_block(attn_out.view(B, H * D), resid, i)
             lg = model.lm_head(normed)
             if sample:
-                nxt = torch.multinomial(torch.softmax(lg.float() / c["temp"], dim=-1), num_samples=1)
+                nxt = sample_tokens(lg, c["temp"], c["top_p"] if nucleus else None)
             else:
                 nxt = torch.argmax(lg, dim=-1, keepdim=True)
             c["gen"].scatter_(1, c["slot"], nxt)
@@ -244,24 +250,37 @@ class FusedPrefill:
 
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, blockmap, max_new_tokens: int, eos_token_id, temperature: float = 0.0,
-                 use_graph: bool = True, poll_every: int = 16) -> torch.Tensor:
+                 use_graph: bool = True, poll_every: int = 16, lengths=None, top_p=None,
+                 eos_from_first: bool = False) -> torch.Tensor:
         """New token ids ``[B, <= max_new_tokens + 1]`` (one from the prefill, the rest from the decode loop —
         SDAG.py:181-211; trimming at EOS is the caller's job).  The decode step (fused glue, split-KV decode
         attention over the preallocated cache, cuBLAS GEMMs, token pick) is captured once into a CUDA graph; position,
-        cache length and output slot live in device memory and advance inside the graph, so the host only replays."""
+        cache length and output slot live in device memory and advance inside the graph, so the host only replays.
+
+        Ragged batches (``lengths`` int64 ``[B]``, prompts right-padded to the common L): every prompt continues at its own
+        position with its own cache length.  ``top_p`` adds nucleus filtering to temperature sampling (the CARG path,
+        attack/content_generation.py:76-83)."""
         B, L = input_ids.shape
         dev = input_ids.device
-        c = self._decode_context(B, L + max_new_tokens + 1, temperature, dev, use_graph)
-        logits, _ = self.prefill(input_ids, blockmap, want_cache=False, kv=(c["kc"], c["vc"], c["cos"], c["sin"]))
+        nucleus = temperature > 0 and top_p is not None and top_p < 1.0
+        c = self._decode_context(B, L + max_new_tokens + 1, temperature, dev, use_graph, nucleus)
+        logits, _ = self.prefill(input_ids, blockmap, want_cache=False, kv=(c["kc"], c["vc"], c["cos"], c["sin"]),
+                                 lengths=lengths)
         if temperature > 0:
             c["temp"].fill_(temperature)
-            tok = torch.multinomial(torch.softmax(logits.float() / temperature, dim=-1), num_samples=1)
+            if nucleus:
+                c["top_p"].fill_(float(top_p))
+            tok = sample_tokens(logits, c["temp"], c["top_p"] if nucleus else None)
         else:
             tok = torch.argmax(logits, dim=-1, keepdim=True)
         c["gen"][:, 0:1] = tok
         c["tok"].copy_(tok)
-        c["pos"].fill_(L)
-        c["len"].fill_(L + 1)
+        if lengths is None:
+            c["pos"].fill_(L)
+            c["len"].fill_(L + 1)
+        else:
+            c["pos"].copy_(lengths)
+            c["len"].copy_(lengths + 1)
         c["slot"].fill_(1)
         done = 0
         while done < max_new_tokens:
@@ -272,9 +291,23 @@ class FusedPrefill:
                 else:
                     c["step"]()
             done += n
-            if eos_token_id is not None and bool((c["gen"][:, 1 : done + 1] == eos_token_id).any(dim=1).all()):
+            first = 0 if eos_from_first else 1  # the SDAG loop never stops on the prefill token
+            if eos_token_id is not None and bool((c["gen"][:, first : done + 1] == eos_token_id).any(dim=1).all()):
                 break
         return c["gen"][:, : done + 1].clone()
+
+
+def sample_tokens(logits: torch.Tensor, temperature: torch.Tensor, top_p: Optional[torch.Tensor]) -> torch.Tensor:
+    """Temperature, then nucleus filtering, then one multinomial draw per row — the order of HF ``generate``'s logits
+    warpers (temperature -> top-p).  A token survives when the probability mass ranked strictly above it is below
+    ``top_p`` (the most likely token always survives).  Device-side scalars, no host sync: usable inside a CUDA graph."""
+    probs = torch.softmax(logits.float() / temperature, dim=-1)
+    if top_p is None:
+        return torch.multinomial(probs, num_samples=1)
+    sp, si = torch.sort(probs, dim=-1, descending=True)
+    above = sp.cumsum(dim=-1) - sp
+    sp = sp.masked_fill(above >= top_p, 0.0)
+    return si.gather(1, torch.multinomial(sp, num_samples=1))
 
 
 def _accepts_config(cls) -> bool:

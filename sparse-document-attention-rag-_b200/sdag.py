@@ -336,8 +336,9 @@ def compute_doc_knn_for_docs(ranker, docs: List[str], k_neighbors: int, device="
 def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling: Optional[float] = None,
                           kv_len_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One decode step, dense over the cache: q ``[B,H,1,D]``, k/v ``[B,Hkv,S,D]`` bf16 -> ``[B,1,H,D]``.
-    ``kv_len_dev`` (int32 device scalar) makes the valid cache length a device-side value (``S`` is then the bound
-    the grid is sized for) so the call can sit inside a CUDA graph that is replayed per token."""
+    ``kv_len_dev`` (int32 device scalar, or one value per prompt for ragged batches) makes the valid cache length a
+    device-side value (``S`` is then the bound the grid is sized for) so the call can sit inside a CUDA graph that is
+    replayed per token."""
     lib = _lib.load()
     B, H, _, D = q.shape
     Hkv, S = k.shape[1], k.shape[2]
@@ -356,6 +357,7 @@ def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sca
                             k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
                             v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
                             out.data_ptr(), B, H, Hkv, S, D, scaling, ws.data_ptr(), ws.numel(), _lib.ptr(kv_len_dev),
+                            1 if (kv_len_dev is not None and kv_len_dev.numel() == B and B > 1) else 0,
                             _lib.stream_ptr(q.device)),
         "sdag_decode_fwd",
     )

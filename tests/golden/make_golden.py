@@ -14,7 +14,7 @@ that are not installable here are replaced by stubs *before* import:
   (so the search arithmetic itself stays "parity unpinned", see oracle/__init__.py).
 
 Outputs (all small): masks.npz, attention.npz, generation.json, knn.json, selector.json, retrieval.json,
-ranked_list.json, hybrid.json, pipeline.json.
+ranked_list.json, hybrid.json, carg.json, pipeline.json.
 """
 from __future__ import annotations
 
@@ -282,6 +282,47 @@ def gen_ranked_list():
         json.dump(recs, f, indent=1)
 
 
+def gen_carg():
+    """CARG: the reference's generate_batch_seq2seq (attack/content_generation.py:44-94, HF ``model.generate`` on a
+    left-padded batch) and generate_noiso_batch (main.py:308-378; main.py imports pyserini at module level, stubbed),
+    greedy, on ragged prompts."""
+    for name in ("pyserini", "pyserini.search", "pyserini.search.lucene"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["pyserini.search.lucene"].LuceneSearcher = object
+    from src.pipeline import config as ref_config
+    from src.pipeline import main as ref_main
+    from src.pipeline.attack import content_generation as ref_cg
+
+    tok = synth.make_tokenizer()
+    tok.padding_side = "left"  # load_llm, content_generation.py:40
+    model = synth.tiny_llama(len(tok))
+    seen = []
+    orig_decode = tok.decode
+
+    def spy(ids, **kw):
+        seen.append([int(x) for x in ids])
+        return orig_decode(ids, **kw)
+
+    tok.decode = spy
+    raw_prompts = ["Paris is", "The highest mountain above sea level is called", "Honey", "Octopuses have three hearts and"]
+    raw_out = ref_cg.generate_batch_seq2seq(tok, model, raw_prompts, max_tokens=7, temperature=0, top_p=1.0)
+    raw_ids, seen[:] = list(seen), []
+    ref_config.ORACLE, ref_config.LLM_BATCH_SIZE, ref_config.MAX_GEN_TOKENS_RAG = True, 2, 6
+    ref_config.TEMPERATURE, ref_config.TOP_P = 0, 1.0
+    docs = [d for d in synth.SAMPLE_DOCS]
+    queries = [synth.SAMPLE_QUERY, "Which ocean is the largest?", "How many hearts does an octopus have?"]
+    defended = [docs[:3], docs[3:6], docs[4:8]]
+    mals = [synth.SAMPLE_MAL[:1], [], synth.SAMPLE_MAL[1:3]]
+    random.seed(5)
+    answers = ref_main.generate_noiso_batch(tok, model, queries, defended, mals, attacker_pos=2, order_mode="bottom_up")
+    tok.decode = orig_decode
+    with open(os.path.join(HERE, "carg.json"), "w") as f:
+        json.dump(dict(raw_prompts=raw_prompts, raw_max_tokens=7, raw_answers=raw_out, raw_token_ids=raw_ids,
+                       queries=queries, defended=defended, malicious=mals, attacker_pos=2, order_mode="bottom_up",
+                       llm_batch_size=2, max_gen_tokens=6, answers=answers, token_ids=list(seen)), f, indent=1)
+    print("carg:", raw_ids, list(seen))
+
+
 def gen_hybrid():
     """Reference RRF fusion (retrieval/hybrid.py) and ranked-list ordering on seeded synthetic lists."""
     from src.pipeline.retrieval import hybrid as ref_hybrid
@@ -331,5 +372,6 @@ if __name__ == "__main__":
     gen_retrieval()
     gen_ranked_list()
     gen_hybrid()
+    gen_carg()
     gen_pipeline()
     print("golden fixtures written to", HERE)
