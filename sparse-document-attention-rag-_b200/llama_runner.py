@@ -140,7 +140,8 @@ class FusedPrefill:
             del qkv
             if cache is not None:
                 cache.update(k, v, i)
-            attn = sdag.sdag_prefill_attention(q.transpose(1, 2), k, v, blockmap, ly["scaling"])  # [B, L, H, D]
+            attn = sdag.sdag_prefill_attention(q.transpose(1, 2), k, v, blockmap, ly["scaling"],
+                                               ragged=lengths is not None)  # [B, L, H, D]
             attn = attn.view(T, H * D)
             last = i == n_layers - 1
             if last:  # only the last position of each prompt is read after the final layer

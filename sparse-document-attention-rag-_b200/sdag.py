@@ -226,8 +226,12 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 
 
 def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, blockmap: BlockMap,
-                           scaling: Optional[float] = None) -> torch.Tensor:
-    """q ``[B,H,L,D]`` (any strides with unit innermost), k/v ``[B,Hkv,S,D]`` bf16 -> out ``[B,L,H,D]`` bf16."""
+                           scaling: Optional[float] = None, ragged: bool = False) -> torch.Tensor:
+    """q ``[B,H,L,D]`` (any strides with unit innermost), k/v ``[B,Hkv,S,D]`` bf16 -> out ``[B,L,H,D]`` bf16.
+
+    ``ragged``: the block maps were built for prompts shorter than L (right-padded batch).  Rows past a prompt's end
+    are not covered by any tile; they are returned as zeros so that everything downstream of them — in particular the
+    K / V rows the next layer derives from them, which sit inside the last kv tile of the prompt — stays finite."""
     lib = _lib.load()
     if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
         raise TypeError("sdag_b200 attention computes in bf16 (fp32 softmax / accumulation)")
@@ -238,7 +242,7 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
     if blockmap.max_L != L or S != L:
         raise ValueError(f"block map was built for L={blockmap.max_L}, got Lq={L}, Skv={S}")
     q, k, v = (_unit_inner(t) for t in (q, k, v))
-    out = torch.empty((B, L, H, D), dtype=torch.bfloat16, device=q.device)
+    out = (torch.zeros if ragged else torch.empty)((B, L, H, D), dtype=torch.bfloat16, device=q.device)
     ws_bytes = int(lib.sdag_prefill_workspace_bytes(B, Hkv, D))
     ws = _workspace(q.device, ws_bytes)
     scaling = float(D ** -0.5 if scaling is None else scaling)
@@ -556,6 +560,58 @@ def run_rag_with_doc_isolation(model, tokenizer, query: str, malicious_docs: Lis
     layout = SdagLayout(L=input_ids.size(1), S=sys_user_len, spans=spans, qa_start=qa_start, neighbors=neighbors)
     bm = build_blockmap_checked(layout, device)
     return _generate(model, tokenizer, input_ids, bm, max_new_tokens)
+
+
+def run_rag_with_doc_isolation_batch(model, tokenizer, queries: Sequence[str], malicious_docs_batch: Sequence[List[str]],
+                                     retrieved_docs_batch: Sequence[list], max_new_tokens: int, device: str,
+                                     add_attack_in_rank: int, ranker, doc_neighbors_k: int) -> List[str]:
+    """SDAG answers for a batch of queries in one ragged pass: the reference calls ``run_rag_with_doc_isolation`` once
+    per query (main.py:469-496); here every query keeps its own prompt, token offsets, block map, RoPE positions and
+    cache length, and the batch shares the prefill launches and one CUDA-graph decode step per token.  Per query the
+    result is what ``run_rag_with_doc_isolation`` returns (greedy; with sampling the draws differ: the reference
+    consumes the global torch RNG one query at a time).  Models the fused engine cannot run, and layouts the span
+    path cannot express, fall back to the per-query call."""
+    from .llama_runner import get_runner
+
+    if torch.device(device).type != "cuda":
+        raise _lib.SdagB200Error("sdag_b200 runs on CUDA devices only (no CPU fallback)")
+    queries = list(queries)
+    prepare_model(model)
+    runner = get_runner(model) if USE_FUSED_PREFILL else None
+
+    def one_by_one():
+        return [run_rag_with_doc_isolation(model, tokenizer, q, list(m), list(r), max_new_tokens, device, add_attack_in_rank,
+                                           ranker, doc_neighbors_k)
+                for q, m, r in zip(queries, malicious_docs_batch, retrieved_docs_batch)]
+
+    if runner is None or not queries:
+        return one_by_one()
+    rows, layouts = [], []
+    for q, mal, ret in zip(queries, malicious_docs_batch, retrieved_docs_batch):
+        chat_str, S, spans, qa_start, ranked = build_rag_chat_and_spans(
+            tokenizer=tokenizer, system_prompt=SYSTEM_PROMPT_RAG, user_template=USER_RAG_PROMPT, query=q,
+            malicious_docs=list(mal), retrieved_docs=list(ret), add_attack_in_rank=add_attack_in_rank)
+        nbrs = None
+        if doc_neighbors_k and doc_neighbors_k > 0:
+            nbrs = compute_doc_knn_for_docs(ranker=ranker, docs=ranked, k_neighbors=doc_neighbors_k, device=device)
+        ids = tokenizer(chat_str, return_tensors="pt")["input_ids"][0]
+        rows.append(ids)
+        layouts.append(SdagLayout(L=int(ids.numel()), S=S, spans=spans, qa_start=qa_start, neighbors=nbrs))
+    if any(len(l.spans) > _lib.MAX_DOCS or l.nbr_k > _lib.MAX_NBR_K for l in layouts):
+        return one_by_one()
+    bm = build_blockmap(layouts, device)
+    stride = bm.stride_bytes // 4
+    status = bm.buf.view(-1)[2 : 2 + stride * len(layouts) : stride]  # header word 2 of every prompt
+    if bool((status != 0).any()):
+        return one_by_one()
+    eos = tokenizer.eos_token_id
+    lengths = torch.tensor([l.L for l in layouts], dtype=torch.int64, device=device)
+    ids = torch.full((len(rows), int(lengths.max())), eos if eos is not None else 0, dtype=torch.int64)
+    for b, r in enumerate(rows):
+        ids[b, : r.numel()] = r
+    temperature = float(TEMPERATURE) if TEMPERATURE > 0 else 0.0
+    gen = runner.generate(ids.to(device), bm, max_new_tokens, eos, temperature=temperature, lengths=lengths)
+    return [tokenizer.decode(_trim_at_eos(row, eos), skip_special_tokens=True).strip() for row in gen.tolist()]
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -489,3 +489,39 @@ def test_carg_sampling_top_p_limits_and_runs_in_graph():
         tok.decode = orig
     assert tiny_p == greedy
     assert all(1 <= len(s) <= 12 for s in sampled)
+
+
+def test_sdag_ragged_batch_equals_per_query_calls(golden_dir):
+    """run_rag_with_doc_isolation_batch (prompts of different lengths, gap rows, neighbour lists) against the per-query
+    function on the fused engine: same greedy tokens up to late bf16 near-ties."""
+    import sdag_b200.sdag as sdag
+
+    sdag.TEMPERATURE = 0
+    tok = synth.make_tokenizer()
+    model = _bf16_model(tok)
+    recs = _records(golden_dir)
+    queries = [synth.SAMPLE_QUERY, "Which ocean is the largest?", "How many hearts?", synth.SAMPLE_QUERY + " Please answer."]
+    mals = [recs[0]["malicious"], [], recs[1]["malicious"], recs[0]["malicious"]]
+    rets = [recs[0]["retrieved"], recs[3]["retrieved"], recs[1]["retrieved"], recs[0]["retrieved"][:2]]
+    for nbr_k in (0, 2):
+        seen = []
+        orig = _spy_decode(tok, seen)
+        try:
+            batch = sdag.run_rag_with_doc_isolation_batch(model, tok, queries, mals, rets, max_new_tokens=20, device="cuda",
+                                                          add_attack_in_rank=1, ranker=synth.HashRanker(), doc_neighbors_k=nbr_k)
+            batch_ids, seen[:] = list(seen), []
+            single = [sdag.run_rag_with_doc_isolation(model, tok, q, m, r, max_new_tokens=20, device="cuda", add_attack_in_rank=1,
+                                                      ranker=synth.HashRanker(), doc_neighbors_k=nbr_k)
+                      for q, m, r in zip(queries, mals, rets)]
+            single_ids = list(seen)
+        finally:
+            tok.decode = orig
+        assert len(batch) == len(queries)
+        exact = 0
+        for a, b_, ta, tb in zip(batch_ids, single_ids, batch, single):
+            fd = next((i for i, (x, y) in enumerate(zip(a, b_)) if x != y), min(len(a), len(b_)))
+            assert fd >= min(8, len(b_)), (nbr_k, a, b_)
+            if a == b_:
+                assert ta == tb
+                exact += 1
+        assert exact >= len(queries) - 1, (nbr_k, batch_ids, single_ids)
