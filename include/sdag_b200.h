@@ -180,6 +180,30 @@ int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out,
 /* LlamaMLP activation: gate_up [rows, 2*inter] (gate first) -> out [rows, inter] = silu(gate) * up. */
 int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Paths B1 / B6 — the sentence encoder behind `ranker.encode(...)` (embed_queries, dense.py:44-65;
+ * encode_texts_with_ranker, malicious_selection.py:12-34; compute_doc_knn_for_docs, SDAG.py:46-48):
+ * BERT-large geometry, bidirectional attention = sdag_prefill_fwd under a block map whose tiles are all
+ * visible, cuBLAS linear layers, and the row-wise glue below.  bf16 tensors.
+ * ---------------------------------------------------------------------------------------------- */
+/* Block maps of B bidirectional sequences of lengths_dev[b] <= max_L tokens (right-padded batch): every
+ * query tile sees every key tile of its own sequence, nothing of the padding. */
+size_t sdag_full_blockmap_bytes(int max_L);
+int sdag_build_blockmap_full(const int32_t* lengths_dev, int B, int max_L, int32_t* out, size_t stride_bytes,
+                             void* stream);
+/* BertSelfOutput / BertOutput: out = LayerNorm(x + residual) * weight + bias (residual may be NULL),
+ * rows x dim, dim % 8 == 0. */
+int enc_layernorm(const void* x, const void* residual, const void* weight, const void* bias, void* out,
+                  int64_t rows, int dim, float eps, void* stream);
+/* BertIntermediate activation: exact (erf) GELU over n_elems contiguous values, n_elems % 8 == 0. */
+int enc_gelu(const void* x, void* out, int64_t n_elems, void* stream);
+/* sentence-transformers Pooling(mean) + Normalize: hidden [B, L, dim] (element strides stride_b, stride_l),
+ * lengths[b] valid tokens -> fp32 row (dst_rows ? dst_rows[b] : row0 + b) of out_f32 [*, dim], and its
+ * bf16 copy in out_bf16 when not NULL — i.e. straight into the index shard ip_search reads. */
+int enc_mean_pool_normalize(const void* hidden, int64_t stride_b, int64_t stride_l, const int32_t* lengths,
+                            int B, int L, int dim, const int64_t* dst_rows, int64_t row0, float* out_f32,
+                            void* out_bf16, int normalize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

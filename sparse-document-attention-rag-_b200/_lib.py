@@ -49,6 +49,11 @@ SIGNATURES = {
     "llm_rmsnorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
     "llm_rope_qkv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _i32, _vp]),
     "llm_swiglu": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "sdag_full_blockmap_bytes": (_sz, [_i32]),
+    "sdag_build_blockmap_full": (_i32, [_vp, _i32, _i32, _vp, _sz, _vp]),
+    "enc_layernorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    "enc_gelu": (_i32, [_vp, _vp, _i64, _vp]),
+    "enc_mean_pool_normalize": (_i32, [_vp, _i64, _i64, _vp, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
 }
 
 _lib = None

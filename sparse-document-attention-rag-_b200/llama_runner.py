@@ -139,7 +139,7 @@ class FusedPrefill:
                        "llm_rope_qkv")
             del qkv
             if cache is not None:
-                cache.update(k, v, i)
+                _cache_adopt(cache, k, v, i)
             attn = sdag.sdag_prefill_attention(q.transpose(1, 2), k, v, blockmap, ly["scaling"],
                                                ragged=lengths is not None)  # [B, L, H, D]
             attn = attn.view(T, H * D)
@@ -296,6 +296,27 @@ class FusedPrefill:
             if eos_token_id is not None and bool((c["gen"][:, first : done + 1] == eos_token_id).any(dim=1).all()):
                 break
         return c["gen"][:, : done + 1].clone()
+
+
+def _cache_adopt(cache, k: torch.Tensor, v: torch.Tensor, layer_idx: int) -> None:
+    """Hand layer ``layer_idx`` of a fresh ``DynamicCache`` the prefill's K / V tensors themselves.  ``cache.update`` would
+    ``torch.cat`` them onto an empty tensor — a full copy of the cache per prefill (HF:cache_utils.py DynamicLayer.update);
+    the tensors are ours and nothing else aliases them, so the layer can simply own them.  Falls back to ``update`` when
+    the cache class does not look like transformers' lazily initialised layers."""
+    try:
+        replicate = getattr(cache, "layer_class_to_replicate", None)
+        if replicate is not None:
+            while len(cache.layers) <= layer_idx:
+                cache.layers.append(replicate())
+        layer = cache.layers[layer_idx]
+        if (not getattr(layer, "is_initialized", True) and hasattr(layer, "lazy_initialization") and hasattr(layer, "keys")
+                and not getattr(cache, "offloading", False)):
+            layer.lazy_initialization(k, v)
+            layer.keys, layer.values = k, v
+            return
+    except Exception:
+        pass
+    cache.update(k, v, layer_idx)
 
 
 def sample_tokens(logits: torch.Tensor, temperature: torch.Tensor, top_p: Optional[torch.Tensor]) -> torch.Tensor:

@@ -91,6 +91,19 @@ class FlatIPIndex:
         idx._adopt(corpus)
         return idx
 
+    @classmethod
+    def from_encoded(cls, rows_f32: torch.Tensor, rows_bf16: torch.Tensor, **kw) -> "FlatIPIndex":
+        """Adopt fp32 rows together with the bf16 shadow the encoder's pooling kernel already wrote
+        (``encoder.encode_corpus``): no cast pass; only the largest row norm is computed."""
+        if rows_f32.dtype != torch.float32 or rows_bf16.dtype != torch.bfloat16 or rows_f32.shape != rows_bf16.shape:
+            raise TypeError("fp32 rows and a bf16 shadow of the same shape expected")
+        idx = cls(rows_f32.shape[1], device=rows_f32.device, **kw)
+        idx._f32, idx._bf16, idx.ntotal = rows_f32.contiguous(), rows_bf16.contiguous(), rows_f32.shape[0]
+        if idx.ntotal:
+            nr = torch.linalg.vector_norm(idx._f32, dim=1).max() * 1.000001
+            idx._max_norm = torch.maximum(idx._max_norm, nr.reshape(1).float())
+        return idx
+
     def _adopt(self, x: torch.Tensor) -> None:
         lib = _lib.load()
         x = x.contiguous()

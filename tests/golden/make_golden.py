@@ -14,7 +14,7 @@ that are not installable here are replaced by stubs *before* import:
   (so the search arithmetic itself stays "parity unpinned", see oracle/__init__.py).
 
 Outputs (all small): masks.npz, attention.npz, generation.json, knn.json, selector.json, retrieval.json,
-ranked_list.json, hybrid.json, carg.json, pipeline.json.
+ranked_list.json, hybrid.json, encoder.npz, carg.json, pipeline.json.
 """
 from __future__ import annotations
 
@@ -323,6 +323,21 @@ def gen_carg():
     print("carg:", raw_ids, list(seen))
 
 
+def gen_encoder():
+    """Sentence embeddings of the e5 module stack restated on HF BertModel (oracle/encoder.py): random-init tiny BERT,
+    fp32, eager attention, CPU — ragged inputs from one token to several tiles long."""
+    from oracle.encoder import encode_oracle
+
+    tok = synth.make_tokenizer()
+    bert = synth.tiny_bert(len(tok))
+    toks = [tok(t)["input_ids"][:512] for t in synth.ENCODER_TEXTS]
+    emb = encode_oracle(bert, toks, pad_id=tok.pad_token_id)
+    raw = encode_oracle(bert, toks, pad_id=tok.pad_token_id, normalize=False)
+    np.savez_compressed(os.path.join(HERE, "encoder.npz"), emb=emb.astype(np.float32), raw=raw.astype(np.float32),
+                        lengths=np.array([len(t) for t in toks], dtype=np.int32))
+    print("encoder:", emb.shape, [len(t) for t in toks])
+
+
 def gen_hybrid():
     """Reference RRF fusion (retrieval/hybrid.py) and ranked-list ordering on seeded synthetic lists."""
     from src.pipeline.retrieval import hybrid as ref_hybrid
@@ -372,6 +387,7 @@ if __name__ == "__main__":
     gen_retrieval()
     gen_ranked_list()
     gen_hybrid()
+    gen_encoder()
     gen_carg()
     gen_pipeline()
     print("golden fixtures written to", HERE)

@@ -93,6 +93,33 @@ def tiny_llama(vocab_size: int, seed: int = 42, dtype=torch.float32, hidden=64, 
     return model.to(dtype).eval()
 
 
+def tiny_bert(vocab_size: int, seed: int = 42, dtype=torch.float32, hidden=128, layers=2, heads=2, inter=256, init_scale=6.0):
+    """Random-init HF ``BertModel`` (no pooler) with head_dim 64, the e5-large-v2 layout in small."""
+    from transformers import BertConfig, BertModel
+
+    cfg = BertConfig(vocab_size=vocab_size, hidden_size=hidden, num_hidden_layers=layers, num_attention_heads=heads,
+                     intermediate_size=inter, max_position_embeddings=512, hidden_act="gelu", hidden_dropout_prob=0.0,
+                     attention_probs_dropout_prob=0.0)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(seed)
+    model = BertModel(cfg, add_pooling_layer=False)
+    with torch.no_grad():  # widen the default init so attention is far from uniform
+        for name, p in model.named_parameters():
+            if p.dim() >= 2 and "LayerNorm" not in name:
+                p.mul_(init_scale)
+    return model.to(dtype).eval()
+
+
+ENCODER_TEXTS = [
+    "query: When was the Eiffel Tower completed?",
+    "passage: The Eiffel Tower was completed in 1889 and stands in Paris.",
+    "passage: x",
+    "passage: " + "Mount Everest is the highest mountain above sea level. " * 9,
+    "passage: Honey never spoils because of its low moisture content.",
+    "passage: " + "The Pacific Ocean is the largest and deepest of Earth's oceans. " * 4,
+]
+
+
 SAMPLE_DOCS = [
     "The Eiffel Tower was completed in 1889 and stands in Paris.",
     "Mount Everest is the highest mountain above sea level.",

@@ -91,3 +91,21 @@ def test_selector_oracle_matches_reference(golden_dir):
             c_emb = np.stack([synth.text_embedding("passage: " + d) for d in cands])
             order = select_order_oracle(r_emb, c_emb, rec["strategy"], target)
             assert [cands[i] for i in order] == chosen
+
+
+def test_encoder_oracle_reproduces_golden(golden_dir):
+    """oracle/encoder.py against the committed HF-BertModel fixture (same seeded tiny BERT, fp32, eager)."""
+    import os
+
+    import numpy as np
+
+    import synth
+    from oracle.encoder import encode_oracle
+
+    gold = np.load(os.path.join(golden_dir, "encoder.npz"))
+    tok = synth.make_tokenizer()
+    bert = synth.tiny_bert(len(tok))
+    toks = [tok(t)["input_ids"][:512] for t in synth.ENCODER_TEXTS]
+    assert [len(t) for t in toks] == gold["lengths"].tolist()
+    np.testing.assert_allclose(encode_oracle(bert, toks, pad_id=tok.pad_token_id), gold["emb"], atol=1e-5)
+    np.testing.assert_allclose(encode_oracle(bert, toks[::-1], pad_id=tok.pad_token_id, batch=2)[::-1], gold["emb"], atol=1e-5)
