@@ -104,6 +104,12 @@ class FlatIPIndex:
             idx._max_norm = torch.maximum(idx._max_norm, nr.reshape(1).float())
         return idx
 
+    def reconstruct_rows(self, rows: torch.Tensor) -> torch.Tensor:
+        """Stored vectors of the given local rows as fp32 ``[n, d]`` on the device (faiss ``reconstruct_batch``)."""
+        rows = rows.to(self.device, dtype=torch.int64) - self.id_offset
+        src = self._f32 if self._f32 is not None else self._bf16
+        return src[: self.ntotal].index_select(0, rows).float()
+
     def _adopt(self, x: torch.Tensor) -> None:
         lib = _lib.load()
         x = x.contiguous()
@@ -341,7 +347,9 @@ class DenseRetriever(Retriever):
         q_embs = embed_queries(self.ranker, list(queries), batch_size=embed_batch_size)
         indices, scores = search_index(self.index, q_embs, top_k=max_k_needed)
         texts, ids, scs = materialize_dense_hits(indices, scores, self.meta)
-        return RetrievalBatch(q_embs=list(q_embs), docs_texts_full=texts, ids_full=ids, scores_full=scs)
+        n_meta = len(self.meta)
+        rows = [[int(i) if 0 <= int(i) < n_meta else -1 for i in row] for row in indices]
+        return RetrievalBatch(q_embs=list(q_embs), docs_texts_full=texts, ids_full=ids, scores_full=scs, rows_full=rows)
 
 
 B200DenseRetriever = DenseRetriever

@@ -73,7 +73,14 @@ def select_malicious_docs_for_batch(
     strategy: str,
     max_docs: int,
     device="cuda",
+    retrieved_rows_batch_full: Optional[List[List[int]]] = None,
+    index=None,
 ) -> List[List[str]]:
+    """Same signature and results as the reference function.  Extension: with ``retrieved_rows_batch_full`` (the
+    ``RetrievalBatch.rows_full`` of this package's ``DenseRetriever``) and the ``index`` they refer to, the retrieved
+    documents' embeddings are read from the index instead of being encoded again — the reference re-encodes them for
+    every query (malicious_selection.py:85,113) although they were embedded with the same ``"passage: "`` prefix when the
+    index was built.  Rows that are missing (-1) fall back to encoding."""
     numeric = strategy in ("closest_to_centroid", "furthest_from_centroid")
     pairs = list(zip(retrieved_docs_batch_full, malicious_doc_groups_batch))
 
@@ -89,6 +96,7 @@ def select_malicious_docs_for_batch(
             plan.append(("random", n))
         else:
             plan.append(("numeric", (n, nonempty)))
+    reuse = retrieved_rows_batch_full is not None and index is not None and hasattr(index, "reconstruct_rows")
 
     order_rows = {}
     numeric_ids = [i for i, (kind, _) in enumerate(plan) if kind == "numeric"]
@@ -97,7 +105,17 @@ def select_malicious_docs_for_batch(
         c_lists = [list(pairs[i][1]) for i in numeric_ids]
         r_flat = [t for lst in r_lists for t in lst]
         c_flat = [t for lst in c_lists for t in lst]
-        r_emb = _encode_device(ranker, r_flat, device)
+        r_emb = None
+        if reuse:
+            rows_flat = []
+            for i in numeric_ids:
+                keep = [j for j, t in enumerate(pairs[i][0]) if t and t.strip()]
+                rows_i = list(retrieved_rows_batch_full[i])
+                rows_flat += [rows_i[j] if j < len(rows_i) else -1 for j in keep]
+            if rows_flat and min(rows_flat) >= 0:
+                r_emb = index.reconstruct_rows(torch.tensor(rows_flat, dtype=torch.int64)).to(device)
+        if r_emb is None:
+            r_emb = _encode_device(ranker, r_flat, device)
         c_emb = _encode_device(ranker, c_flat, device)
         d = r_emb.shape[1]
         R = max(len(l) for l in r_lists)

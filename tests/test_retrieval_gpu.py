@@ -250,3 +250,31 @@ def test_doc_knn_kernel_matches_oracle_and_reference_golden(golden_dir):
         recs = json.load(f)
     for r in recs:
         assert sdag.compute_doc_knn_for_docs(synth.HashRanker(), r["docs"], r["k"]) == r["neighbors"]
+
+
+def test_selector_reuses_index_embeddings_by_row():
+    """select_malicious_docs_for_batch with RetrievalBatch.rows_full + the index reads the retrieved documents'
+    embeddings from the index (no second encode of those texts) and chooses exactly what the re-encoding path chooses."""
+    import synth
+    from sdag_b200.retrieval import DenseRetriever, FlatIPIndex
+    from sdag_b200.selection import select_malicious_docs_for_batch
+
+    ranker = synth.HashRanker()
+    docs = [f"document number {i} about topic {i % 7}" for i in range(200)]
+    emb = ranker.encode(["passage: " + d for d in docs], convert_to_tensor=True, normalize_embeddings=True)
+    index = FlatIPIndex.from_device(emb.cuda().float())
+    meta = [{"id": f"d{i}", "text": d} for i, d in enumerate(docs)]
+    rb = DenseRetriever(ranker, index, meta).retrieve_batch(["what about topic 3?", "and topic 5?", "x"], 6, 32)
+    assert rb.rows_full is not None and [len(r) for r in rb.rows_full] == [6, 6, 6]
+    assert all(meta[r]["text"] == t for rows, texts in zip(rb.rows_full, rb.docs_texts_full) for r, t in zip(rows, texts))
+    cands = [[f"fake {q} {j}" for j in range(5)] for q in range(3)]
+    for strategy in ("closest_to_centroid", "furthest_from_centroid"):
+        ranker.calls.clear()
+        a = select_malicious_docs_for_batch(ranker, rb.docs_texts_full, cands, strategy, 2)
+        calls_encode = len([c for c in ranker.calls if any(t.startswith("passage: document") for t in c)])
+        ranker.calls.clear()
+        b = select_malicious_docs_for_batch(ranker, rb.docs_texts_full, cands, strategy, 2,
+                                            retrieved_rows_batch_full=rb.rows_full, index=index)
+        calls_reuse = len([c for c in ranker.calls if any(t.startswith("passage: document") for t in c)])
+        assert a == b
+        assert calls_encode == 1 and calls_reuse == 0
