@@ -329,7 +329,16 @@ def run_b200(args):
         xq_host = torch.randn(Q, d, generator=qg)
         xq_host = (xq_host / xq_host.norm(dim=1, keepdim=True)).pin_memory()
         xq_dev = xq_host.to(device)
-        s_steps = max(3, min(args.steps, 10))
+        # enough steps for the clock sampler (100 ms period) to see the timed region: >= 0.6 s of searches
+        search_index_probe = index.search_device(xq_dev, k)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        index.search_device(xq_dev, k)
+        p1.record()
+        torch.cuda.synchronize()
+        del search_index_probe
+        est_ms = max_over_ranks(max(p0.elapsed_time(p1), 0.05))
+        s_steps = int(max(3, min(args.steps, 10), min(200, -(-600.0 // est_ms))))
 
         def search_resident():
             return index.search_device(xq_dev, k)
