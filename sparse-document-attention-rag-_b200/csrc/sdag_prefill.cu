@@ -1,14 +1,18 @@
 // SDAG prefill attention for sm_100a: block-sparse FlashAttention-style forward over the tile lists of
 // sdag_blockmap.cu.  Replaces the masked SDPA call the reference reaches from SDAG.py:176
-// (HF modeling_llama.py:199-221 / integrations/sdpa_attention.py:40-104).
+// (HF modeling_llama.py:199-221 / integrations/sdpa_attention.py:40-104); also the CARG causal prefill and, under a
+// bidirectional block map, the encoder's attention.
 //
-// One CTA per (query tile, head, prompt); 2 CTAs per SM so one CTA's softmax overlaps the other's MMAs.
-//   warp 0      TMA producer: Q once, then K_j / V_j tiles (single-buffered each, separate barriers)
-//   warp 1      tcgen05 issuer: S = Q K_j^T (SS, both K-major) -> TMEM; O += P_j V_j (TS: P in TMEM,
-//               V MN-major straight from its natural [kv][d] layout)
-//   warps 2-5   softmax: one query row per thread (TMEM lane), fp32 online softmax with lazy rescaling,
-//               P written back over S as packed bf16; then the epilogue (O / l -> bf16 -> global)
-// TMEM columns: [0,128) S / P, [128,128+D) O.
+// Persistent kernel, 2 CTAs per SM so one CTA's softmax overlaps the other's MMAs; work items = (query tile, head,
+// prompt), longest first, pulled from a global counter.
+//   warps 0-3   softmax + epilogue: one query row per thread (TMEM lane), fp32 online softmax with lazy rescaling,
+//               P written back over S as packed bf16; O / l -> bf16 -> global
+//   warp 4      scheduler + TMA producer: publishes decoded items through smem, loads Q once per item and K as 64-row
+//               halves through a two-slot ring
+//   warp 5      tcgen05 issuer: S = Q K_g^T (SS, both K-major) -> TMEM; O += P_g V_g (TS: P in TMEM, V MN-major straight
+//               from its natural [kv][d] layout); issued under elect.sync from warp-uniform descriptors
+//   warp 6      TMA producer for V (64-row halves, two-slot ring)
+// TMEM columns: [0,64) / [64,128) score buffers S0 / S1 (P aliased onto the first 32 columns of each), [128,128+D) O.
 #include <math.h>
 
 #include "common.cuh"
@@ -208,13 +212,10 @@ __device__ __forceinline__ Item item_from_slot(const PrefillParams& p, const Sch
   return it;
 }
 
-// Persistent: 2 CTAs per SM, each walks items blockIdx.x, blockIdx.x + gridDim.x, ...  Every role derives the same
-// item sequence on its own; mbarrier parities are tracked with per-role use counters.  The producer runs ahead
-// across item boundaries (Q after the item's last QK^T, K after each QK^T, V after each PV and after the previous
-// item's epilogue has drained its staging rows, which live in the V buffer), and the first QK^T of the next item is
-// issued while the softmax warps are still in the epilogue of the current one.
-// Threads: warps 0-3 = softmax / epilogue warpgroup (one query row per thread; grows to 200 registers), warp 4 = TMA
-// producer, warp 5 = MMA issuer (+ TMEM allocation), warps 6-7 idle; the second warpgroup shrinks to 56 registers.
+// Every role derives the same item sequence from the scheduler's ring; mbarrier parities are tracked with per-role use
+// counters.  The producers run ahead across item boundaries (Q after the item's last QK^T, K after each QK^T, V after
+// each PV), and the first QK^T of the next item is issued while the softmax warps are still in the epilogue of the
+// current one.  The softmax warpgroup grows to 200 registers, the second warpgroup shrinks to 56.
 template <int D>
 __global__ void __launch_bounds__(256, 2)
 sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ64,
