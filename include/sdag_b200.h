@@ -179,6 +179,13 @@ int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out,
                  const int32_t* pos0_dev, int pos0_dev_stride, void* stream);
 /* LlamaMLP activation: gate_up [rows, 2*inter] (gate first) -> out [rows, inter] = silu(gate) * up. */
 int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* stream);
+/* Decode-step linear layer (SDAG.py:191-211, one token per prompt, B <= 4): out [B,N] = xin [B,K] . weight[N,K]^T
+ * (+ bias) (+ residual [B,N]), weight rows streamed once.  prologue 0: xin = x [B,K]; 1: xin = RMSNorm(x) *
+ * norm_weight (eps); 2: x is a gate|up row [B,2K] and xin = silu(gate) * up.  pair_swiglu != 0: weight is a
+ * fused gate|up matrix [N = 2*I, K] and out [B, I] = silu(gate row j) * (up row j + I) — no bias / residual.
+ * K % 8 == 0, N % 4 == 0. */
+int llm_gemv(const void* x, const void* weight, const void* bias, const void* norm_weight, const void* residual,
+             void* out, int B, int K, int N, int prologue, float eps, int pair_swiglu, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Paths B1 / B6 — the sentence encoder behind `ranker.encode(...)` (embed_queries, dense.py:44-65;

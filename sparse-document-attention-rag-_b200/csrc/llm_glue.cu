@@ -200,3 +200,242 @@ int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* st
 }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------------------------------------------
+// Decode-step linear layers (path A5: one token per prompt, SDAG.py:191-211): out[b][n] = sum_k W[n][k] * xin[b][k].
+// Weight rows are streamed from HBM exactly once with 16-byte loads (HBM-bound: 2*B FLOP per weight byte); the small
+// input is staged in shared memory, transformed on the way in (nothing / RMSNorm / SwiGLU of a gate|up row) so the
+// norm and activation launches of the layer disappear, and the residual add rides in the epilogue.  Roundings follow
+// the HF bf16 module order (same helpers as the stand-alone glue kernels above).
+// ----------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int GEMV_THREADS = 256;
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 v;  // volatile: the loads of one iteration stay together, ahead of the arithmetic that consumes them
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+enum GemvPrologue { PRO_NONE = 0, PRO_RMSNORM = 1, PRO_SWIGLU = 2 };
+
+// R output rows per warp pass (the staged input chunk is reused from registers for all of them): 4 for wide layers,
+// 2 for narrow ones so that every SM still gets warps to run.  `pair_swiglu`: weight rows come in (gate j, up j + N/2)
+// pairs and the epilogue writes out[b][j] = silu(gate) * up — the MLP activation never exists as a separate pass.
+template <int B, int R>
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ bias,
+            const __nv_bfloat16* __restrict__ norm_w, const __nv_bfloat16* __restrict__ resid, __nv_bfloat16* __restrict__ out,
+            int K, int N, int prologue, float eps, int pair_swiglu) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(dyn);  // [B][K] transformed input
+  __shared__ float red[B][GEMV_THREADS / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nvec = K / 8;
+  const int warps_total = gridDim.x * (GEMV_THREADS / 32);
+  const int n_first = (blockIdx.x * (GEMV_THREADS / 32) + warp) * R;
+  const int half = N / 2;
+  // weight row of the warp's r-th row at pass base n0: plain, or interleaved (gate, up) pairs
+  auto wrow_of = [&](int n0, int r) -> const uint4* {
+    const int row = pair_swiglu ? ((r & 1) ? half : 0) + (n0 >> 1) + (r >> 1) : n0 + r;
+    return reinterpret_cast<const uint4*>(W + static_cast<long long>(row) * K);
+  };
+
+  // The first weight loads of this warp go out before the input is staged: the prologue costs a few microseconds per
+  // CTA, comparable to the whole streaming time of the narrow layers; the registers ride across the barrier.
+  constexpr int U = R == 2 ? 4 : 2;  // chunk groups per iteration: U * R independent 16-byte loads per lane
+  const int nvec_main = nvec - nvec % (32 * U);
+  uint4 wa[U][R], wb[U][R];
+  if (n_first < N && lane < nvec_main) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int r = 0; r < R; ++r) wa[u][r] = ld_stream(wrow_of(n_first, r) + lane + u * 32);
+  }
+
+  // ---- prologue: stage the (transformed) input ----
+  if (prologue == PRO_SWIGLU) {
+    // x = gate|up rows [B][2K]: xin = bf16(bf16(silu(g)) * u)   (LlamaMLP.forward)
+    for (int i = tid; i < B * nvec; i += GEMV_THREADS) {
+      const int b = i / nvec, v = i % nvec;
+      float g[8], u[8];
+      unpack8(reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * 2 * K)[v], g);
+      unpack8(reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * 2 * K + K)[v], u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = bf(g[e] / (1.f + __expf(-g[e]))) * u[e];
+      reinterpret_cast<uint4*>(sx + b * K)[v] = pack8(g);
+    }
+  } else if (prologue == PRO_RMSNORM) {
+    float ss[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      ss[b] = 0.f;
+      for (int v = tid; v < nvec; v += GEMV_THREADS) {
+        const uint4 a = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * K)[v];
+        reinterpret_cast<uint4*>(sx + b * K)[v] = a;
+        float f[8];
+        unpack8(a, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss[b] = fmaf(f[e], f[e], ss[b]);
+      }
+      for (int o = 16; o > 0; o >>= 1) ss[b] += __shfl_xor_sync(0xffffffffu, ss[b], o);
+      if (lane == 0) red[b][warp] = ss[b];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < GEMV_THREADS / 32; ++w) tot += red[b][w];
+      const float rstd = rsqrtf(tot / static_cast<float>(K) + eps);
+      for (int v = tid; v < nvec; v += GEMV_THREADS) {  // each thread re-reads exactly the chunks it wrote
+        float f[8], g[8];
+        unpack8(reinterpret_cast<const uint4*>(sx + b * K)[v], f);
+        unpack8(reinterpret_cast<const uint4*>(norm_w)[v], g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = g[e] * bf(f[e] * rstd);  // LlamaRMSNorm.forward
+        reinterpret_cast<uint4*>(sx + b * K)[v] = pack8(f);
+      }
+    }
+  } else {
+    for (int i = tid; i < B * nvec; i += GEMV_THREADS) reinterpret_cast<uint4*>(sx)[i] = reinterpret_cast<const uint4*>(x)[i];
+  }
+  __syncthreads();
+
+  // ---- main loop: R weight rows per warp pass; the loads of iteration i+1 are issued before iteration i is consumed ----
+  for (int n0 = n_first; n0 < N; n0 += warps_total * R) {
+    float acc[R][B];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < B; ++b) acc[r][b] = 0.f;
+    const uint4* wr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) wr[r] = wrow_of(n0, r);
+    auto chunk_fma = [&](const uint4 (&w)[R], int v) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        float xv[8];
+        unpack8(reinterpret_cast<const uint4*>(sx + b * K)[v], xv);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float wf[8];
+          unpack8(w[r], wf);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[r][b] = fmaf(wf[e], xv[e], acc[r][b]);
+        }
+      }
+    };
+    auto load_iter = [&](uint4 (&w)[U][R], int v0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) w[u][r] = ld_stream(wr[r] + v0 + u * 32);
+    };
+    auto use_iter = [&](const uint4 (&w)[U][R], int v0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) chunk_fma(w[u], v0 + u * 32);
+    };
+    if (n0 != n_first && lane < nvec_main) load_iter(wa, lane);  // the first pass was loaded before the prologue
+    for (int v0 = lane; v0 < nvec_main; v0 += 64 * U) {
+      const bool more1 = v0 + 32 * U < nvec_main;
+      if (more1) load_iter(wb, v0 + 32 * U);
+      use_iter(wa, v0);
+      if (more1) {
+        if (v0 + 64 * U < nvec_main) load_iter(wa, v0 + 64 * U);
+        use_iter(wb, v0 + 32 * U);
+      }
+    }
+    for (int v = nvec_main + lane; v < nvec; v += 32) {  // tail when K is not a multiple of 256 * U
+      uint4 w[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) w[r] = ld_stream(wr[r] + v);
+      chunk_fma(w, v);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        float sum = acc[r][b];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        acc[r][b] = sum;
+      }
+    if (!pair_swiglu) {
+      if (lane < R * B) {
+        const int r = lane / B, b = lane % B;
+        float sum = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+          for (int bb = 0; bb < B; ++bb)
+            if (rr == r && bb == b) sum = acc[rr][bb];
+        const int n = n0 + r;
+        if (bias) sum += __bfloat162float(bias[n]);
+        sum = bf(sum);                                                                          // nn.Linear output in bf16
+        if (resid) sum = bf(sum + __bfloat162float(resid[static_cast<long long>(b) * N + n]));  // residual + hidden
+        out[static_cast<long long>(b) * N + n] = __float2bfloat16(sum);
+      }
+    } else if (lane < (R / 2) * B) {
+      const int p = lane / B, b = lane % B;  // pair p of this pass: rows 2p (gate) and 2p + 1 (up)
+      float g = 0.f, u = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < R / 2; ++pp)
+#pragma unroll
+        for (int bb = 0; bb < B; ++bb)
+          if (pp == p && bb == b) g = acc[2 * pp][bb], u = acc[2 * pp + 1][bb];
+      g = bf(g), u = bf(u);  // the two nn.Linear outputs in bf16, then LlamaMLP: bf16(bf16(silu(g)) * u)
+      const int j = (n0 >> 1) + p;
+      out[static_cast<long long>(b) * half + j] = __float2bfloat16(bf(g / (1.f + __expf(-g))) * u);
+    }
+  }
+}
+
+template <int B, int R>
+int launch_gemv_r(const void* x, const void* W, const void* bias, const void* norm_w, const void* resid, void* out, int K, int N,
+                  int prologue, float eps, int pair, int n_sm, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(B) * K * 2;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(gemv_kernel<B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
+  long long ctas = (static_cast<long long>(N) / R + (GEMV_THREADS / 32) - 1) / (GEMV_THREADS / 32);
+  if (ctas > static_cast<long long>(n_sm) * per_sm) ctas = static_cast<long long>(n_sm) * per_sm;
+  gemv_kernel<B, R><<<static_cast<unsigned>(ctas), GEMV_THREADS, smem, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(W), static_cast<const __nv_bfloat16*>(bias),
+      static_cast<const __nv_bfloat16*>(norm_w), static_cast<const __nv_bfloat16*>(resid), static_cast<__nv_bfloat16*>(out), K, N,
+      prologue, eps, pair);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <int B>
+int launch_gemv(const void* x, const void* W, const void* bias, const void* norm_w, const void* resid, void* out, int K, int N,
+                int prologue, float eps, int pair, cudaStream_t st) {
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
+  }
+  // narrow layers: two rows per warp pass, so that N / 2 warp passes still cover every SM a few times
+  if (N / 4 < n_sm * 16) return launch_gemv_r<B, 2>(x, W, bias, norm_w, resid, out, K, N, prologue, eps, pair, n_sm, st);
+  return launch_gemv_r<B, 4>(x, W, bias, norm_w, resid, out, K, N, prologue, eps, pair, n_sm, st);
+}
+
+}  // namespace
+
+extern "C" int llm_gemv(const void* x, const void* weight, const void* bias, const void* norm_weight, const void* residual,
+                        void* out, int B, int K, int N, int prologue, float eps, int pair_swiglu, void* stream) {
+  if (!x || !weight || !out || B <= 0 || K <= 0 || N <= 0 || (K % 8) || (N % 4)) return SDAG_ERR_INVALID;
+  if (prologue < PRO_NONE || prologue > PRO_SWIGLU || (prologue == PRO_RMSNORM && !norm_weight)) return SDAG_ERR_INVALID;
+  if (pair_swiglu && (bias || residual)) return SDAG_ERR_INVALID;
+  if (B > 4 || static_cast<size_t>(B) * K * 2 > 200 * 1024) return SDAG_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int pair = pair_swiglu ? 1 : 0;
+  switch (B) {
+    case 1: return launch_gemv<1>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);
+    case 2: return launch_gemv<2>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);
+    case 3: return launch_gemv<3>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);
+    default: return launch_gemv<4>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);
+  }
+}

@@ -179,7 +179,7 @@ class FusedPrefill:
 
         lib = _lib.load()
         S_cap = max(2048, (need_cap + 2047) // 2048 * 2048)
-        key = (B, S_cap, temperature > 0, nucleus, use_graph, str(dev))
+        key = (B, S_cap, temperature > 0, nucleus, use_graph, USE_FUSED_GEMV, str(dev))
         ctxs = self.__dict__.setdefault("_ctx", {})
         ctx = ctxs.get(key)
         if ctx is not None:
@@ -230,6 +230,54 @@ class FusedPrefill:
             c["len"].add_(1)
             c["slot"].add_(1)
 
+        # B <= 2: the linear layers of the step run on llm_gemv — weights streamed once, RMSNorm applied to the staged
+        # input, SwiGLU and the residual add in the epilogues — 7 launches per layer instead of 10 (no norm / activation
+        # kernels).  CUDA-core arithmetic: beyond two prompts its unpack + FMA work per weight byte catches up with the
+        # HBM stream (tools/gemv_bench.py) and cuBLAS is the faster path again.
+        inter, hid = self.inter, self.hidden
+        head_w = model.lm_head.weight
+        fused_ok = (USE_FUSED_GEMV and B <= 2 and hid % 8 == 0 and inter % 8 == 0 and (H * D) % 8 == 0
+                    and all(n % 4 == 0 for n in ((H + 2 * Hkv) * D, hid, 2 * inter, head_w.shape[0]))
+                    and model.lm_head.bias is None and head_w.dtype == torch.bfloat16 and B * inter * 2 <= 200 * 1024)
+        if fused_ok:
+            qkv_b = torch.empty((B, (H + 2 * Hkv) * D), dtype=torch.bfloat16, device=dev)
+            gu_b = torch.empty((B, inter), dtype=torch.bfloat16, device=dev)  # SwiGLU activation (gate|up never materialised)
+            res_a = torch.empty((B, hid), dtype=torch.bfloat16, device=dev)
+            res_b = torch.empty((B, hid), dtype=torch.bfloat16, device=dev)
+            logits_b = torch.empty((B, head_w.shape[0]), dtype=torch.bfloat16, device=dev)
+            st = _lib.stream_ptr(dev)
+
+            def gemv(x, w, bias, norm_w, resid, out, K, N, pro, eps=0.0, pair=0):
+                _lib.count_launches(1)
+                _lib.check(lib.llm_gemv(x.data_ptr(), w.data_ptr(), _lib.ptr(bias), _lib.ptr(norm_w), _lib.ptr(resid), out.data_ptr(),
+                                        B, K, N, pro, float(eps), pair, _lib.stream_ptr(dev)), "llm_gemv")
+
+            def step_fused():
+                resid = inner.embed_tokens(c["tok"]).view(B, hid)
+                for i, ly in enumerate(self.layers):
+                    gemv(resid, ly["wqkv"], ly["bqkv"], ly["w_in"], None, qkv_b, hid, qkv_b.shape[1], 1, ly["eps_in"])
+                    _lib.count_launches(1)
+                    _lib.check(lib.llm_rope_qkv(qkv_b.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kc[i].data_ptr(),
+                                                vc[i].data_ptr(), B, 1, H, Hkv, D, kc[i].stride(0), kc[i].stride(1), 0,
+                                                c["pos"].data_ptr(), 1, _lib.stream_ptr(dev)), "llm_rope_qkv")
+                    sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out)
+                    gemv(attn_out, ly["wo"], ly["bo"], None, resid, res_a, H * D, hid, 0)
+                    gemv(res_a, ly["wgu"], None, ly["w_post"], None, gu_b, hid, 2 * inter, 1, ly["eps_post"], pair=1)  # -> act [B, inter]
+                    gemv(gu_b, ly["wdown"], None, None, res_a, res_b, inter, hid, 0)
+                    resid = res_b
+                gemv(resid, head_w, None, inner.norm.weight, None, logits_b, hid, head_w.shape[0], 1, inner.norm.variance_epsilon)
+                lg = logits_b
+                if sample:
+                    nxt = sample_tokens(lg, c["temp"], c["top_p"] if nucleus else None)
+                else:
+                    nxt = torch.argmax(lg, dim=-1, keepdim=True)
+                c["gen"].scatter_(1, c["slot"], nxt)
+                c["tok"].copy_(nxt)
+                c["pos"].add_(1)
+                c["len"].add_(1)
+                c["slot"].add_(1)
+
+            step = step_fused
         c["step"] = step
         c["graph"] = None
         if use_graph:
@@ -296,6 +344,9 @@ class FusedPrefill:
             if eos_token_id is not None and bool((c["gen"][:, first : done + 1] == eos_token_id).any(dim=1).all()):
                 break
         return c["gen"][:, : done + 1].clone()
+
+
+USE_FUSED_GEMV = True  # decode-step linear layers on llm_gemv (B <= 4); False: cuBLAS + stand-alone glue kernels
 
 
 def _cache_adopt(cache, k: torch.Tensor, v: torch.Tensor, layer_idx: int) -> None:

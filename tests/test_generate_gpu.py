@@ -525,3 +525,72 @@ def test_sdag_ragged_batch_equals_per_query_calls(golden_dir):
                 assert ta == tb
                 exact += 1
         assert exact >= len(queries) - 1, (nbr_k, batch_ids, single_ids)
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 4])
+def test_decode_gemv_matches_module_math(B):
+    """llm_gemv: plain, RMSNorm-prologue, SwiGLU-prologue, bias and residual epilogues vs the torch bf16 module order."""
+    import sdag_b200._lib as L
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(B)
+    K, N, I = 1024, 520, 2048
+    x = torch.randn(B, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    nw = (1 + 0.1 * torch.randn(K, generator=g, device="cuda")).to(torch.bfloat16)
+    res = torch.randn(B, N, generator=g, device="cuda").to(torch.bfloat16)
+    out = torch.empty(B, N, dtype=torch.bfloat16, device="cuda")
+    st = L.stream_ptr(x.device)
+
+    def close(a, ref):
+        torch.testing.assert_close(a.float(), ref.float(), atol=3e-2, rtol=3e-2)
+        assert (a == ref).float().mean() > 0.9  # same roundings; fp32 summation order differs from cuBLAS
+
+    L.check(lib.llm_gemv(x.data_ptr(), W.data_ptr(), bias.data_ptr(), 0, 0, out.data_ptr(), B, K, N, 0, 0.0, 0, st), "plain")
+    close(out, torch.nn.functional.linear(x, W, bias))
+    L.check(lib.llm_gemv(x.data_ptr(), W.data_ptr(), 0, 0, res.data_ptr(), out.data_ptr(), B, K, N, 0, 0.0, 0, st), "residual")
+    close(out, res + torch.nn.functional.linear(x, W))
+    xf = x.float()
+    normed = nw * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(torch.bfloat16)
+    L.check(lib.llm_gemv(x.data_ptr(), W.data_ptr(), 0, nw.data_ptr(), 0, out.data_ptr(), B, K, N, 1, 1e-5, 0, st), "rmsnorm")
+    close(out, torch.nn.functional.linear(normed, W))
+    gu = torch.randn(B, 2 * I, generator=g, device="cuda").to(torch.bfloat16)
+    Wd = (torch.randn(N, I, generator=g, device="cuda") * I ** -0.5).to(torch.bfloat16)
+    act = torch.nn.functional.silu(gu[:, :I]) * gu[:, I:]
+    L.check(lib.llm_gemv(gu.data_ptr(), Wd.data_ptr(), 0, 0, res.data_ptr(), out.data_ptr(), B, I, N, 2, 0.0, 0, st), "swiglu")
+    close(out, res + torch.nn.functional.linear(act, Wd))
+    # fused gate|up layer with the SwiGLU in the epilogue: weight [2*I2, K], out [B, I2]
+    I2 = 260
+    Wgu = (torch.randn(2 * I2, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    out2 = torch.empty(B, I2, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.llm_gemv(x.data_ptr(), Wgu.data_ptr(), 0, nw.data_ptr(), 0, out2.data_ptr(), B, K, 2 * I2, 1, 1e-5, 1, st), "pair")
+    gu2 = torch.nn.functional.linear(normed, Wgu)
+    close(out2, torch.nn.functional.silu(gu2[:, :I2]) * gu2[:, I2:])
+    assert lib.llm_gemv(x.data_ptr(), W.data_ptr(), 0, 0, 0, out.data_ptr(), 5, K, N, 0, 0.0, 0, st) == 1002  # B > 4: unsupported
+
+
+def test_fused_gemv_decode_step_equals_cublas_step():
+    """The generation engine with the decode step on llm_gemv vs the same engine on cuBLAS + stand-alone glue kernels."""
+    import sdag_b200.llama_runner as lr
+    import sdag_b200.sdag as sdag
+
+    tok = synth.make_tokenizer()
+    model = _bf16_model(tok)
+    runner = lr.get_runner(sdag.prepare_model(model))
+    ids = tok(["The Eiffel Tower was completed in 1889 and stands in Paris.", "Honey never spoils because of its low moisture."],
+              return_tensors="pt", padding=True)["input_ids"][:, :40].cuda()
+    bm = sdag.causal_blockmap(ids.shape[1], ids.device)
+    try:
+        lr.USE_FUSED_GEMV = True
+        a = runner.generate(ids, bm, 32, None)
+        a_eager = runner.generate(ids, bm, 32, None, use_graph=False)
+        lr.USE_FUSED_GEMV = False
+        b = runner.generate(ids, bm, 32, None)
+    finally:
+        lr.USE_FUSED_GEMV = True
+    assert torch.equal(a, a_eager)
+    for row_a, row_b in zip(a.tolist(), b.tolist()):
+        fd = next((i for i, (x, y) in enumerate(zip(row_a, row_b)) if x != y), len(row_a))
+        assert fd >= 8, (row_a, row_b)
+    assert sum(ra == rb for ra, rb in zip(a.tolist(), b.tolist())) >= 1
