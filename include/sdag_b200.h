@@ -30,6 +30,7 @@ extern "C" {
 #define SDAG_ERR_DRIVER 1004      /* tensor-map encoding unavailable / failed */
 
 #define SDAG_TILE 128             /* query rows and key columns per attention tile */
+#define SDAG_PREFILL_NO_UNIFORM_ROWS 1 /* sdag_prefill_fwd flag: no query row is without an allowed key */
 #define SDAG_BLOCKMAP_HEADER 16   /* int32 words */
 #define SDAG_LAYOUT_HEADER 8      /* int32 words */
 #define SDAG_MAX_NBR_K 16
@@ -87,14 +88,15 @@ size_t sdag_prefill_workspace_bytes(int B, int Hkv, int D);
 
 /* q [B,H,Lq,D] / k,v [B,Hkv,Skv,D] / out [B,Lq,H,D] addressed through element strides (innermost
  * stride 1, others multiples of 8).  blockmaps: one per batch entry (stride in bytes, 0 = shared).
- * D in {64, 128}. */
+ * D in {64, 128}.  flags: SDAG_PREFILL_NO_UNIFORM_ROWS skips the mean-of-V pass when the caller knows
+ * that no query row is without an allowed key (plain causal and bidirectional maps). */
 int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l,
                      const void* k, int64_t sk_b, int64_t sk_h, int64_t sk_l,
                      const void* v, int64_t sv_b, int64_t sv_h, int64_t sv_l,
                      void* out, int64_t so_b, int64_t so_l, int64_t so_h,
                      int B, int H, int Hkv, int Lq, int Skv, int D, float scaling,
                      const int32_t* blockmaps_dev, size_t blockmap_stride_bytes, int cap_qtiles,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 /* One decode step, dense over the cache (SDAG.py:193-197 passes no mask): q [B,H,D] (stride sq_b,
  * sq_h), k/v cache [B,Hkv,S_cap,D], kv_len valid positions, out [B,H,D] contiguous.  When kv_len_dev is

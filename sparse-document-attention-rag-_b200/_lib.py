@@ -36,7 +36,7 @@ SIGNATURES = {
     "sdag_prefill_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "sdag_prefill_fwd": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64,
                                 _vp, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _f32,
-                                _vp, _sz, _i32, _vp, _sz, _vp]),
+                                _vp, _sz, _i32, _vp, _sz, _i32, _vp]),
     "sdag_decode_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "sdag_decode_fwd": (_i32, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp,
                                _i32, _i32, _i32, _i32, _i32, _f32, _vp, _sz, _vp, _i32, _vp]),

@@ -45,7 +45,52 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return tot;
 }
 
-// One CTA per row; the (summed) row stays in shared memory between the statistics pass and the output pass.
+// One warp per row, the (summed) row held in registers between the statistics passes and the output pass: no shared
+// memory, no block barrier.  VPL = 16-byte vectors per lane (dim = 256 * VPL).
+template <int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                      const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out,
+                      long long rows, float eps) {
+  constexpr int dim = 256 * VPL;
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float f[VPL][8];
+  float s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    unpack8(reinterpret_cast<const uint4*>(x + row * dim)[j * 32 + lane], f[j]);
+    if (res) {
+      float g[8];
+      unpack8(reinterpret_cast<const uint4*>(res + row * dim)[j * 32 + lane], g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j][i] = bf(f[j][i] + g[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1 += f[j][i];
+  }
+  for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  const float mean = s1 / static_cast<float>(dim);
+  float s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s2 = fmaf(f[j][i] - mean, f[j][i] - mean, s2);
+  for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  const float rstd = rsqrtf(s2 / static_cast<float>(dim) + eps);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    float g[8], h[8];
+    unpack8(reinterpret_cast<const uint4*>(w)[j * 32 + lane], g);
+    unpack8(reinterpret_cast<const uint4*>(b)[j * 32 + lane], h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[j][i] = fmaf((f[j][i] - mean) * rstd, g[i], h[i]);
+    reinterpret_cast<uint4*>(out + row * dim)[j * 32 + lane] = pack8(f[j]);
+  }
+}
+
+// General widths: one CTA per row; the (summed) row stays in shared memory between the statistics pass and the output pass.
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
@@ -177,6 +222,23 @@ int enc_layernorm(const void* x, const void* residual, const void* weight, const
   if (!x || !weight || !bias || !out || rows < 0 || dim <= 0 || (dim % 8)) return SDAG_ERR_INVALID;
   if (dim * 2 > 48 * 1024) return SDAG_ERR_UNSUPPORTED;
   if (rows == 0) return SDAG_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto *xp = static_cast<const __nv_bfloat16*>(x), *rp = static_cast<const __nv_bfloat16*>(residual),
+       *wp = static_cast<const __nv_bfloat16*>(weight), *bp = static_cast<const __nv_bfloat16*>(bias);
+  auto* op = static_cast<__nv_bfloat16*>(out);
+  const unsigned wgrid = static_cast<unsigned>((rows + 7) / 8);
+  if (dim == 1024) {  // BERT-large / e5-large-v2
+    layernorm_warp_kernel<4><<<wgrid, 256, 0, st>>>(xp, rp, wp, bp, op, rows, eps);
+    return static_cast<int>(cudaGetLastError());
+  }
+  if (dim == 768) {
+    layernorm_warp_kernel<3><<<wgrid, 256, 0, st>>>(xp, rp, wp, bp, op, rows, eps);
+    return static_cast<int>(cudaGetLastError());
+  }
+  if (dim == 256) {
+    layernorm_warp_kernel<1><<<wgrid, 256, 0, st>>>(xp, rp, wp, bp, op, rows, eps);
+    return static_cast<int>(cudaGetLastError());
+  }
   constexpr int THREADS = 128;
   layernorm_kernel<THREADS><<<static_cast<unsigned>(rows), THREADS, static_cast<size_t>(dim) * 2, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual), static_cast<const __nv_bfloat16*>(weight),

@@ -891,7 +891,7 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
                      int64_t sk_h, int64_t sk_l, const void* v, int64_t sv_b, int64_t sv_h, int64_t sv_l, void* out,
                      int64_t so_b, int64_t so_l, int64_t so_h, int B, int H, int Hkv, int Lq, int Skv, int D,
                      float scaling, const int32_t* blockmaps_dev, size_t blockmap_stride_bytes, int cap_qtiles,
-                     void* workspace, size_t workspace_bytes, void* stream) {
+                     void* workspace, size_t workspace_bytes, int flags, void* stream) {
   if (!q || !k || !v || !out || !blockmaps_dev || !workspace) return SDAG_ERR_INVALID;
   if (B <= 0 || H <= 0 || Hkv <= 0 || Lq <= 0 || Skv <= 0 || H % Hkv || cap_qtiles <= 0) return SDAG_ERR_INVALID;
   if (D != 64 && D != 128) return SDAG_ERR_UNSUPPORTED;
@@ -925,6 +925,13 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
   p.scale_log2 = scaling * 1.4426950408889634f;
 
   const dim3 vgrid(VSUM_CHUNKS, Hkv, B);
+  if (flags & SDAG_PREFILL_NO_UNIFORM_ROWS) {
+    // caller guarantees every query row has an allowed key (causal / bidirectional maps): no mean-of-V pass, only the
+    // work-stealing counter has to be reset
+    SDAG_CUDA_TRY(cudaMemsetAsync(p.next_item, 0, sizeof(int), st));
+    if (D == 128) return launch_prefill<128>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
+    return launch_prefill<64>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
+  }
   if (D == 128) {
     v_colsum_kernel<128><<<vgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(v), sv_b, sv_h, sv_l, Skv,
                                                 static_cast<float*>(workspace), blockmaps_dev, p.bm_stride_ints);

@@ -44,6 +44,7 @@ def full_blockmap(lengths_dev: torch.Tensor, max_L: int):
     T = (max_L + _lib.SDAG_TILE - 1) // _lib.SDAG_TILE
     bm = BlockMap(buf, stride, T, B, max_L, "full")
     bm._lengths = lengths_dev  # keep alive until the kernel has run
+    bm.no_uniform_rows = True  # every token of a sequence sees the whole sequence
     return bm
 
 

@@ -89,6 +89,7 @@ def generate_batch_seq2seq(tokenizer, model, prompts_list: Sequence[str], max_to
             ids[b, : r.numel()] = r
         layouts = [sdag.SdagLayout(L=int(n), S=int(n), spans=[], qa_start=int(n)) for n in lengths.tolist()]
         bm = sdag.build_blockmap(layouts, device)
+        bm.no_uniform_rows = True  # plain causal prompts
         # the prefill yields the first new token, the decode loop the remaining max_tokens - 1
         gen = runner.generate(ids, bm, max(max_tokens - 1, 0), eos, temperature=float(temperature), lengths=lengths,
                               top_p=top_p, eos_from_first=True)

@@ -203,6 +203,7 @@ def causal_blockmap(L: int, device) -> BlockMap:
     bm = _causal_cache.get(key)
     if bm is None:
         bm = build_blockmap([SdagLayout(L=L, S=L, spans=[], qa_start=L)], device)
+        bm.no_uniform_rows = True  # plain causal: every row sees at least itself
         if len(_causal_cache) > 64:
             _causal_cache.clear()
         _causal_cache[key] = bm
@@ -250,7 +251,7 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
     if _profile_events is not None:  # bench.py: CUDA-event timing of the attention launches, on their stream
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    _lib.count_launches(3)  # v_colsum + v_mean + sdag_prefill
+    _lib.count_launches(1 if getattr(blockmap, "no_uniform_rows", False) else 3)  # (v_colsum + v_mean +) sdag_prefill
     _lib.check(
         lib.sdag_prefill_fwd(
             q.data_ptr(), q.stride(0), q.stride(1), q.stride(2),
@@ -259,7 +260,7 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
             out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
             B, H, Hkv, L, S, D, scaling,
             blockmap.buf.data_ptr(), blockmap.stride_bytes if blockmap.n_prompts > 1 else 0, blockmap.launch_qtiles,
-            ws.data_ptr(), ws.numel(), _lib.stream_ptr(q.device)),
+            ws.data_ptr(), ws.numel(), 1 if getattr(blockmap, "no_uniform_rows", False) else 0, _lib.stream_ptr(q.device)),
         "sdag_prefill_fwd",
     )
     if ev is not None:
