@@ -213,7 +213,9 @@ namespace {
 constexpr int GEMV_THREADS = 256;
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
   uint4 v;  // volatile: the loads of one iteration stay together, ahead of the arithmetic that consumes them
-  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  // read-only weights, never reused: no L1 allocation (with large shared-memory carve-outs L1 is only a few tens of KB and
+  // would otherwise bound the bytes in flight)
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 
@@ -424,14 +426,215 @@ int launch_gemv(const void* x, const void* W, const void* bias, const void* norm
 
 }  // namespace
 
+// ----------------------------------------------------------------------------------------------------------------
+// Tensor-core form of the same layer for up to 8 prompts: D[16 rows x 8 prompts] += W[16 x 16] * x^T[16 x 8] with warp
+// MMAs, only to keep the instruction count per weight byte independent of the batch (the op stays HBM-bound).  A dot
+// product does not care about the order of k, so each lane loads one contiguous 16-byte chunk of a weight row and feeds
+// it to two MMAs: within a block of 32 k's, lane (g, t) owns k = 8t..8t+7 of rows g and g+8; MMA 1 takes elements
+// {0,1 | 2,3} of the chunk as its (k_lo | k_hi) pair, MMA 2 elements {4,5 | 6,7}; the input chunk of prompt g is split
+// the same way.  Persistent CTAs stage the input once; the 8 warps of a CTA split K and reduce through shared memory.
+// ----------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int MMA_GEMV_WARPS = 8;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(MMA_GEMV_WARPS * 32)
+gemv_mma_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ bias,
+                const __nv_bfloat16* __restrict__ norm_w, const __nv_bfloat16* __restrict__ resid, __nv_bfloat16* __restrict__ out,
+                int B, int K, int N, int prologue, float eps, int pair_swiglu, int rows_staged) {
+  // rows_staged: B input rows in shared memory, or 0 = the input is too large to stage: it is then read from global memory
+  // through L1 / L2, prologue 0 only
+  constexpr int THREADS = MMA_GEMV_WARPS * 32;
+  extern __shared__ __align__(16) uint8_t dyn[];
+  float* sred = reinterpret_cast<float*>(dyn);                                                  // [warps][32 lanes][4]
+  // [rows_staged][K + 32]: rows are 64 bytes apart modulo 128, so the 8 lanes of a load phase — (g, t) and (g + 1, t) —
+  // touch 8 different 16-byte bank groups
+  __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(dyn + MMA_GEMV_WARPS * 32 * 4 * sizeof(float));
+  const int KS = K + 32;
+  __shared__ float red[8][MMA_GEMV_WARPS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int nvec = K / 8;
+  const int half = N / 2;
+  const int n_blocks = N / 16;
+  // K split: warp w owns k-blocks (32 elements) [kb0, kb1)
+  const int kblocks = K / 32;
+  const int kb0 = static_cast<int>(static_cast<long long>(kblocks) * warp / MMA_GEMV_WARPS);
+  const int kb1 = static_cast<int>(static_cast<long long>(kblocks) * (warp + 1) / MMA_GEMV_WARPS);
+  auto row_ptr = [&](int blk, int r16) -> const uint4* {  // r16 in [0, 16): rows 0-7 / 8-15 of the block
+    int row;
+    if (pair_swiglu) row = (r16 >= 8 ? half : 0) + blk * 8 + (r16 & 7);  // 8 gate rows + their 8 up rows
+    else row = blk * 16 + r16;
+    return reinterpret_cast<const uint4*>(W + static_cast<long long>(row) * K) + t;
+  };
+
+  // ---- prologue: stage the input (rows >= B stay zero), optionally RMS-normalised or as silu(gate) * up ----
+  for (int i = tid; i < rows_staged * nvec; i += THREADS) {
+    const int b = i / nvec, v = i % nvec;
+    uint4 a = make_uint4(0u, 0u, 0u, 0u);
+    if (b < B) {
+      if (prologue == PRO_SWIGLU) {
+        float gg[8], uu[8];
+        unpack8(reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * 2 * K)[v], gg);
+        unpack8(reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * 2 * K + K)[v], uu);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gg[e] = bf(gg[e] / (1.f + __expf(-gg[e]))) * uu[e];
+        a = pack8(gg);
+      } else {
+        a = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * K)[v];
+      }
+    }
+    reinterpret_cast<uint4*>(sx + b * KS)[v] = a;
+  }
+  if (prologue == PRO_RMSNORM) {
+    __syncthreads();
+    for (int b = 0; b < B; ++b) {  // every thread sums a slice of the row, one block reduction per row
+      float ss = 0.f;
+      for (int v = tid; v < nvec; v += THREADS) {
+        float f[8];
+        unpack8(reinterpret_cast<const uint4*>(sx + b * KS)[v], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss = fmaf(f[e], f[e], ss);
+      }
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      if (lane == 0) red[b][warp] = ss;
+    }
+    __syncthreads();
+    for (int b = 0; b < B; ++b) {
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < MMA_GEMV_WARPS; ++w) tot += red[b][w];
+      const float rstd = rsqrtf(tot / static_cast<float>(K) + eps);
+      for (int v = tid; v < nvec; v += THREADS) {
+        float f[8], nw[8];
+        unpack8(reinterpret_cast<const uint4*>(sx + b * KS)[v], f);
+        unpack8(reinterpret_cast<const uint4*>(norm_w)[v], nw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = nw[e] * bf(f[e] * rstd);  // LlamaRMSNorm.forward
+        reinterpret_cast<uint4*>(sx + b * KS)[v] = pack8(f);
+      }
+    }
+  }
+  __syncthreads();
+
+  // prompt g's chunks of this lane: shared memory when staged, else global (nullptr: no such prompt -> zeros)
+  const uint4* sxv = rows_staged ? (g < rows_staged ? reinterpret_cast<const uint4*>(sx + static_cast<long long>(g) * KS) + t : nullptr)
+                                 : (g < B ? reinterpret_cast<const uint4*>(x + static_cast<long long>(g) * K) + t : nullptr);
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  constexpr int UN = 8;  // k-blocks per batch of loads: 16 independent 16-byte weight loads per lane in flight
+  for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const uint4* wlo = row_ptr(blk, g);
+    const uint4* whi = row_ptr(blk, g + 8);
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    int kb = kb0;
+    for (; kb + UN <= kb1; kb += UN) {
+      uint4 lo[UN], hi[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        lo[u] = ld_stream(wlo + (kb + u) * 4);
+        hi[u] = ld_stream(whi + (kb + u) * 4);
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const uint4 xv = sxv ? sxv[(kb + u) * 4] : zero4;
+        mma_bf16_16816(c, lo[u].x, hi[u].x, lo[u].y, hi[u].y, xv.x, xv.y);
+        mma_bf16_16816(c, lo[u].z, hi[u].z, lo[u].w, hi[u].w, xv.z, xv.w);
+      }
+    }
+    for (; kb < kb1; ++kb) {
+      const uint4 lo = ld_stream(wlo + kb * 4), hi = ld_stream(whi + kb * 4), xv = sxv ? sxv[kb * 4] : zero4;
+      mma_bf16_16816(c, lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
+      mma_bf16_16816(c, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
+    }
+    // ---- reduce the K slices of the 8 warps, then the epilogue on warp 0's fragment layout ----
+    *reinterpret_cast<float4*>(sred + (warp * 32 + lane) * 4) = make_float4(c[0], c[1], c[2], c[3]);
+    __syncthreads();
+    if (warp == 0) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < MMA_GEMV_WARPS; ++w) {
+        const float4 p4 = *reinterpret_cast<const float4*>(sred + (w * 32 + lane) * 4);
+        acc.x += p4.x, acc.y += p4.y, acc.z += p4.z, acc.w += p4.w;
+      }
+      // fragment: (row g, prompts 2t, 2t+1) = acc.x, acc.y; (row g + 8, same prompts) = acc.z, acc.w
+      const float v[2][2] = {{acc.x, acc.y}, {acc.z, acc.w}};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int b = t * 2 + e;
+        if (b >= B) continue;
+        if (pair_swiglu) {
+          const float gate = bf(v[0][e]), up = bf(v[1][e]);  // the two nn.Linear outputs in bf16, then LlamaMLP
+          out[static_cast<long long>(b) * half + blk * 8 + g] = __float2bfloat16(bf(gate / (1.f + __expf(-gate))) * up);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n = blk * 16 + g + h * 8;
+            float sum = v[h][e];
+            if (bias) sum += __bfloat162float(bias[n]);
+            sum = bf(sum);
+            if (resid) sum = bf(sum + __bfloat162float(resid[static_cast<long long>(b) * N + n]));
+            out[static_cast<long long>(b) * N + n] = __float2bfloat16(sum);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_gemv_mma(const void* x, const void* W, const void* bias, const void* norm_w, const void* resid, void* out, int B, int K,
+                    int N, int prologue, float eps, int pair, cudaStream_t st) {
+  const size_t red_bytes = MMA_GEMV_WARPS * 32 * 4 * sizeof(float);
+  int rows_staged = B;
+  if (static_cast<size_t>(rows_staged) * (K + 32) * 2 + red_bytes > 72 * 1024) {  // keep three CTAs per SM
+    if (prologue != PRO_NONE && static_cast<size_t>(rows_staged) * (K + 32) * 2 + red_bytes > 200 * 1024) return SDAG_ERR_UNSUPPORTED;
+    if (prologue == PRO_NONE) rows_staged = 0;
+  }
+  const size_t smem = static_cast<size_t>(rows_staged) * (K + 32) * 2 + red_bytes;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(gemv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = smem;
+  }
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
+  }
+  const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
+  long long ctas = N / 16;
+  if (ctas > static_cast<long long>(n_sm) * per_sm) ctas = static_cast<long long>(n_sm) * per_sm;
+  gemv_mma_kernel<<<static_cast<unsigned>(ctas), MMA_GEMV_WARPS * 32, smem, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(W), static_cast<const __nv_bfloat16*>(bias),
+      static_cast<const __nv_bfloat16*>(norm_w), static_cast<const __nv_bfloat16*>(resid), static_cast<__nv_bfloat16*>(out), B, K, N,
+      prologue, eps, pair, rows_staged);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
 extern "C" int llm_gemv(const void* x, const void* weight, const void* bias, const void* norm_weight, const void* residual,
                         void* out, int B, int K, int N, int prologue, float eps, int pair_swiglu, void* stream) {
   if (!x || !weight || !out || B <= 0 || K <= 0 || N <= 0 || (K % 8) || (N % 4)) return SDAG_ERR_INVALID;
   if (prologue < PRO_NONE || prologue > PRO_SWIGLU || (prologue == PRO_RMSNORM && !norm_weight)) return SDAG_ERR_INVALID;
   if (pair_swiglu && (bias || residual)) return SDAG_ERR_INVALID;
-  if (B > 4 || static_cast<size_t>(B) * K * 2 > 200 * 1024) return SDAG_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int pair = pair_swiglu ? 1 : 0;
+  // tensor-core form: any B <= 8 when the row blocks line up and the staged input (8 rows) fits in shared memory
+  const bool mma_ok = B <= 8 && (K % 32) == 0 && (N % 16) == 0 &&
+                      (prologue == PRO_NONE || static_cast<size_t>(B) * (K + 32) * 2 + 4096 <= 200 * 1024);
+#ifdef SDAG_GEMV_FORCE_MMA
+  if (mma_ok) return launch_gemv_mma(x, weight, bias, norm_weight, residual, out, B, K, N, prologue, eps, pair, st);
+#endif
+  if (B > 2 && mma_ok) return launch_gemv_mma(x, weight, bias, norm_weight, residual, out, B, K, N, prologue, eps, pair, st);
+  if (B > 4 || static_cast<size_t>(B) * K * 2 > 200 * 1024) return SDAG_ERR_UNSUPPORTED;
   switch (B) {
     case 1: return launch_gemv<1>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);
     case 2: return launch_gemv<2>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);

@@ -527,14 +527,14 @@ def test_sdag_ragged_batch_equals_per_query_calls(golden_dir):
         assert exact >= len(queries) - 1, (nbr_k, batch_ids, single_ids)
 
 
-@pytest.mark.parametrize("B", [1, 2, 3, 4])
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 5, 8])
 def test_decode_gemv_matches_module_math(B):
     """llm_gemv: plain, RMSNorm-prologue, SwiGLU-prologue, bias and residual epilogues vs the torch bf16 module order."""
     import sdag_b200._lib as L
 
     lib = L.load()
     g = torch.Generator(device="cuda").manual_seed(B)
-    K, N, I = 1024, 520, 2048
+    K, N, I = 1024, 528, 2048  # N % 16 == 0: the tensor-core form (B > 2) works on 16-row blocks
     x = torch.randn(B, K, generator=g, device="cuda").to(torch.bfloat16)
     W = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
     bias = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
@@ -561,13 +561,13 @@ def test_decode_gemv_matches_module_math(B):
     L.check(lib.llm_gemv(gu.data_ptr(), Wd.data_ptr(), 0, 0, res.data_ptr(), out.data_ptr(), B, I, N, 2, 0.0, 0, st), "swiglu")
     close(out, res + torch.nn.functional.linear(act, Wd))
     # fused gate|up layer with the SwiGLU in the epilogue: weight [2*I2, K], out [B, I2]
-    I2 = 260
+    I2 = 264
     Wgu = (torch.randn(2 * I2, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
     out2 = torch.empty(B, I2, dtype=torch.bfloat16, device="cuda")
     L.check(lib.llm_gemv(x.data_ptr(), Wgu.data_ptr(), 0, nw.data_ptr(), 0, out2.data_ptr(), B, K, 2 * I2, 1, 1e-5, 1, st), "pair")
     gu2 = torch.nn.functional.linear(normed, Wgu)
     close(out2, torch.nn.functional.silu(gu2[:, :I2]) * gu2[:, I2:])
-    assert lib.llm_gemv(x.data_ptr(), W.data_ptr(), 0, 0, 0, out.data_ptr(), 5, K, N, 0, 0.0, 0, st) == 1002  # B > 4: unsupported
+    assert lib.llm_gemv(x.data_ptr(), W.data_ptr(), 0, 0, 0, out.data_ptr(), 9, K, N, 0, 0.0, 0, st) == 1002  # B > 8: unsupported
 
 
 def test_fused_gemv_decode_step_equals_cublas_step():
