@@ -4,7 +4,7 @@
 // attention is the prefill kernel with a block map in which every tile of a sequence is fully visible; the linear
 // layers are cuBLAS.  What is left between them is HBM-bound row work, one pass each here:
 //   LayerNorm   y = bf16(w * (s - mean) * rstd + b),  s = bf16(x + residual)     (BertSelfOutput / BertOutput)
-//   GELU        y = bf16(0.5 x (1 + erf(x / sqrt 2)))                             (BertIntermediate, exact erf form)
+//   GELU        y = bf16(0.5 x (1 + erf(x / sqrt 2)))                             (BertIntermediate, erf form; erf to 1.5e-7)
 //   pooling     e = sum_{t < len} h_t / len;  e / max(|e|, 1e-12)                (Pooling(mean) + Normalize)
 // The pooled vector is written as fp32 (and, optionally, its bf16 shadow) straight into the rows of the HBM-resident
 // index shard the search kernels read.
@@ -137,6 +137,21 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __res
   }
 }
 
+// x * Phi(x) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e. <= 0.75e-7 * |x| on the result —
+// three orders of magnitude below a bf16 ulp of the output wherever the output is not itself below 1e-6): one reciprocal,
+// one exponential and five FMAs instead of erff's two divergent polynomial branches, which made this pass compute-bound.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erfc_z = p * t * __expf(-z * z);           // 1 - erf(|x| / sqrt 2)
+  const float phi = x >= 0.f ? 1.f - 0.5f * erfc_z : 0.5f * erfc_z;
+  return x * phi;
+}
+
 __global__ void __launch_bounds__(256) gelu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                    long long nvec) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
@@ -144,7 +159,7 @@ __global__ void __launch_bounds__(256) gelu_kernel(const __nv_bfloat16* __restri
     float f[8];
     unpack8(reinterpret_cast<const uint4*>(x)[i], f);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = 0.5f * f[e] * (1.f + erff(f[e] * 0.70710678118654752f));
+    for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
     reinterpret_cast<uint4*>(out)[i] = pack8(f);
   }
 }

@@ -35,7 +35,13 @@ def test_layernorm_gelu_pool_kernels_match_torch():
                                atol=2e-2, rtol=2e-2)
     y = torch.empty_like(x)
     L.check(lib.enc_gelu(x.data_ptr(), y.data_ptr(), x.numel(), L.stream_ptr(x.device)), "gelu")
-    assert torch.equal(y, torch.nn.functional.gelu(x.float()).to(torch.bfloat16))
+    ref = torch.nn.functional.gelu(x.float())  # exact erf form; the kernel's erf is accurate to 1.5e-7
+    assert (y == ref.to(torch.bfloat16)).float().mean() > 0.98
+    torch.testing.assert_close(y.float(), ref, atol=1e-6, rtol=2 ** -7)  # never more than one bf16 ulp away
+    wide = torch.linspace(-12, 12, 4096, device="cuda").to(torch.bfloat16)
+    yw = torch.empty_like(wide)
+    L.check(lib.enc_gelu(wide.data_ptr(), yw.data_ptr(), wide.numel(), L.stream_ptr(wide.device)), "gelu tails")
+    torch.testing.assert_close(yw.float(), torch.nn.functional.gelu(wide.float()), atol=1e-6, rtol=2 ** -7)
     # pooling: ragged lengths (0 included), scattered destination rows, fp32 + bf16 outputs
     B, Lm = 5, 40
     h = torch.randn(B, Lm, dim, generator=g, device="cuda").to(torch.bfloat16)
