@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun, NCCL): top-k of a corpus sharded by rows over the ranks
+(ShardedFlatIPIndex: local search, all-gather of [Q,k] scores + ids, merge) must equal the top-k of one index over the
+whole corpus, ids bit for bit and scores to 1e-6, including duplicated rows that tie exactly across shard boundaries.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_sharded.py
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sdag_b200.retrieval import FlatIPIndex, ShardedFlatIPIndex  # noqa: E402
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    N, d, Q, k = 400_000, 256, 512, 10
+    g = torch.Generator(device=dev).manual_seed(123)  # same corpus on every rank
+    x = torch.randn(N, d, generator=g, device=dev)
+    x /= x.norm(dim=1, keepdim=True)
+    dup = torch.arange(0, N, 997, device=dev)
+    x[(dup + N // 2 + 3) % N] = x[dup]  # exact ties whose two copies live on different shards
+    xq = torch.randn(Q, d, generator=g, device=dev)
+    xq /= xq.norm(dim=1, keepdim=True)
+    xq[:32] = x[dup[:32]]  # queries that hit a duplicated pair with score 1
+    rows = N // world
+    lo = rank * rows
+    hi = N if rank == world - 1 else lo + rows
+    sharded = ShardedFlatIPIndex(FlatIPIndex.from_device(x[lo:hi].contiguous(), id_offset=lo))
+    s_sh, i_sh = sharded.search_device(xq, k)
+    s_full, i_full = FlatIPIndex.from_device(x).search_device(xq, k)
+    ok = bool(torch.equal(i_sh, i_full)) and bool(torch.allclose(s_sh, s_full, rtol=0, atol=1e-6))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"sharded == single-index top-{k} on {world} GPUs: {'OK' if int(flag) else 'MISMATCH'} "
+              f"(N={N}, Q={Q}, {len(dup)} duplicated rows across shards)")
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag) else 1)
+
+
+if __name__ == "__main__":
+    main()
