@@ -380,6 +380,32 @@ def run_b200(args):
         flops = 2.0 * Q * n_local * d  # per GPU per batch (algorithmic; re-scoring and merge excluded)
         ach = flops / (ms_s / s_steps / 1000.0) / 1e12
         stats = index.local.last_stats.cpu().tolist()
+
+        # full-size parity: 8 sampled queries brute-forced in fp32 over this rank's whole shard (plain torch, chunked),
+        # against the kernel path's local top-k — ids must match (exact ties aside), scores to 1e-5 relative
+        def full_size_check(n_check=8):
+            sel = torch.linspace(0, Q - 1, n_check, device=device).long()
+            s_k, i_k = index.local.search_device(xq_dev[sel], k)
+            best_s = torch.full((n_check, k), -float("inf"), device=device)
+            best_i = torch.full((n_check, k), -1, dtype=torch.int64, device=device)
+            for r0 in range(0, n_local, 1 << 20):
+                r1 = min(n_local, r0 + (1 << 20))
+                sc = xq_dev[sel] @ x[r0:r1].T
+                cs, ci = torch.cat([best_s, sc], dim=1).topk(k, dim=1)
+                ids = torch.cat([best_i, torch.arange(r0, r1, device=device).expand(n_check, -1) + lo], dim=1)
+                best_s, best_i = cs, ids.gather(1, ci)
+            same = (best_i == i_k)
+            rel = ((best_s - s_k).abs() / best_s.abs().clamp(min=1e-12)).max()
+            # a mismatching id is acceptable only where the two scores tie to fp32 summation-order noise
+            tie_ok = ((best_s - s_k).abs() <= 2e-6 * best_s.abs()) | same
+            return {"queries": n_check, "rows": n_local, "ids_equal_frac": float(same.float().mean()),
+                    "all_ids_equal_or_tied": bool(tie_ok.all()), "max_rel_score_err": float(rel)}
+
+        parity = full_size_check()
+        ok_all = torch.tensor([1 if parity["all_ids_equal_or_tied"] and parity["max_rel_score_err"] < 1e-5 else 0], device=device)
+        if world > 1:
+            dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        parity["all_ranks_ok"] = bool(int(ok_all))
         line["secondary"] = {
             "metric": SECONDARY_METRIC, "value": qps, "unit": "queries/s", "ms_per_step": ms_s / s_steps, "steps": s_steps,
             "scaling": "strong", "dtype": "bf16 tensor-core pass + fp32 exact re-score",
@@ -390,7 +416,7 @@ def run_b200(args):
                          "kernel": "ip_gemm_filter_kernel (whole ip_search timed)", "peak_source": pk["_source"] + ", bf16 sustained"},
             "e2e": {"value": Q * s_steps / (ms_se / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4,
                     "d2h_bytes_per_step": Q * k * 12, "api": "FlatIPIndex.search_device + host copies (faiss-shaped search)"},
-            "gpu_launches": launches_s, "clocks": clocks_s,
+            "gpu_launches": launches_s, "clocks": clocks_s, "parity_check": parity,
         }
         del index, x
         torch.cuda.empty_cache()
