@@ -294,7 +294,14 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const uint32_t slot = ns & 1;
         Item it;
         it.valid = false, it.n_kv = 0, it.q0 = it.nrows = it.h = it.b = it.hkv = 0, it.pack = 1, it.R = BM, it.kvt = nullptr;
-        if (i < n_items) it = fetch_item(p, i);
+        // items without tensor work are never handed out: tiles beyond a prompt's count, heads covered by a packed item of
+        // their group, and key-less tiles (written by v_mean_kernel)
+        while (i < n_items) {
+          it = fetch_item(p, i);
+          if (it.valid && it.n_kv > 0) break;
+          i = i_next;
+          i_next = next_index();
+        }
         int4 kv0 = make_int4(0, 0, 0, 0), kv1 = kv0;
         if (it.valid && it.n_kv > 0) kv0 = it.kvt[0];
         if (it.valid && it.n_kv > 1) kv1 = it.kvt[1];
@@ -825,10 +832,14 @@ __global__ void __launch_bounds__(256) v_colsum_kernel(const __nv_bfloat16* __re
   }
 }
 
-// vmean[b][hkv][d] = (sum of the chunk partials, fixed order) / Skv, stored after the partials.
+// vmean[b][hkv][d] = (sum of the chunk partials, fixed order) / Skv, stored after the partials.  The same block also
+// writes the output of every query tile that has no kv tile at all (gap rows: uniform softmax = mean of V) for the G
+// query heads of its kv group, so the attention kernel's scheduler never has to hand those tiles out.
 template <int D>
 __global__ void __launch_bounds__(D) v_mean_kernel(float* __restrict__ vsum, int B, int Hkv, int Skv,
-                                                   const int32_t* __restrict__ blockmaps, long long bm_stride_ints) {
+                                                   const int32_t* __restrict__ blockmaps, long long bm_stride_ints,
+                                                   __nv_bfloat16* __restrict__ out, long long so_b, long long so_l, long long so_h,
+                                                   int H, int Lq) {
   const int hkv = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
   if (hkv == 0 && b == 0 && d == 0)  // work-stealing counter of the attention kernel that follows on the stream
     *reinterpret_cast<int*>(vsum + static_cast<long long>(B) * Hkv * (VSUM_CHUNKS + 1) * D) = 0;
@@ -837,7 +848,32 @@ __global__ void __launch_bounds__(D) v_mean_kernel(float* __restrict__ vsum, int
   const float* part = vsum + (static_cast<long long>(b) * Hkv + hkv) * VSUM_CHUNKS * D;
   float s = 0.f;
   for (int ch = 0; ch < VSUM_CHUNKS; ++ch) s += part[ch * D + d];
-  vsum[(static_cast<long long>(B) * Hkv * VSUM_CHUNKS + static_cast<long long>(b) * Hkv + hkv) * D + d] = s / static_cast<float>(Skv);
+  const float mean = s / static_cast<float>(Skv);
+  vsum[(static_cast<long long>(B) * Hkv * VSUM_CHUNKS + static_cast<long long>(b) * Hkv + hkv) * D + d] = mean;
+  if (!blockmaps) return;
+  const int32_t* map = blockmaps + static_cast<long long>(b) * bm_stride_ints;
+  if (map[2] != 0) return;
+  const __nv_bfloat16 mb = __float2bfloat16(mean);
+  const int4* qtiles = reinterpret_cast<const int4*>(map + SDAG_BLOCKMAP_HEADER);
+  const int G = H / Hkv;
+  // the threads scan the tile list in parallel and collect the key-less tiles; then every thread writes its column
+  __shared__ int2 gaps[128];
+  __shared__ int n_gaps;
+  if (d == 0) n_gaps = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < map[0]; t0 += 128 * D / D) {  // rounds of up to 128 collected tiles keep the list bounded
+    for (int t = t0 + d; t < min(map[0], t0 + 128); t += D) {
+      const int4 qt = qtiles[t];
+      if (qt.w == 0) gaps[atomicAdd(&n_gaps, 1)] = make_int2(qt.x, min(qt.x + qt.y, Lq));
+    }
+    __syncthreads();
+    for (int i = 0; i < n_gaps; ++i)
+      for (int r = gaps[i].x; r < gaps[i].y; ++r)
+        for (int gh = 0; gh < G; ++gh) out[b * so_b + r * so_l + (hkv * G + gh) * so_h + d] = mb;
+    __syncthreads();
+    if (d == 0) n_gaps = 0;
+    __syncthreads();
+  }
 }
 
 int make_map_4d(CUtensorMap* m, const void* base, int D, int rows, int heads, int B, int64_t s_l, int64_t s_h,
@@ -935,13 +971,15 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
   if (D == 128) {
     v_colsum_kernel<128><<<vgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(v), sv_b, sv_h, sv_l, Skv,
                                                 static_cast<float*>(workspace), blockmaps_dev, p.bm_stride_ints);
-    v_mean_kernel<128><<<dim3(Hkv, B), 128, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints);
+    v_mean_kernel<128><<<dim3(Hkv, B), 128, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints,
+                                                     p.out, p.so_b, p.so_l, p.so_h, H, Lq);
     SDAG_CUDA_TRY(cudaGetLastError());
     return launch_prefill<128>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
   }
   v_colsum_kernel<64><<<vgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(v), sv_b, sv_h, sv_l, Skv,
                                              static_cast<float*>(workspace), blockmaps_dev, p.bm_stride_ints);
-  v_mean_kernel<64><<<dim3(Hkv, B), 64, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints);
+  v_mean_kernel<64><<<dim3(Hkv, B), 64, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints, p.out,
+                                                 p.so_b, p.so_l, p.so_h, H, Lq);
   SDAG_CUDA_TRY(cudaGetLastError());
   return launch_prefill<64>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
 }
