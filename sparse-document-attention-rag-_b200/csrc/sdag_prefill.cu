@@ -5,13 +5,15 @@
 //
 // Persistent kernel, 2 CTAs per SM so one CTA's softmax overlaps the other's MMAs; work items = (query tile, head,
 // prompt), longest first, pulled from a global counter.
-//   warps 0-3   softmax + epilogue: one query row per thread (TMEM lane), fp32 online softmax with lazy rescaling,
-//               P written back over S as packed bf16; O / l -> bf16 -> global
+//   warps 0-3   softmax: one query row per thread (TMEM lane), fp32 online softmax with lazy rescaling, P written back
+//               over S as packed bf16; the row sums of a finished item go to the epilogue warpgroup through smem
 //   warp 4      scheduler + TMA producer: publishes decoded items through smem, loads Q once per item and K as 64-row
 //               halves through a two-slot ring
 //   warp 5      tcgen05 issuer: S = Q K_g^T (SS, both K-major) -> TMEM; O += P_g V_g (TS: P in TMEM, V MN-major straight
 //               from its natural [kv][d] layout); issued under elect.sync from warp-uniform descriptors
 //   warp 6      TMA producer for V (64-row halves, two-slot ring)
+//   warps 8-11  epilogue: O out of TMEM (releasing it for the next item), O / l -> bf16 -> staging -> coalesced stores,
+//               concurrently with the softmax warps' next item
 // TMEM columns: [0,64) / [64,128) score buffers S0 / S1 (P aliased onto the first 32 columns of each), [128,128+D) O.
 #include <math.h>
 
@@ -102,7 +104,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define STAMP(item, slot)                                                                  \
   do {                                                                                     \
-    if (g_timing && threadIdx.x == 0) g_timing[(item) * 8ull + (slot)] = gtime();          \
+    if (g_timing && (threadIdx.x == 0 || threadIdx.x == 256)) g_timing[(item) * 8ull + (slot)] = gtime(); \
   } while (0)
 #else
 #define STAMP(item, slot) \
@@ -215,9 +217,9 @@ __device__ __forceinline__ Item item_from_slot(const PrefillParams& p, const Sch
 // Every role derives the same item sequence from the scheduler's ring; mbarrier parities are tracked with per-role use
 // counters.  The producers run ahead across item boundaries (Q after the item's last QK^T, K after each QK^T, V after
 // each PV), and the first QK^T of the next item is issued while the softmax warps are still in the epilogue of the
-// current one.  The softmax warpgroup grows to 200 registers, the second warpgroup shrinks to 56.
+// current one.  384 threads at 80 registers; setmaxnreg moves them to 136 (softmax) / 48 (producers, issuer) / 56 (epilogue).
 template <int D>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(384, 2)
 sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ64,
                     const __grid_constant__ CUtensorMap tmQ32, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const PrefillParams p, const long long n_items) {
@@ -227,9 +229,10 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = sQ + Smem<D>::kQ;
   uint8_t* sV = sK + Smem<D>::kK;
   uint8_t* sStage = sV + Smem<D>::kV;
-  __shared__ uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done, o_full, o_empty;
+  __shared__ uint64_t q_full, q_empty, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_full[2], pv_done, o_full, o_empty, l_full[2], l_empty[2];
   __shared__ uint64_t sched_full[2], sched_empty[2];
   __shared__ SchedSlot sched[2];
+  __shared__ float l_buf[2][BM];  // row sums handed from the softmax warpgroup to the epilogue warpgroup
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -251,8 +254,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(&o_full, 1);
     mbar_init(&o_empty, 128);
     for (int x = 0; x < 2; ++x) {
+      mbar_init(&l_full[x], 128);   // softmax threads: row sums of an item are in l_buf
+      mbar_init(&l_empty[x], 128);  // epilogue threads: read them
+    }
+    for (int x = 0; x < 2; ++x) {
       mbar_init(&sched_full[x], 1);
-      mbar_init(&sched_empty[x], 32 + 128 + 1);  // every MMA-warp lane, softmax thread and the V producer reads the slot
+      mbar_init(&sched_empty[x], 32 + 128 + 1 + 128);  // MMA-warp lanes, softmax threads, the V producer, epilogue threads
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmQ);
@@ -274,8 +281,101 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_S = tmem;
   const uint32_t tmem_O = tmem + 128;
 
-  if (warp >= 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // ======================= epilogue warpgroup (warps 8..11) =======================
+    // O / l -> bf16 -> per-warp staging rows -> coalesced 16-byte stores, off the softmax warps' critical path: while this
+    // runs, they are already in the next item.  O is read out of TMEM first (o_empty), so the next item's first P.V —
+    // issued only after that item's first softmax sub-step — normally never waits for it.
+    const int quarter = warp - 8;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t nq = 0;
+    for (uint32_t ns = 0;; ++ns) {
+      const uint32_t slot = ns & 1;
+      mbar_wait(&sched_full[slot], (ns >> 1) & 1);
+      const Item it = item_from_slot(p, sched[slot]);
+      const int state = sched[slot].b.w;
+      const long long i = sched[slot].i;
+      mbar_arrive(&sched_empty[slot]);
+      if (state < 0) break;
+      if (!it.valid || it.n_kv == 0) continue;
+      const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(it.b) * p.Hkv + it.hkv) * D;
+      const int q0 = it.q0;
+      const int rr = row & (it.R - 1);
+      const bool valid = rr < it.nrows;
+      constexpr int SROW = 64 + 16;  // +16 B spreads the row-strided 16-byte stores over the banks
+      uint8_t* wbase = sStage + quarter * 32 * SROW;
+      uint8_t* srow = wbase + lane * SROW;
+      const int wr = lane >> 2, ch = lane & 3;  // write-out role: row within a group of 8, 16-byte chunk of the row
+      // destination of the four rows this lane writes out per 32-column round (nullptr: beyond the query tile)
+      __nv_bfloat16* orow[4];
+      {
+        const int rshift = 7 - (it.pack >> 1);  // log2(R)
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int trow = quarter * 32 + g8 * 8 + wr;  // tile row
+          const int orr = trow & (it.R - 1);
+          orow[g8] = orr < it.nrows ? p.out + it.b * p.so_b + static_cast<long long>(q0 + orr) * p.so_l +
+                                          (it.h + (trow >> rshift)) * p.so_h + ch * 8
+                                    : nullptr;
+        }
+      }
+      mbar_wait(&l_full[nq & 1], (nq >> 1) & 1);
+      const float l = l_buf[nq & 1][row];
+      mbar_arrive(&l_empty[nq & 1]);
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      mbar_wait(&o_full, nq & 1);
+      tc_fence_after();
+      STAMP(i, 3);
+      uint32_t r[16];
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[16];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // two 16-column loads per 32-column staging round (register budget)
+          tmem_ld_32x32b_x16(tmem_O + lane_addr + c * 32 + hh * 16, r);
+          tmem_ld_wait();
+          if (c == D / 32 - 1 && hh == 1) {
+            // O is in registers now: the next item's first P.V may overwrite it
+            tc_fence_before();
+            mbar_arrive(&o_empty);
+          }
+          if (l > 0.f) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2)
+              o[hh * 8 + (e >> 1)] = pack_bf16x2(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+          } else {
+            // no allowed key in the whole row: uniform softmax over all Skv keys = mean of V
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 f = valid ? *reinterpret_cast<const float4*>(vm + c * 32 + hh * 16 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+              o[hh * 8 + (e >> 1)] = pack_bf16x2(f.x, f.y);
+              o[hh * 8 + (e >> 1) + 1] = pack_bf16x2(f.z, f.w);
+            }
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(srow);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+        __syncwarp();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (orow[g8]) {
+            const uint4 val = *reinterpret_cast<const uint4*>(wbase + (g8 * 8 + wr) * SROW + ch * 16);
+            *reinterpret_cast<uint4*>(orow[g8] + c * 32) = val;
+          }
+        }
+        __syncwarp();
+      }
+      STAMP(i, 4);
+      if (g_timing_enabled() && lane == 0 && quarter == 0) g_timing_write(i, 5, it.n_kv), g_timing_write(i, 6, blockIdx.x);
+      ++nq;
+    }
+  } else if (warp >= 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
    if (warp == 4) {
     // ======================= TMA producer (Q, K) + scheduler =======================
     // The whole warp walks the loop (uniform control flow, uniform registers); single lanes are elected only to issue.
@@ -526,8 +626,8 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
    }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    // ======================= softmax + epilogue (warps 0..3) =======================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    // ======================= softmax (warps 0..3) =======================
     const int quarter = warp;  // TMEM lanes this warp may touch: [32*quarter, 32*quarter+32)
     const int row = quarter * 32 + lane;
     const int stid = tid;      // 0..127 among the softmax threads
@@ -713,79 +813,12 @@ sdag_prefill_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
 
-      // ---- epilogue: O / l -> bf16 -> staging rows in the (now idle) V buffer -> one bulk copy per row ----
+      // ---- hand the row sums to the epilogue warpgroup and move on to the next item ----
       STAMP(i, 2);
       TRACE(tr, 8);
-      mbar_wait(&o_full, nq & 1);
-      tc_fence_after();
-      STAMP(i, 3);
-      const bool valid = rr < it.nrows;
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      // Each warp stages its 32 rows, 32 columns at a time, in its private staging rows and writes them out itself
-      // with coalesced 16-byte stores: 8 rows x 64 B per instruction instead of 32 partial lines.
-      constexpr int SROW = 64 + 16;  // +16 B spreads the row-strided 16-byte stores over the banks
-      uint8_t* wbase = sStage + quarter * 32 * SROW;
-      uint8_t* srow = wbase + lane * SROW;
-      const int wr = lane >> 2, ch = lane & 3;  // write-out role: row within a group of 8, 16-byte chunk of the row
-      // destination of the four rows this lane writes out per 32-column round (nullptr: beyond the query tile)
-      __nv_bfloat16* orow[4];
-      {
-        const int rshift = 7 - (it.pack >> 1);  // log2(R)
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int trow = quarter * 32 + g8 * 8 + wr;  // tile row
-          const int orr = trow & (it.R - 1);
-          orow[g8] = orr < it.nrows ? p.out + it.b * p.so_b + static_cast<long long>(q0 + orr) * p.so_l +
-                                          (it.h + (trow >> rshift)) * p.so_h + ch * 8
-                                    : nullptr;
-        }
-      }
-      TRACE(tr, 5);
-      tmem_ld_32x32b_x32(tmem_O + lane_addr, r);
-#pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t* cur = (c & 1) ? r2 : r;
-        uint32_t* nxt = (c & 1) ? r : r2;
-        tmem_ld_wait();
-        if (c + 1 < D / 32) {
-          tmem_ld_32x32b_x32(tmem_O + lane_addr + (c + 1) * 32, nxt);
-        } else {
-          tc_fence_before();
-          mbar_arrive(&o_empty);  // O is in registers: the next item's first P.V may overwrite it
-        }
-        uint32_t o[16];
-        if (l > 0.f) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2)
-            o[e >> 1] = pack_bf16x2(__uint_as_float(cur[e]) * inv, __uint_as_float(cur[e + 1]) * inv);
-        } else {
-          // no allowed key in the whole row: uniform softmax over all Skv keys = mean of V
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 f = valid ? *reinterpret_cast<const float4*>(vm + c * 32 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-            o[e >> 1] = pack_bf16x2(f.x, f.y);
-            o[(e >> 1) + 1] = pack_bf16x2(f.z, f.w);
-          }
-        }
-        TRACE(tr, 6);
-        uint4* dst = reinterpret_cast<uint4*>(srow);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
-        __syncwarp();
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          if (orow[g8]) {
-            const uint4 val = *reinterpret_cast<const uint4*>(wbase + (g8 * 8 + wr) * SROW + ch * 16);
-            *reinterpret_cast<uint4*>(orow[g8] + c * 32) = val;
-          }
-        }
-        __syncwarp();
-        TRACE(tr, 7);
-      }
-      STAMP(i, 4);
-      if (g_timing_enabled() && threadIdx.x == 0) g_timing_write(i, 5, it.n_kv), g_timing_write(i, 6, blockIdx.x);
+      if (nq >= 2) mbar_wait(&l_empty[nq & 1], ((nq >> 1) - 1) & 1);
+      l_buf[nq & 1][row] = l;
+      mbar_arrive(&l_full[nq & 1]);
       ++nq;
     }
   }
@@ -901,7 +934,7 @@ int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtenso
   const long long n_items = static_cast<long long>(cap_qtiles) * p.H * p.B;
   if (n_items <= 0) return SDAG_ERR_INVALID;
   const long long grid = n_items < 2ll * n_sm ? n_items : 2ll * n_sm;
-  sdag_prefill_kernel<D><<<static_cast<unsigned>(grid), 256, smem, st>>>(tq, tq64, tq32, tk, tv, p, n_items);
+  sdag_prefill_kernel<D><<<static_cast<unsigned>(grid), 384, smem, st>>>(tq, tq64, tq32, tk, tv, p, n_items);
   return static_cast<int>(cudaGetLastError());
 }
 
