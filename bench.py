@@ -324,7 +324,7 @@ def run_b200(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 8 prompts
                      # (profiles/r01_ncu_sdag_prefill_cfg2.md); algorithmic q+k+v+out bytes are 433 MB
-                     "traffic": 522.6e6 * B / 8 if B == 8 else None,
+                     "traffic": 508.5e6 * B / 8 if B == 8 else None,
                      "kernel": "sdag_prefill_kernel<128> (+ v_colsum, v_mean) per layer launch",
                      "launch_ms": attn_avg_ms, "flops_per_launch": attn_flops_per_launch,
                      "peak_source": pk["_source"] + ", bf16 sustained", "unmasked_tiles": dense_tiles},
