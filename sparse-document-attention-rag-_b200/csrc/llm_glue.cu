@@ -528,27 +528,42 @@ gemv_mma_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   const uint4* sxv = rows_staged ? (g < rows_staged ? reinterpret_cast<const uint4*>(sx + static_cast<long long>(g) * KS) + t : nullptr)
                                  : (g < B ? reinterpret_cast<const uint4*>(x + static_cast<long long>(g) * K) + t : nullptr);
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-  constexpr int UN = 8;  // k-blocks per batch of loads: 16 independent 16-byte weight loads per lane in flight
+  constexpr int UN = 4;  // k-blocks per batch of loads: 8 independent 16-byte weight loads per lane and batch
   for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
     const uint4* wlo = row_ptr(blk, g);
     const uint4* whi = row_ptr(blk, g + 8);
     float c[4] = {0.f, 0.f, 0.f, 0.f};
-    int kb = kb0;
-    for (; kb + UN <= kb1; kb += UN) {
-      uint4 lo[UN], hi[UN];
+    // Register double-buffering: the loads of batch i+1 are issued before batch i is consumed, so a batch of UN * 2
+    // 16-byte loads per lane is always in flight.
+    uint4 la[UN], ha[UN], lb[UN], hb[UN];
+    auto load_batch = [&](uint4 (&lo)[UN], uint4 (&hi)[UN], int kb) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         lo[u] = ld_stream(wlo + (kb + u) * 4);
         hi[u] = ld_stream(whi + (kb + u) * 4);
       }
+    };
+    auto use_batch = [&](const uint4 (&lo)[UN], const uint4 (&hi)[UN], int kb) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const uint4 xv = sxv ? sxv[(kb + u) * 4] : zero4;
         mma_bf16_16816(c, lo[u].x, hi[u].x, lo[u].y, hi[u].y, xv.x, xv.y);
         mma_bf16_16816(c, lo[u].z, hi[u].z, lo[u].w, hi[u].w, xv.z, xv.w);
       }
+    };
+    int kb = kb0;
+    const int kb_main = kb0 + (kb1 - kb0) / UN * UN;
+    if (kb < kb_main) load_batch(la, ha, kb);
+    for (; kb < kb_main; kb += 2 * UN) {
+      const bool more1 = kb + UN < kb_main;
+      if (more1) load_batch(lb, hb, kb + UN);
+      use_batch(la, ha, kb);
+      if (more1) {
+        if (kb + 2 * UN < kb_main) load_batch(la, ha, kb + 2 * UN);
+        use_batch(lb, hb, kb + UN);
+      }
     }
-    for (; kb < kb1; ++kb) {
+    for (kb = kb_main; kb < kb1; ++kb) {
       const uint4 lo = ld_stream(wlo + kb * 4), hi = ld_stream(whi + kb * 4), xv = sxv ? sxv[kb * 4] : zero4;
       mma_bf16_16816(c, lo.x, hi.x, lo.y, hi.y, xv.x, xv.y);
       mma_bf16_16816(c, lo.z, hi.z, lo.w, hi.w, xv.z, xv.w);
