@@ -222,15 +222,27 @@ class B200Ranker:
         return out if convert_to_tensor else out.cpu().numpy()
 
 
-def encode_corpus(ranker: B200Ranker, texts: Sequence[str], prefix: str = "passage: ", chunk: int = 65536):
+def encode_corpus(ranker: B200Ranker, texts: Sequence[str], prefix: str = "passage: ", chunk: int = 8192):
     """"Encode corpus" (north star): a ``FlatIPIndex`` over the unit-norm embeddings of ``texts`` (e5 passage prefix,
     malicious_selection.py:25-29), with the pooled rows written by the encoder's last kernel directly into the index's
-    fp32 rows and bf16 shadow — no host round trip, no second cast pass."""
+    fp32 rows and bf16 shadow — no host round trip, no second cast pass.  The host tokenizer of chunk i+1 runs on a
+    worker thread (fast tokenizers release the GIL) while the GPU encodes chunk i."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from .retrieval import FlatIPIndex
 
     n, dim = len(texts), ranker.get_sentence_embedding_dimension()
     f32 = torch.empty((n, dim), dtype=torch.float32, device=ranker.device)
     b16 = torch.empty((n, dim), dtype=torch.bfloat16, device=ranker.device)
-    for r0 in range(0, n, chunk):
-        ranker.encode_into([prefix + t for t in texts[r0 : r0 + chunk]], f32, b16, row0=r0)
+    starts = list(range(0, n, chunk))
+
+    def tokenize(r0):
+        return ranker._tokenize([prefix + t for t in texts[r0 : r0 + chunk]])
+
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        pending = pool.submit(tokenize, starts[0]) if starts else None
+        for k, r0 in enumerate(starts):
+            toks = pending.result()
+            pending = pool.submit(tokenize, starts[k + 1]) if k + 1 < len(starts) else None
+            ranker.encode_tokens_into(toks, f32, b16, row0=r0)
     return FlatIPIndex.from_encoded(f32, b16)
