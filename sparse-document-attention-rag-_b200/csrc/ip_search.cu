@@ -26,6 +26,9 @@ namespace {
 constexpr int TM = 128;      // queries per tile (UMMA M)
 constexpr int TN = 256;      // corpus rows per tile (UMMA N)
 constexpr int KB = 64;       // k-block (one 128-byte swizzle row of bf16)
+#ifndef SDAG_IP_USE_2CTA
+#define SDAG_IP_USE_2CTA 1
+#endif
 constexpr int STAGES = 4;
 constexpr int A_BYTES = TM * KB * 2;
 constexpr int B_BYTES = TN * KB * 2;
@@ -225,6 +228,157 @@ ip_gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Same GEMM + filter on CTA pairs (cta_group::2): one MMA covers 256 queries x 256 corpus rows, each CTA of the pair holds
+// its own 128 queries (A) and its own 128 of the 256 corpus rows (B) per k-block, so the shared-memory operand traffic per
+// SM and MMA drops from 128 + 256 to 128 + 128 rows — the SS-mode operand fetch is what keeps the single-CTA kernel at
+// ~75 % of the tensor pipe.  The leader (rank 0) issues the MMAs; both CTAs run TMA producers and filter epilogues.
+// ------------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr int B2_BYTES = (TN / 2) * KB * 2;
+constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;
+constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+ip_gemm_filter_kernel_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[STAGES2], empty[STAGES2], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full[s], 1);   // (leader's copy is the live one) the leader's producer expects the bytes of both CTAs
+      mbar_init(&empty[s], 1);  // multicast commit of the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);     // multicast commit of the leader
+      mbar_init(&acc_empty[a], 8);    // (leader's copy) one arrival per epilogue warp of both CTAs
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBh);
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(&tmem_base_s, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int n_qt2 = (p.n_qt + 1) / 2;
+  const long long n_units = static_cast<long long>(p.n_ct) * n_qt2;
+  const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long u = pair; u < n_units; u += n_pairs) {
+        const int ct = static_cast<int>(u / n_qt2), qt2 = static_cast<int>(u % n_qt2);
+        const int row0 = static_cast<int>(p.row_begin + static_cast<long long>(ct) * TN) + static_cast<int>(rank) * (TN / 2);
+        const int q0 = (qt2 * 2 + static_cast<int>(rank)) * TM;
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % STAGES2;
+          mbar_wait(&empty[s], ((it / STAGES2) & 1) ^ 1);
+          // The peer's bytes may complete on the leader's barrier before the leader has announced them (the
+          // transaction count goes negative meanwhile); no remote arrive, hence no cluster-scope release per stage.
+          const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+          if (leader) mbar_expect_tx(&full[s], 2 * STAGE2_BYTES);
+          uint8_t* sa = smem + s * STAGE2_BYTES;
+          tma_load_2d_2sm(sa, &tmA, lead_full, kb * KB, q0);
+          tma_load_2d_2sm(sa + A_BYTES, &tmBh, lead_full, kb * KB, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader only) =======================
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16_f32(2 * TM, TN, 0, 0);
+      uint32_t it = 0, ui = 0;
+      for (long long u = pair; u < n_units; u += n_pairs, ++ui) {
+        const uint32_t a = ui & 1;
+        mbar_wait(&acc_empty[a], ((ui >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % STAGES2;
+          mbar_wait(&full[s], (it / STAGES2) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE2_BYTES);
+          const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024), db = umma_smem_desc_sw128(sa + A_BYTES, 16, 1024);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < KB / 16; ++kk)
+              umma_ss_2cta(tmem + a * TN, da + ((kk * 32) >> 4), db + ((kk * 32) >> 4), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            umma_commit_2cta(&empty[s], 3);
+            if (kb == p.kblocks - 1) umma_commit_2cta(&acc_full[a], 3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue: threshold filter (warps 2..5, both CTAs) =======================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t ui = 0;
+    uint32_t r[32];
+    for (long long u = pair; u < n_units; u += n_pairs, ++ui) {
+      const int ct = static_cast<int>(u / n_qt2), qt2 = static_cast<int>(u % n_qt2);
+      const uint32_t a = ui & 1;
+      const int q = (qt2 * 2 + static_cast<int>(rank)) * TM + row;
+      const bool q_ok = q < p.Q;
+      const float thr = q_ok ? p.st.thr[q] : INFINITY;
+      const long long col0 = p.row_begin + static_cast<long long>(ct) * TN;
+      Cand* cq = p.st.cand + static_cast<long long>(q_ok ? q : 0) * p.st.cap;
+      mbar_wait(&acc_full[a], (ui >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < TN / 32; ++c) {
+        tmem_ld_32x32b_x32(tmem + lane_addr + a * TN + c * 32, r);
+        tmem_ld_wait();
+        const long long cb = col0 + c * 32;
+        if (p.dump) {
+          if (q_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const long long rr = cb + i;
+              if (rr < p.row_end) cq[rr - p.row_begin] = Cand{__uint_as_float(r[i]), static_cast<int32_t>(rr)};
+            }
+          }
+        } else {
+          float mx = __uint_as_float(r[0]);
+#pragma unroll
+          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          if (mx >= thr) {  // rare: fully unrolled so r[] stays in registers
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float s = __uint_as_float(r[i]);
+              if (s >= thr && cb + i < p.row_end) {
+                const int slot = atomicAdd(&p.st.cnt[q], 1);
+                if (slot < p.st.cap) cq[slot] = Cand{s, static_cast<int32_t>(cb + i)};
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[a]), 0));  // the leader's barrier gates both CTAs' accumulators
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody may still be reading the peer's shared memory / TMEM when a CTA tears down
+  if (warp == 1) tmem_dealloc_2cta(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -572,10 +726,18 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
       uint32_t box[2] = {KB, TN};
       if (make_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, corpus_bf16, dims, str, box)) return SDAG_ERR_DRIVER;
     }
+    CUtensorMap tmBh;  // half corpus tiles for the CTA-pair kernel
+    {
+      uint64_t dims[2] = {static_cast<uint64_t>(d), static_cast<uint64_t>(N)};
+      uint64_t str[1] = {static_cast<uint64_t>(d) * 2};
+      uint32_t box[2] = {KB, TN / 2};
+      if (make_tmap(&tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, corpus_bf16, dims, str, box)) return SDAG_ERR_DRIVER;
+    }
     static bool configured = false;
     static int n_sm = 148;
     if (!configured) {
       SDAG_CUDA_TRY(cudaFuncSetAttribute(ip_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+      SDAG_CUDA_TRY(cudaFuncSetAttribute(ip_gemm_filter_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
       int dev = 0;
       SDAG_CUDA_TRY(cudaGetDevice(&dev));
       SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -599,8 +761,15 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
       gp.n_ct = static_cast<int>((end - begin + TN - 1) / TN);
       gp.dump = first ? 1 : 0;
       const long long units = static_cast<long long>(gp.n_ct) * gp.n_qt;
-      const int grid = static_cast<int>(units < n_sm ? units : n_sm);
-      ip_gemm_filter_kernel<<<grid, 192, GEMM_SMEM, st>>>(tmA, tmB, gp);
+      // CTA pairs (256 x 256 MMAs) once a batch has at least two query tiles; the single-CTA kernel otherwise
+      if (SDAG_IP_USE_2CTA && gp.n_qt >= 2) {
+        const long long units2 = static_cast<long long>(gp.n_ct) * ((gp.n_qt + 1) / 2);
+        const long long pairs = units2 < n_sm / 2 ? units2 : n_sm / 2;
+        ip_gemm_filter_kernel_2cta<<<static_cast<unsigned>(2 * pairs), 192, GEMM2_SMEM, st>>>(tmA, tmBh, gp);
+      } else {
+        const int grid = static_cast<int>(units < n_sm ? units : n_sm);
+        ip_gemm_filter_kernel<<<grid, 192, GEMM_SMEM, st>>>(tmA, tmB, gp);
+      }
       tighten_kernel<<<Q, 256, 0, st>>>(state, k, first ? static_cast<int>(end - begin) : -1, max_norm_dev);
       SDAG_CUDA_TRY(cudaGetLastError());
       if (!first) span *= 2;
