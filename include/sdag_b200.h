@@ -181,6 +181,16 @@ int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out,
                  const int32_t* pos0_dev, int pos0_dev_stride, void* stream);
 /* LlamaMLP activation: gate_up [rows, 2*inter] (gate first) -> out [rows, inter] = silu(gate) * up. */
 int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* stream);
+/* Prefill linear layer (the q/k/v, o, gate/up and down projections HF runs inside the prefill forward,
+ * SDAG.py:175-176 -> LlamaAttention / LlamaMLP): out [M, N] = x [M, K] . weight [N, K]^T (+ bias), bf16 with fp32
+ * accumulation on CTA pairs (tcgen05 cta_group::2).  x rows ldx elements apart, out rows ldo apart; K, ldx,
+ * ldo, N multiples of 8, 16-byte aligned pointers.  epilogue LLM_GEMM_SWIGLU: weight is the fused [gate; up]
+ * matrix (N = 2*I rows, no bias) and out [M, I] = silu(gate) * up with the LlamaMLP bf16 roundings — the
+ * [M, 2*I] intermediate is never written. */
+#define LLM_GEMM_PLAIN 0
+#define LLM_GEMM_SWIGLU 1
+int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
+             int N, int K, int epilogue, void* stream);
 /* Decode-step linear layer (SDAG.py:191-211, one token per prompt, B <= 4): out [B,N] = xin [B,K] . weight[N,K]^T
  * (+ bias) (+ residual [B,N]), weight rows streamed once.  prologue 0: xin = x [B,K]; 1: xin = RMSNorm(x) *
  * norm_weight (eps); 2: x is a gate|up row [B,2K] and xin = silu(gate) * up.  pair_swiglu != 0: weight is a

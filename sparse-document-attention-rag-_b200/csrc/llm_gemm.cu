@@ -1,0 +1,292 @@
+// Prefill linear layers of the decoder (path A4): out[M, N] = x[M, K] . W[N, K]^T in bf16 with fp32 accumulation — the
+// q/k/v, o, gate/up and down projections HF runs inside generate_with_custom_mask's prefill forward (SDAG.py:175-176 ->
+// LlamaAttention / LlamaMLP, models/llama/modeling_llama.py).  Written for CTA pairs: one tcgen05.mma.cta_group::2 covers
+// 256 token rows x 256 weight rows; each CTA of the pair keeps its own 128 token rows (A) and its own 128 of the 256
+// weight rows (B) per 64-wide k-block in shared memory, the fp32 accumulators (2 x 256 columns, double buffered) live in
+// each CTA's TMEM.  The epilogue converts straight out of TMEM:
+//   LLM_GEMM_PLAIN   out = bf16(acc + bias)
+//   LLM_GEMM_SWIGLU  W = [gate; up] rows (N = 2*I): every MMA holds 128 gate rows and the 128 matching up rows, and
+//                    out[M, I] = bf16(bf16(silu(g)) * u) with g, u rounded to bf16 first — the roundings of LlamaMLP with
+//                    a bf16 gate_proj / up_proj — so the [M, 2*I] intermediate never reaches HBM.
+// Same pipeline as the retrieval GEMM (ip_search.cu): warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA),
+// warps 2-5 epilogue; the leader's producer announces the bytes of both CTAs so the stage loop has no remote arrive.
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int TMH = 128;   // token rows per CTA (the pair's MMA has M = 256)
+constexpr int TNP = 256;   // MMA N: weight rows per pair tile, 128 per CTA
+constexpr int KB = 64;     // k-block: one 128-byte swizzle row of bf16
+constexpr int STAGES = 6;
+constexpr int A_BYTES = TMH * KB * 2;
+constexpr int BQ_BYTES = 64 * KB * 2;  // one 64-row box of weight rows; a CTA loads two per k-block
+constexpr int STAGE_BYTES = A_BYTES + 2 * BQ_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+constexpr int GROUP_N = 8;  // weight tiles per raster group: one wave of 74 pairs touches ~8 weight and ~9 token tiles
+
+struct Params {
+  const __nv_bfloat16* bias;  // [N] or null
+  __nv_bfloat16* out;
+  long long ldo;  // elements
+  long long M;
+  int n_out;      // output columns (N, or I for SwiGLU)
+  int n_mt, n_nt; // pair tiles along M (256 rows) and N
+  int kblocks;
+  int up_offset;  // SwiGLU: first up row (= I)
+};
+
+struct Unit {
+  int mt, nt;
+};
+__device__ __forceinline__ Unit unit_of(long long u, const Params& p) {
+  const long long per_group = static_cast<long long>(GROUP_N) * p.n_mt;
+  const int g = static_cast<int>(u / per_group);
+  const int rem = static_cast<int>(u - g * per_group);
+  const int gn = min(GROUP_N, p.n_nt - g * GROUP_N);
+  return Unit{rem / gn, g * GROUP_N + rem % gn};
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);   // (leader's copy is live) the leader's producer expects the bytes of both CTAs
+      mbar_init(&empty[s], 1);  // multicast commit of the leader
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);   // multicast commit of the leader
+      mbar_init(&acc_empty[a], 8);  // (leader's copy) one arrival per epilogue warp of both CTAs
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(&tmem_base_s, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const long long n_units = static_cast<long long>(p.n_mt) * p.n_nt;
+  const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long u = pair; u < n_units; u += n_pairs) {
+        const Unit un = unit_of(u, p);
+        const int m0 = un.mt * 2 * TMH + static_cast<int>(rank) * TMH;
+        int w0, w1;  // first weight row of this CTA's two 64-row boxes
+        if (EPI == LLM_GEMM_SWIGLU) {
+          w0 = un.nt * 128 + static_cast<int>(rank) * 64;  // gate rows
+          w1 = p.up_offset + w0;                            // the matching up rows
+        } else {
+          w0 = un.nt * TNP + static_cast<int>(rank) * 128;
+          w1 = w0 + 64;
+        }
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+          if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          tma_load_2d_2sm(sa, &tmX, lead_full, kb * KB, m0);
+          tma_load_2d_2sm(sa + A_BYTES, &tmW, lead_full, kb * KB, w0);
+          tma_load_2d_2sm(sa + A_BYTES + BQ_BYTES, &tmW, lead_full, kb * KB, w1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader only) =======================
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16_f32(2 * TMH, TNP, 0, 0);
+      uint32_t it = 0, ui = 0;
+      for (long long u = pair; u < n_units; u += n_pairs, ++ui) {
+        const uint32_t a = ui & 1;
+        mbar_wait(&acc_empty[a], ((ui >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024), db = umma_smem_desc_sw128(sa + A_BYTES, 16, 1024);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < KB / 16; ++kk)
+              umma_ss_2cta(tmem + a * TNP, da + ((kk * 32) >> 4), db + ((kk * 32) >> 4), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            umma_commit_2cta(&empty[s], 3);
+            if (kb == p.kblocks - 1) umma_commit_2cta(&acc_full[a], 3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue (warps 2..5, both CTAs): TMEM -> bf16 rows =======================
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t ui = 0;
+    for (long long u = pair; u < n_units; u += n_pairs, ++ui) {
+      const Unit un = unit_of(u, p);
+      const uint32_t a = ui & 1;
+      const long long m = static_cast<long long>(un.mt) * 2 * TMH + static_cast<long long>(rank) * TMH + quarter * 32 + lane;
+      const bool m_ok = m < p.M;
+      __nv_bfloat16* orow = p.out + (m_ok ? m : 0) * p.ldo;
+      mbar_wait(&acc_full[a], (ui >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem + lane_addr + a * TNP;
+      if (EPI == LLM_GEMM_SWIGLU) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {  // (half, 32-column chunk): gate at half*128 + chunk*32, up 64 columns further
+          uint32_t g[32], v[32];
+          const int hc = (c >> 1) * 128 + (c & 1) * 32;
+          tmem_ld_32x32b_x32(tacc + hc, g);
+          tmem_ld_32x32b_x32(tacc + hc + 64, v);
+          tmem_ld_wait();
+          const int col0 = un.nt * 128 + (c >> 1) * 64 + (c & 1) * 32;
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float g0 = bf_round(__uint_as_float(g[2 * i])), g1 = bf_round(__uint_as_float(g[2 * i + 1]));
+            const float u0 = bf_round(__uint_as_float(v[2 * i])), u1 = bf_round(__uint_as_float(v[2 * i + 1]));
+            o[i] = pack_bf16x2(bf_round(g0 / (1.f + __expf(-g0))) * u0, bf_round(g1 / (1.f + __expf(-g1))) * u1);
+          }
+          if (m_ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (col0 + 8 * i + 8 <= p.n_out)
+                *reinterpret_cast<uint4*>(orow + col0 + 8 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < TNP / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tacc + c * 32, r);
+          tmem_ld_wait();
+          const int col0 = un.nt * TNP + c * 32;
+          uint32_t o[16];
+          if (p.bias != nullptr && col0 + 32 <= p.n_out) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 bv = __ldg(bp + i);
+              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+                o[4 * i + j] = pack_bf16x2(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float b0 = 0.f, b1 = 0.f;
+              if (p.bias != nullptr && col0 + 2 * i + 1 < p.n_out) {
+                b0 = __bfloat162float(p.bias[col0 + 2 * i]);
+                b1 = __bfloat162float(p.bias[col0 + 2 * i + 1]);
+              }
+              o[i] = pack_bf16x2(__uint_as_float(r[2 * i]) + b0, __uint_as_float(r[2 * i + 1]) + b1);
+            }
+          }
+          if (m_ok) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (col0 + 8 * i + 8 <= p.n_out)
+                *reinterpret_cast<uint4*>(orow + col0 + 8 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[a]), 0));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody may still read the peer's shared memory / TMEM when a CTA tears down
+  if (warp == 1) tmem_dealloc_2cta(tmem, 512);
+}
+
+}  // namespace
+
+extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
+                        int N, int K, int epilogue, void* stream) {
+  if (!x || !weight || !out || M < 0 || N <= 0 || K <= 0) return SDAG_ERR_INVALID;
+  if (epilogue != LLM_GEMM_PLAIN && epilogue != LLM_GEMM_SWIGLU) return SDAG_ERR_INVALID;
+  if ((K % 8) || (ldx % 8) || (ldo % 8) || ldx < K) return SDAG_ERR_INVALID;  // 16-byte rows for TMA and the stores
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return SDAG_ERR_INVALID;
+  const bool swiglu = epilogue == LLM_GEMM_SWIGLU;
+  if (swiglu && ((N % 16) || bias)) return SDAG_ERR_INVALID;
+  if (!swiglu && (N % 8)) return SDAG_ERR_INVALID;
+  const int n_out = swiglu ? N / 2 : N;
+  if (ldo < n_out) return SDAG_ERR_INVALID;
+  if (M == 0) return SDAG_OK;
+  if (M > (1ll << 31) - 512) return SDAG_ERR_UNSUPPORTED;
+
+  CUtensorMap tmX, tmW;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t str[1] = {static_cast<uint64_t>(ldx) * 2};
+    uint32_t box[2] = {KB, TMH};
+    if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, x, dims, str, box)) return SDAG_ERR_DRIVER;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t str[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {KB, 64};
+    if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, weight, dims, str, box)) return SDAG_ERR_DRIVER;
+  }
+  static bool configured = false;
+  static int n_sm = 148;
+  if (!configured) {
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    int dev = 0;
+    SDAG_CUDA_TRY(cudaGetDevice(&dev));
+    SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  Params p;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.M = M;
+  p.n_out = n_out;
+  p.n_mt = static_cast<int>((M + 2 * TMH - 1) / (2 * TMH));
+  p.n_nt = swiglu ? (n_out + 127) / 128 : (N + TNP - 1) / TNP;
+  p.kblocks = (K + KB - 1) / KB;
+  p.up_offset = n_out;
+  const long long units = static_cast<long long>(p.n_mt) * p.n_nt;
+  const long long pairs = units < n_sm / 2 ? units : n_sm / 2;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (swiglu)
+    llm_gemm_kernel<LLM_GEMM_SWIGLU><<<static_cast<unsigned>(2 * pairs), 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else
+    llm_gemm_kernel<LLM_GEMM_PLAIN><<<static_cast<unsigned>(2 * pairs), 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -157,10 +157,16 @@ class FusedPrefill:
         inner = self.model.model
         o = F.linear(attn_rows, ly["wo"], ly["bo"])
         resid, normed = _rmsnorm(o, resid, ly["w_post"], ly["eps_post"])
-        gu = F.linear(normed, ly["wgu"])
-        act = torch.empty((gu.shape[0], self.inter), dtype=torch.bfloat16, device=gu.device)
+        rows = normed.shape[0]
+        act = torch.empty((rows, self.inter), dtype=torch.bfloat16, device=normed.device)
         _lib.count_launches(1)
-        _lib.check(lib.llm_swiglu(gu.data_ptr(), act.data_ptr(), gu.shape[0], self.inter, _lib.stream_ptr(gu.device)), "llm_swiglu")
+        if rows >= PAIR_GEMM_MIN_ROWS and self.inter % 8 == 0:
+            # gate/up GEMM on CTA pairs with the SwiGLU in its epilogue: the [rows, 2*inter] intermediate is never written
+            _lib.check(lib.llm_gemm(normed.data_ptr(), normed.stride(0), ly["wgu"].data_ptr(), 0, act.data_ptr(), self.inter,
+                                    rows, 2 * self.inter, self.hidden, 1, _lib.stream_ptr(normed.device)), "llm_gemm")
+        else:
+            gu = F.linear(normed, ly["wgu"])
+            _lib.check(lib.llm_swiglu(gu.data_ptr(), act.data_ptr(), rows, self.inter, _lib.stream_ptr(gu.device)), "llm_swiglu")
         d = F.linear(act, ly["wdown"])
         if i + 1 < len(self.layers):
             nxt = self.layers[i + 1]
@@ -346,6 +352,7 @@ class FusedPrefill:
         return c["gen"][:, : done + 1].clone()
 
 
+PAIR_GEMM_MIN_ROWS = 512  # prefill gate/up projections with at least this many token rows run on llm_gemm (fused SwiGLU)
 USE_FUSED_GEMV = True  # decode-step linear layers on llm_gemv (B <= 4); False: cuBLAS + stand-alone glue kernels
 
 

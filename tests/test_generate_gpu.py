@@ -594,3 +594,69 @@ def test_fused_gemv_decode_step_equals_cublas_step():
         fd = next((i for i, (x, y) in enumerate(zip(row_a, row_b)) if x != y), len(row_a))
         assert fd >= 8, (row_a, row_b)
     assert sum(ra == rb for ra, rb in zip(a.tolist(), b.tolist())) >= 1
+
+
+@pytest.mark.parametrize("M,N,K,ldx_pad", [(300, 264, 72, 0), (1000, 512, 256, 8), (129, 8, 64, 0), (2048, 768, 1024, 0), (1, 256, 4096, 0)])
+def test_prefill_gemm_matches_linear(M, N, K, ldx_pad):
+    """llm_gemm (CTA-pair tcgen05 GEMM) vs torch's linear on the same bf16 operands, ragged M / N / K edges, strided rows,
+    bias; rows and columns outside [M, N] are never written."""
+    import sdag_b200._lib as L
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    xs = torch.randn(M, K + ldx_pad, generator=g, device="cuda").to(torch.bfloat16)
+    x = xs[:, :K]
+    W = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    st = L.stream_ptr(x.device)
+    for b in (None, bias):
+        buf = torch.full((M + 3, N + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+        L.check(lib.llm_gemm(x.data_ptr(), xs.stride(0), W.data_ptr(), L.ptr(b), buf.data_ptr(), buf.stride(0), M, N, K, 0, st), "llm_gemm")
+        ref = torch.nn.functional.linear(x.float(), W.float(), None if b is None else b.float()).to(torch.bfloat16)
+        torch.testing.assert_close(buf[:M, :N].float(), ref.float(), atol=2e-2, rtol=2e-2)
+        assert (buf[:M, :N] == ref).float().mean() > 0.97  # one rounding of an fp32 sum; only the summation order differs
+        assert (buf[M:] == 7.0).all() and (buf[:, N:] == 7.0).all()
+    assert lib.llm_gemm(x.data_ptr(), xs.stride(0), W.data_ptr(), 0, buf.data_ptr(), buf.stride(0), M, N + 1, K, 0, st) == 1001
+    assert lib.llm_gemm(0, K, W.data_ptr(), 0, buf.data_ptr(), buf.stride(0), M, N, K, 0, st) == 1001
+
+
+@pytest.mark.parametrize("M,I,K", [(700, 200, 136), (512, 1024, 512), (260, 64, 64), (3000, 14336 // 8, 4096 // 4)])
+def test_prefill_gemm_swiglu_epilogue_matches_mlp_roundings(M, I, K):
+    """llm_gemm with the SwiGLU epilogue vs linear -> llm_swiglu (the unfused path, LlamaMLP's bf16 rounding order)."""
+    import sdag_b200._lib as L
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(M + I)
+    x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    Wgu = (torch.randn(2 * I, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    st = L.stream_ptr(x.device)
+    out = torch.full((M + 1, I + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.llm_gemm(x.data_ptr(), K, Wgu.data_ptr(), 0, out.data_ptr(), out.stride(0), M, 2 * I, K, 1, st), "llm_gemm swiglu")
+    gu = torch.nn.functional.linear(x.float(), Wgu.float()).to(torch.bfloat16)
+    ref = torch.nn.functional.silu(gu[:, :I]) * gu[:, I:]
+    torch.testing.assert_close(out[:M, :I].float(), ref.float(), atol=3e-2, rtol=3e-2)
+    assert (out[:M, :I] == ref).float().mean() > 0.9
+    assert (out[M:] == 7.0).all() and (out[:, I:] == 7.0).all()
+    unfused = torch.empty(M, I, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.llm_swiglu(gu.data_ptr(), unfused.data_ptr(), M, I, st), "llm_swiglu")
+    torch.testing.assert_close(out[:M, :I].float(), unfused.float(), atol=3e-2, rtol=3e-2)
+    assert lib.llm_gemm(x.data_ptr(), K, Wgu.data_ptr(), x.data_ptr(), out.data_ptr(), out.stride(0), M, 2 * I, K, 1, st) == 1001  # no bias here
+
+
+def test_fused_prefill_with_pair_gemm_matches_cublas_path(monkeypatch):
+    """The prefill engine with gate/up on llm_gemm (fused SwiGLU) vs the same engine on cuBLAS + llm_swiglu."""
+    import sdag_b200.llama_runner as lr
+    import sdag_b200.sdag as sdag
+
+    tok = synth.make_tokenizer()
+    model = _bf16_model(tok)
+    runner = lr.get_runner(sdag.prepare_model(model))
+    assert runner is not None
+    ids = torch.randint(5, len(tok), (2, 384), device="cuda")
+    bm = sdag.causal_blockmap(384, ids.device)
+    monkeypatch.setattr(lr, "PAIR_GEMM_MIN_ROWS", 1 << 30)
+    ref, _ = runner.prefill(ids, bm, want_cache=False)
+    monkeypatch.setattr(lr, "PAIR_GEMM_MIN_ROWS", 1)
+    got, _ = runner.prefill(ids, bm, want_cache=False)
+    torch.testing.assert_close(got.float(), ref.float(), atol=5e-2, rtol=5e-2)
+    assert (got.argmax(-1) == ref.argmax(-1)).all()

@@ -1,0 +1,67 @@
+"""llm_gemm (CTA-pair tcgen05 GEMM) vs cuBLAS on the Llama-3-8B prefill shapes.
+
+    python tools/gemm_bench.py [--tokens 21248]
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sdag_b200  # noqa: E402
+from sdag_b200 import _lib  # noqa: E402
+
+
+def timed(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--tokens", type=int, default=21248)
+    args = ap.parse_args()
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    M = args.tokens
+    st = _lib.stream_ptr(dev)
+    torch.manual_seed(0)
+    for name, N, K, epi in (("qkv", 6144, 4096, 0), ("o", 4096, 4096, 0), ("gate_up", 28672, 4096, 0),
+                            ("gate_up+swiglu", 28672, 4096, 1), ("down", 4096, 14336, 0)):
+        x = torch.randn(M, K, device=dev, dtype=torch.bfloat16) * 0.5
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.02
+        n_out = N // 2 if epi else N
+        out = torch.empty(M, n_out, device=dev, dtype=torch.bfloat16)
+
+        def ours():
+            _lib.check(lib.llm_gemm(x.data_ptr(), K, w.data_ptr(), 0, out.data_ptr(), n_out, M, N, K, epi, st), "llm_gemm")
+
+        act = torch.empty(M, N // 2, device=dev, dtype=torch.bfloat16)
+
+        def cublas():
+            y = torch.nn.functional.linear(x, w)
+            if epi:
+                _lib.check(lib.llm_swiglu(y.data_ptr(), act.data_ptr(), M, N // 2, st), "swiglu")
+            return y
+
+        t_o, t_c = timed(ours), timed(cublas)
+        ref = cublas()
+        ref = act if epi else ref
+        ours()
+        err = (out.float() - ref.float()).abs().max().item()
+        fl = 2.0 * M * N * K
+        print(f"{name:16s} M={M} N={N} K={K}: llm_gemm {t_o:.3f} ms ({fl / t_o / 1e9:.0f} TFLOP/s)  cuBLAS{'+swiglu' if epi else ''} "
+              f"{t_c:.3f} ms ({fl / t_c / 1e9:.0f} TFLOP/s)  max|diff| {err:.4f}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
