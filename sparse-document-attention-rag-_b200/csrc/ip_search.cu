@@ -279,23 +279,26 @@ ip_gemm_filter_kernel_2cta(const __grid_constant__ CUtensorMap tmA, const __grid
 
   if (warp == 0) {
     // ======================= TMA producer (both CTAs) =======================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (long long u = pair; u < n_units; u += n_pairs) {
-        const int ct = static_cast<int>(u / n_qt2), qt2 = static_cast<int>(u % n_qt2);
-        const int row0 = static_cast<int>(p.row_begin + static_cast<long long>(ct) * TN) + static_cast<int>(rank) * (TN / 2);
-        const int q0 = (qt2 * 2 + static_cast<int>(rank)) * TM;
-        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-          const int s = it % STAGES2;
-          mbar_wait(&empty[s], ((it / STAGES2) & 1) ^ 1);
-          // The peer's bytes may complete on the leader's barrier before the leader has announced them (the
-          // transaction count goes negative meanwhile); no remote arrive, hence no cluster-scope release per stage.
-          const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+    // warp-uniform control flow, one elected lane issues (no per-lane operands -> no uniform-register broadcast loops)
+    const uint32_t lead_full0 = mapa_shared(smem_u32(&full[0]), 0);
+    uint32_t it = 0;
+    for (long long u = pair; u < n_units; u += n_pairs) {
+      const int ct = static_cast<int>(u / n_qt2), qt2 = static_cast<int>(u % n_qt2);
+      const int row0 = static_cast<int>(p.row_begin + static_cast<long long>(ct) * TN) + static_cast<int>(rank) * (TN / 2);
+      const int q0 = (qt2 * 2 + static_cast<int>(rank)) * TM;
+      for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+        const int s = it % STAGES2;
+        mbar_wait(&empty[s], ((it / STAGES2) & 1) ^ 1);
+        // The peer's bytes may complete on the leader's barrier before the leader has announced them (the
+        // transaction count goes negative meanwhile); no remote arrive, hence no cluster-scope release per stage.
+        const uint32_t lead_full = lead_full0 + s * 8;
+        uint8_t* sa = smem + s * STAGE2_BYTES;
+        if (elect_one()) {
           if (leader) mbar_expect_tx(&full[s], 2 * STAGE2_BYTES);
-          uint8_t* sa = smem + s * STAGE2_BYTES;
           tma_load_2d_2sm(sa, &tmA, lead_full, kb * KB, q0);
           tma_load_2d_2sm(sa + A_BYTES, &tmBh, lead_full, kb * KB, row0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {

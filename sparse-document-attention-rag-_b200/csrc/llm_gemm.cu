@@ -10,6 +10,8 @@
 //                    a bf16 gate_proj / up_proj — so the [M, 2*I] intermediate never reaches HBM.
 // Same pipeline as the retrieval GEMM (ip_search.cu): warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA),
 // warps 2-5 epilogue; the leader's producer announces the bytes of both CTAs so the stage loop has no remote arrive.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -25,7 +27,7 @@ constexpr int A_BYTES = TMH * KB * 2;
 constexpr int BQ_BYTES = 64 * KB * 2;  // one 64-row box of weight rows; a CTA loads two per k-block
 constexpr int STAGE_BYTES = A_BYTES + 2 * BQ_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
-constexpr int GROUP_N = 8;  // weight tiles per raster group: one wave of 74 pairs touches ~8 weight and ~9 token tiles
+constexpr int GROUP_N = 16;  // most weight tiles per raster group (one wave of 74 pairs then touches 16 weight and ~5 token tiles)
 
 struct Params {
   const __nv_bfloat16* bias;  // [N] or null
@@ -36,17 +38,19 @@ struct Params {
   int n_mt, n_nt; // pair tiles along M (256 rows) and N
   int kblocks;
   int up_offset;  // SwiGLU: first up row (= I)
+  int group_n;    // weight tiles per raster group
+  uint64_t hint_x, hint_w;  // L2 eviction priorities of the two operand streams
 };
 
 struct Unit {
   int mt, nt;
 };
 __device__ __forceinline__ Unit unit_of(long long u, const Params& p) {
-  const long long per_group = static_cast<long long>(GROUP_N) * p.n_mt;
+  const long long per_group = static_cast<long long>(p.group_n) * p.n_mt;
   const int g = static_cast<int>(u / per_group);
   const int rem = static_cast<int>(u - g * per_group);
-  const int gn = min(GROUP_N, p.n_nt - g * GROUP_N);
-  return Unit{rem / gn, g * GROUP_N + rem % gn};
+  const int gn = min(p.group_n, p.n_nt - g * p.group_n);
+  return Unit{rem / gn, g * p.group_n + rem % gn};
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -55,7 +59,39 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 __device__ __forceinline__ float bf_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-template <int EPI>
+// One 32-column bf16 chunk (64 bytes) of this thread's output row.  Lane pairs exchange halves so that every store
+// instruction of the warp writes whole 32-byte sectors (even lane: first 16 bytes, odd lane: the other 16) instead of
+// two half-written sectors per row.
+__device__ __forceinline__ void store_chunk(__nv_bfloat16* row_even, __nv_bfloat16* row_odd, bool ok_even, bool ok_odd,
+                                            int col0, int n_out, const uint32_t (&o)[16], int lane) {
+  const bool odd = lane & 1;
+  uint32_t give[8], got[8];  // even lane gives 16-byte pieces 1 and 3 of its row, odd lane pieces 0 and 2
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    give[i] = odd ? o[i] : o[4 + i];
+    give[4 + i] = odd ? o[8 + i] : o[12 + i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) got[i] = __shfl_xor_sync(0xffffffffu, give[i], 1);
+  // sector t of (row_even: t = 0, 1; row_odd: t = 2, 3): even lane writes bytes [32 (t&1), +16), odd lane the next 16
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const bool to_even_row = t < 2;
+    const int sec = t & 1;
+    uint4 v;
+    if (to_even_row)  // even lane: own piece 2*sec; odd lane: partner's piece 2*sec + 1
+      v = odd ? make_uint4(got[4 * sec], got[4 * sec + 1], got[4 * sec + 2], got[4 * sec + 3])
+              : make_uint4(o[8 * sec], o[8 * sec + 1], o[8 * sec + 2], o[8 * sec + 3]);
+    else              // even lane: partner's piece 2*sec; odd lane: own piece 2*sec + 1
+      v = odd ? make_uint4(o[8 * sec + 4], o[8 * sec + 5], o[8 * sec + 6], o[8 * sec + 7])
+              : make_uint4(got[4 * sec], got[4 * sec + 1], got[4 * sec + 2], got[4 * sec + 3]);
+    const int col = col0 + 16 * sec + (odd ? 8 : 0);
+    __nv_bfloat16* row = to_even_row ? row_even : row_odd;
+    if ((to_even_row ? ok_even : ok_odd) && col + 8 <= n_out) *reinterpret_cast<uint4*>(row + col) = v;
+  }
+}
+
+template <int EPI, bool BIAS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -93,29 +129,34 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   if (warp == 0) {
     // ======================= TMA producer (both CTAs) =======================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (long long u = pair; u < n_units; u += n_pairs) {
-        const Unit un = unit_of(u, p);
-        const int m0 = un.mt * 2 * TMH + static_cast<int>(rank) * TMH;
-        int w0, w1;  // first weight row of this CTA's two 64-row boxes
-        if (EPI == LLM_GEMM_SWIGLU) {
-          w0 = un.nt * 128 + static_cast<int>(rank) * 64;  // gate rows
-          w1 = p.up_offset + w0;                            // the matching up rows
-        } else {
-          w0 = un.nt * TNP + static_cast<int>(rank) * 128;
-          w1 = w0 + 64;
-        }
-        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-          const uint32_t lead_full = mapa_shared(smem_u32(&full[s]), 0);
+    // warp-uniform control flow; one elected lane issues (a divergent `if (lane == 0)` makes every TMA operand a
+    // per-lane value and costs a uniform-register broadcast loop per instruction)
+    const uint32_t lead_full0 = mapa_shared(smem_u32(&full[0]), 0);
+    uint32_t it = 0;
+    for (long long u = pair; u < n_units; u += n_pairs) {
+      const Unit un = unit_of(u, p);
+      const int m0 = un.mt * 2 * TMH + static_cast<int>(rank) * TMH;
+      int w0, w1;  // first weight row of this CTA's two 64-row boxes
+      if (EPI == LLM_GEMM_SWIGLU) {
+        w0 = un.nt * 128 + static_cast<int>(rank) * 64;  // gate rows
+        w1 = p.up_offset + w0;                            // the matching up rows
+      } else {
+        w0 = un.nt * TNP + static_cast<int>(rank) * 128;
+        w1 = w0 + 64;
+      }
+      for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+        const uint32_t lead_full = lead_full0 + s * 8;
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        if (elect_one()) {
           if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
-          uint8_t* sa = smem + s * STAGE_BYTES;
-          tma_load_2d_2sm(sa, &tmX, lead_full, kb * KB, m0);
-          tma_load_2d_2sm(sa + A_BYTES, &tmW, lead_full, kb * KB, w0);
-          tma_load_2d_2sm(sa + A_BYTES + BQ_BYTES, &tmW, lead_full, kb * KB, w1);
+          // token rows stream through once per raster group; the group's weight tiles are re-read by every wave
+          tma_load_2d_2sm_hint(sa, &tmX, lead_full, kb * KB, m0, p.hint_x);
+          tma_load_2d_2sm_hint(sa + A_BYTES, &tmW, lead_full, kb * KB, w0, p.hint_w);
+          tma_load_2d_2sm_hint(sa + A_BYTES + BQ_BYTES, &tmW, lead_full, kb * KB, w1, p.hint_w);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -152,9 +193,11 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (long long u = pair; u < n_units; u += n_pairs, ++ui) {
       const Unit un = unit_of(u, p);
       const uint32_t a = ui & 1;
-      const long long m = static_cast<long long>(un.mt) * 2 * TMH + static_cast<long long>(rank) * TMH + quarter * 32 + lane;
-      const bool m_ok = m < p.M;
-      __nv_bfloat16* orow = p.out + (m_ok ? m : 0) * p.ldo;
+      // this lane's row, and the rows of its lane pair (even lane's, odd lane's) for the paired stores
+      const long long m_even = static_cast<long long>(un.mt) * 2 * TMH + static_cast<long long>(rank) * TMH + quarter * 32 + (lane & ~1);
+      const bool ok_even = m_even < p.M, ok_odd = m_even + 1 < p.M;
+      __nv_bfloat16* row_even = p.out + (ok_even ? m_even : 0) * p.ldo;
+      __nv_bfloat16* row_odd = p.out + (ok_odd ? m_even + 1 : 0) * p.ldo;
       mbar_wait(&acc_full[a], (ui >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem + lane_addr + a * TNP;
@@ -174,12 +217,7 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const float u0 = bf_round(__uint_as_float(v[2 * i])), u1 = bf_round(__uint_as_float(v[2 * i + 1]));
             o[i] = pack_bf16x2(bf_round(g0 / (1.f + __expf(-g0))) * u0, bf_round(g1 / (1.f + __expf(-g1))) * u1);
           }
-          if (m_ok) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (col0 + 8 * i + 8 <= p.n_out)
-                *reinterpret_cast<uint4*>(orow + col0 + 8 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-          }
+          store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
         }
       } else {
 #pragma unroll 1
@@ -189,35 +227,37 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           tmem_ld_wait();
           const int col0 = un.nt * TNP + c * 32;
           uint32_t o[16];
-          if (p.bias != nullptr && col0 + 32 <= p.n_out) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+          if (BIAS) {
+            if (col0 + 32 <= p.n_out) {
+              const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 bv = __ldg(bp + i);
-              const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+              for (int i = 0; i < 4; ++i) {
+                const uint4 bv = __ldg(bp + i);
+                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
-                o[4 * i + j] = pack_bf16x2(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
+                for (int j = 0; j < 4; ++j) {
+                  const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+                  o[4 * i + j] = pack_bf16x2(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
+                }
+              }
+            } else {  // ragged last tile: 8-column groups (N % 8 == 0), zero bias past the edge
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 bv = make_uint4(0u, 0u, 0u, 0u);
+                if (col0 + 8 * i + 8 <= p.n_out) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + 8 * i));
+                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+                  o[4 * i + j] = pack_bf16x2(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
+                }
               }
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float b0 = 0.f, b1 = 0.f;
-              if (p.bias != nullptr && col0 + 2 * i + 1 < p.n_out) {
-                b0 = __bfloat162float(p.bias[col0 + 2 * i]);
-                b1 = __bfloat162float(p.bias[col0 + 2 * i + 1]);
-              }
-              o[i] = pack_bf16x2(__uint_as_float(r[2 * i]) + b0, __uint_as_float(r[2 * i + 1]) + b1);
-            }
+            for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
           }
-          if (m_ok) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (col0 + 8 * i + 8 <= p.n_out)
-                *reinterpret_cast<uint4*>(orow + col0 + 8 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-          }
+          store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
         }
       }
       tc_fence_before();
@@ -264,8 +304,9 @@ extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const vo
   static bool configured = false;
   static int n_sm = 148;
   if (!configured) {
-    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_SWIGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int dev = 0;
     SDAG_CUDA_TRY(cudaGetDevice(&dev));
     SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -281,12 +322,29 @@ extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const vo
   p.n_nt = swiglu ? (n_out + 127) / 128 : (N + TNP - 1) / TNP;
   p.kblocks = (K + KB - 1) / KB;
   p.up_offset = n_out;
+  // raster group: as many weight tiles as stay L2-resident (~60 MB, loaded EVICT_LAST) while the token tiles stream past
+  // them; EVICT_FIRST on the token rows was measured to hurt (bit 0 of the knob) and stays off
+  static int group_env = -1, hint_env = -1;
+  if (group_env < 0) {
+    const char* e = getenv("SDAG_GEMM_GROUP_N");  // tuning knobs
+    group_env = e ? atoi(e) : 0;
+    const char* h = getenv("SDAG_GEMM_HINTS");
+    hint_env = h ? atoi(h) : 2;
+  }
+  int gn = static_cast<int>((60ll << 20) / (static_cast<long long>(swiglu ? 256 : TNP) * K * 2));
+  gn = gn < 2 ? 2 : (gn > GROUP_N ? GROUP_N : gn);
+  p.group_n = group_env > 0 ? group_env : gn;
+  p.hint_x = (hint_env & 1) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+  p.hint_w = (hint_env & 2) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
   const long long units = static_cast<long long>(p.n_mt) * p.n_nt;
   const long long pairs = units < n_sm / 2 ? units : n_sm / 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>(2 * pairs);
   if (swiglu)
-    llm_gemm_kernel<LLM_GEMM_SWIGLU><<<static_cast<unsigned>(2 * pairs), 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+    llm_gemm_kernel<LLM_GEMM_SWIGLU, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (bias)
+    llm_gemm_kernel<LLM_GEMM_PLAIN, true><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   else
-    llm_gemm_kernel<LLM_GEMM_PLAIN><<<static_cast<unsigned>(2 * pairs), 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+    llm_gemm_kernel<LLM_GEMM_PLAIN, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   return static_cast<int>(cudaGetLastError());
 }

@@ -12,12 +12,24 @@ so decoding continues through the normal HF path (with the ``sdag_b200`` decode 
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
 import torch.nn.functional as F
 
 from . import _lib
+
+
+def _linear(x, w, bias):
+    """F.linear, or llm_gemm for large token counts when PAIR_GEMM_ALL is set (experiment)."""
+    if PAIR_GEMM_ALL and x.shape[0] >= PAIR_GEMM_MIN_ROWS and w.shape[0] % 8 == 0 and x.stride(1) == 1 and x.stride(0) % 8 == 0:
+        lib = _lib.load()
+        out = torch.empty((x.shape[0], w.shape[0]), dtype=torch.bfloat16, device=x.device)
+        _lib.check(lib.llm_gemm(x.data_ptr(), x.stride(0), w.data_ptr(), _lib.ptr(bias), out.data_ptr(), w.shape[0], x.shape[0],
+                                w.shape[0], w.shape[1], 0, _lib.stream_ptr(x.device)), "llm_gemm")
+        return out
+    return F.linear(x, w, bias)
 
 
 def _rmsnorm(x, residual, weight, eps):
@@ -125,7 +137,7 @@ class FusedPrefill:
         last_rows = torch.arange(B, device=dev) * L + ((lengths - 1) if lengths is not None else (L - 1))
         n_layers = len(self.layers)
         for i, ly in enumerate(self.layers):
-            qkv = F.linear(normed, ly["wqkv"], ly["bqkv"])
+            qkv = _linear(normed, ly["wqkv"], ly["bqkv"])
             q = torch.empty((B, L, H, D), dtype=torch.bfloat16, device=dev)
             if kv is not None:
                 kbuf, vbuf = kc_all[i], vc_all[i]
@@ -155,7 +167,7 @@ class FusedPrefill:
         lib = _lib.load()
         ly = self.layers[i]
         inner = self.model.model
-        o = F.linear(attn_rows, ly["wo"], ly["bo"])
+        o = _linear(attn_rows, ly["wo"], ly["bo"])
         resid, normed = _rmsnorm(o, resid, ly["w_post"], ly["eps_post"])
         rows = normed.shape[0]
         act = torch.empty((rows, self.inter), dtype=torch.bfloat16, device=normed.device)
@@ -167,7 +179,7 @@ class FusedPrefill:
         else:
             gu = F.linear(normed, ly["wgu"])
             _lib.check(lib.llm_swiglu(gu.data_ptr(), act.data_ptr(), rows, self.inter, _lib.stream_ptr(gu.device)), "llm_swiglu")
-        d = F.linear(act, ly["wdown"])
+        d = _linear(act, ly["wdown"], None)
         if i + 1 < len(self.layers):
             nxt = self.layers[i + 1]
             resid, normed = _rmsnorm(d, resid, nxt["w_in"], nxt["eps_in"])
@@ -352,6 +364,7 @@ class FusedPrefill:
         return c["gen"][:, : done + 1].clone()
 
 
+PAIR_GEMM_ALL = os.environ.get("SDAG_PAIR_GEMM", "") == "all"
 PAIR_GEMM_MIN_ROWS = 512  # prefill gate/up projections with at least this many token rows run on llm_gemm (fused SwiGLU)
 USE_FUSED_GEMV = True  # decode-step linear layers on llm_gemv (B <= 4); False: cuBLAS + stand-alone glue kernels
 

@@ -26,9 +26,20 @@ def timed(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
+def sustained(fn, flops, seconds=1.5):
+    """TFLOP/s over the second half of a `seconds`-long back-to-back run (power-capped clocks, not burst clocks)."""
+    t1 = timed(fn, 3)
+    n = max(4, int(seconds * 1e3 / t1 / 2))
+    for _ in range(n):
+        fn()
+    t2 = timed(fn, n)
+    return flops / t2 / 1e9
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tokens", type=int, default=21248)
+    ap.add_argument("--sustain", action="store_true", help="also report TFLOP/s of 1.5 s back-to-back runs")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
@@ -61,6 +72,8 @@ def main():
         fl = 2.0 * M * N * K
         print(f"{name:16s} M={M} N={N} K={K}: llm_gemm {t_o:.3f} ms ({fl / t_o / 1e9:.0f} TFLOP/s)  cuBLAS{'+swiglu' if epi else ''} "
               f"{t_c:.3f} ms ({fl / t_c / 1e9:.0f} TFLOP/s)  max|diff| {err:.4f}", flush=True)
+        if args.sustain:
+            print(f"{'':16s} sustained: llm_gemm {sustained(ours, fl):.0f}  cuBLAS {sustained(cublas, fl):.0f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":
