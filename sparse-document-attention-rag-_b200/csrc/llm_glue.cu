@@ -7,6 +7,7 @@
 //   RoPE      q' = bf16(bf16(q*cos) + bf16(rot(q)*sin))           (apply_rotary_pos_emb / rotate_half)
 //   SwiGLU    h = bf16(bf16(silu(g)) * u)                         (LlamaMLP.forward)
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -255,6 +256,12 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict
       for (int r = 0; r < R; ++r) wa[u][r] = ld_stream(wrow_of(n_first, r) + lane + u * 32);
   }
 
+  // Launched as a programmatic dependent: everything above only touched the weights, which no kernel of the step
+  // writes; the activations are read (and `out` written) only once the preceding kernel has completed.  The trigger
+  // lets the next layer's kernel take over SM slots as this grid's CTAs retire, its first weight loads already in flight.
+  pdl_wait();
+  pdl_trigger();
+
   // ---- prologue: stage the (transformed) input ----
   if (prologue == PRO_SWIGLU) {
     // x = gate|up rows [B][2K]: xin = bf16(bf16(silu(g)) * u)   (LlamaMLP.forward)
@@ -404,11 +411,25 @@ int launch_gemv_r(const void* x, const void* W, const void* bias, const void* no
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
   long long ctas = (static_cast<long long>(N) / R + (GEMV_THREADS / 32) - 1) / (GEMV_THREADS / 32);
   if (ctas > static_cast<long long>(n_sm) * per_sm) ctas = static_cast<long long>(n_sm) * per_sm;
-  gemv_kernel<B, R><<<static_cast<unsigned>(ctas), GEMV_THREADS, smem, st>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(W), static_cast<const __nv_bfloat16*>(bias),
-      static_cast<const __nv_bfloat16*>(norm_w), static_cast<const __nv_bfloat16*>(resid), static_cast<__nv_bfloat16*>(out), K, N,
-      prologue, eps, pair);
-  return static_cast<int>(cudaGetLastError());
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("SDAG_NO_PDL");
+    use_pdl = (e && atoi(e)) ? 0 : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(GEMV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  return static_cast<int>(cudaLaunchKernelEx(
+      &cfg, gemv_kernel<B, R>, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(W),
+      static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(norm_w), static_cast<const __nv_bfloat16*>(resid),
+      static_cast<__nv_bfloat16*>(out), K, N, prologue, eps, pair));
 }
 
 template <int B>

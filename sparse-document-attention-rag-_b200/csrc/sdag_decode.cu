@@ -242,6 +242,7 @@ template <int D>
 __global__ void __launch_bounds__(D)
 decode_merge_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out, int H, int Hkv, int nsplit) {
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  pdl_trigger();  // the o_proj GEMV that follows may start streaming its weights; it waits for this grid before reading `out`
   const int G = H / Hkv, hkv = h / G, g = h % G;
   const float* base = partial + (static_cast<long long>(b) * Hkv + hkv) * nsplit * G * (D + 2) + g * (D + 2);
   const long long stride = static_cast<long long>(G) * (D + 2);
