@@ -87,6 +87,8 @@ rope_qkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
                 const __nv_bfloat16* __restrict__ sinb, __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_out,
                 __nv_bfloat16* __restrict__ v_out, int B, int L, int H, int Hkv, int D, long long kv_stride_b,
                 long long kv_stride_h, int pos0_host, const int32_t* __restrict__ pos0_dev, int pos0_dev_stride) {
+  pdl_wait();     // (decode step) launched as a programmatic dependent of the q/k/v GEMV
+  pdl_trigger();  // the attention kernel that follows waits for this grid before it reads the cache
   const int heads = H + 2 * Hkv;
   const int vec_per_head = D / 16;  // threads per head (each handles 8 + 8 elements)
   const long long total = static_cast<long long>(B) * L * heads * vec_per_head;
@@ -182,11 +184,11 @@ int llm_rope_qkv(const void* qkv, const void* cos, const void* sin, void* q_out,
   const long long total = static_cast<long long>(B) * L * (H + 2 * Hkv) * (D / 16);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  rope_qkv_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  return static_cast<int>(launch_pdl(
+      rope_qkv_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream),
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(cos), static_cast<const __nv_bfloat16*>(sin),
       static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(k_out), static_cast<__nv_bfloat16*>(v_out), B, L, H, Hkv,
-      D, kv_stride_b, kv_stride_h, pos0, pos0_dev, pos0_dev_stride);
-  return static_cast<int>(cudaGetLastError());
+      D, static_cast<long long>(kv_stride_b), static_cast<long long>(kv_stride_h), pos0, pos0_dev, pos0_dev_stride));
 }
 
 int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* stream) {
@@ -411,25 +413,10 @@ int launch_gemv_r(const void* x, const void* W, const void* bias, const void* no
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
   long long ctas = (static_cast<long long>(N) / R + (GEMV_THREADS / 32) - 1) / (GEMV_THREADS / 32);
   if (ctas > static_cast<long long>(n_sm) * per_sm) ctas = static_cast<long long>(n_sm) * per_sm;
-  static int use_pdl = -1;
-  if (use_pdl < 0) {
-    const char* e = getenv("SDAG_NO_PDL");
-    use_pdl = (e && atoi(e)) ? 0 : 1;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
-  cfg.blockDim = dim3(GEMV_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  return static_cast<int>(cudaLaunchKernelEx(
-      &cfg, gemv_kernel<B, R>, static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(W),
-      static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(norm_w), static_cast<const __nv_bfloat16*>(resid),
-      static_cast<__nv_bfloat16*>(out), K, N, prologue, eps, pair));
+  return static_cast<int>(launch_pdl(
+      gemv_kernel<B, R>, dim3(static_cast<unsigned>(ctas)), dim3(GEMV_THREADS), smem, st, static_cast<const __nv_bfloat16*>(x),
+      static_cast<const __nv_bfloat16*>(W), static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(norm_w),
+      static_cast<const __nv_bfloat16*>(resid), static_cast<__nv_bfloat16*>(out), K, N, prologue, eps, pair));
 }
 
 template <int B>

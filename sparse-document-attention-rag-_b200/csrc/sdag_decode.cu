@@ -66,6 +66,8 @@ decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   __shared__ uint64_t full[S::kStages], empty[S::kStages];
 
   const int split = blockIdx.x, nsplit = gridDim.x, hkv = blockIdx.y, b = blockIdx.z;
+  pdl_wait();     // launched as a programmatic dependent: q, the cache rows and the length come from preceding kernels
+  pdl_trigger();  // the merge kernel may be scheduled; it waits for this grid before reading the partial results
   // device-side length: one value for the batch (stride 0) or one per prompt of a ragged batch (stride 1)
   const int kv_len = kv_len_dev ? max(0, min(kv_len_dev[b * kv_len_dev_stride], kv_len_host)) : kv_len_host;
   const int G = H / Hkv;
@@ -242,6 +244,7 @@ template <int D>
 __global__ void __launch_bounds__(D)
 decode_merge_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out, int H, int Hkv, int nsplit) {
   const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+  pdl_wait();     // the split kernel's partial results
   pdl_trigger();  // the o_proj GEMV that follows may start streaming its weights; it waits for this grid before reading `out`
   const int G = H / Hkv, hkv = h / G, g = h % G;
   const float* base = partial + (static_cast<long long>(b) * Hkv + hkv) * nsplit * G * (D + 2) + g * (D + 2);
@@ -295,11 +298,11 @@ int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloa
                                        DecodeSmem<D>::kTotal));
     cfg = true;
   }
-  decode_split_kernel<D><<<dim3(nsplit, Hkv, B), THREADS, DecodeSmem<D>::kTotal, st>>>(tk, tv, q, sq_b, sq_h, part, H, Hkv,
-                                                                                      kv_len, sl2, kv_len_dev, kv_len_dev_stride);
-  SDAG_CUDA_TRY(cudaGetLastError());
-  decode_merge_kernel<D><<<dim3(H, B), D, 0, st>>>(part, out, H, Hkv, nsplit);
-  return static_cast<int>(cudaGetLastError());
+  // both kernels are programmatic dependents of their predecessor: launch latency hides behind the previous kernel's tail
+  SDAG_CUDA_TRY(launch_pdl(decode_split_kernel<D>, dim3(nsplit, Hkv, B), dim3(THREADS), DecodeSmem<D>::kTotal, st, tk, tv, q,
+                           sq_b, sq_h, part, H, Hkv, kv_len, sl2, kv_len_dev, kv_len_dev_stride));
+  return static_cast<int>(launch_pdl(decode_merge_kernel<D>, dim3(H, B), dim3(D), 0, st, static_cast<const float*>(part), out, H,
+                                     Hkv, nsplit));
 }
 
 }  // namespace
