@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __nv_bfloat16* __restrict__ q, long long sq_b, long long sq_h, float* __restrict__ partial,
                     int H, int Hkv, int kv_len_host, float scale_log2, const int32_t* __restrict__ kv_len_dev,
-                    int kv_len_dev_stride) {
+                    int kv_len_dev_stride, __nv_bfloat16* __restrict__ merged_out, unsigned int* __restrict__ tickets) {
   using S = DecodeSmem<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -238,7 +238,43 @@ decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       out[gg * (D + 2) + 1] = den;
     }
   }
+  if (tickets == nullptr) return;  // merged by decode_merge_kernel
+
+  // ---- the split CTA that finishes last merges the records of its (b, hkv): no separate merge launch ----
+  __shared__ int is_last_s;
+  __threadfence();
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS * 32) : "memory");
+  if (tid == 0) {
+    unsigned int* t = tickets + b * Hkv + hkv;
+    const unsigned int ticket = atomicAdd(t, 1u);
+    is_last_s = ticket == static_cast<unsigned int>(nsplit - 1);
+    if (is_last_s) *t = 0u;  // left clean for the next call
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS * 32) : "memory");
+  if (!is_last_s) return;
+  __threadfence();
+  const float* rec = partial + (static_cast<long long>(b) * Hkv + hkv) * nsplit * G * (D + 2);
+  const int stride = G * (D + 2);
+  for (int i = tid; i < G * D; i += CONSUMERS * 32) {
+    const int gg = i / D, d = i % D;
+    const float* base = rec + gg * (D + 2);  // other CTAs wrote these: read through L2
+    float M = -INFINITY;
+#pragma unroll 4
+    for (int sp = 0; sp < nsplit; ++sp) M = fmaxf(M, __ldcg(base + sp * stride));
+    float num = 0.f, den = 0.f;
+#pragma unroll 4
+    for (int sp = 0; sp < nsplit; ++sp) {
+      const float mw = __ldcg(base + sp * stride);
+      const float w = mw == -INFINITY ? 0.f : exp2f(mw - M);
+      num = fmaf(w, __ldcg(base + sp * stride + 2 + d), num);
+      den = fmaf(w, __ldcg(base + sp * stride + 1), den);
+    }
+    merged_out[(static_cast<long long>(b) * H + hkv * G + gg) * D + d] = __float2bfloat16(num / den);
+  }
 }
+
+constexpr int MAX_TICKETS = 4096;
+__device__ unsigned int g_decode_tickets[MAX_TICKETS];  // zero at load; every call leaves them zero
 
 template <int D>
 __global__ void __launch_bounds__(D)
@@ -299,8 +335,11 @@ int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloa
     cfg = true;
   }
   // both kernels are programmatic dependents of their predecessor: launch latency hides behind the previous kernel's tail
+  unsigned int* tickets = nullptr;
+  if (B * Hkv <= MAX_TICKETS) SDAG_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_decode_tickets));
   SDAG_CUDA_TRY(launch_pdl(decode_split_kernel<D>, dim3(nsplit, Hkv, B), dim3(THREADS), DecodeSmem<D>::kTotal, st, tk, tv, q,
-                           sq_b, sq_h, part, H, Hkv, kv_len, sl2, kv_len_dev, kv_len_dev_stride));
+                           sq_b, sq_h, part, H, Hkv, kv_len, sl2, kv_len_dev, kv_len_dev_stride, out, tickets));
+  if (tickets != nullptr) return SDAG_OK;  // the last split CTA of every (b, hkv) merged in place
   return static_cast<int>(launch_pdl(decode_merge_kernel<D>, dim3(H, B), dim3(D), 0, st, static_cast<const float*>(part), out, H,
                                      Hkv, nsplit));
 }
