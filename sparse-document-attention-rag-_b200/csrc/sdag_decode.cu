@@ -276,6 +276,8 @@ decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 constexpr int MAX_TICKETS = 4096;
 __device__ unsigned int g_decode_tickets[MAX_TICKETS];  // zero at load; every call leaves them zero
 
+constexpr int MAX_SPLITS = 256;  // >= SM count: split_count never exceeds it
+
 template <int D>
 __global__ void __launch_bounds__(D)
 decode_merge_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out, int H, int Hkv, int nsplit) {
@@ -285,15 +287,28 @@ decode_merge_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict
   const int G = H / Hkv, hkv = h / G, g = h % G;
   const float* base = partial + (static_cast<long long>(b) * Hkv + hkv) * nsplit * G * (D + 2) + g * (D + 2);
   const long long stride = static_cast<long long>(G) * (D + 2);
-  float M = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, base[s * stride]);
-  float num = 0.f, den = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
-    const float m = base[s * stride];
-    const float w = m == -INFINITY ? 0.f : exp2f(m - M);
-    num = fmaf(w, base[s * stride + 2 + d], num);
-    den = fmaf(w, base[s * stride + 1], den);
+  // the split weights once per head (threads = splits), then D independent column sums with the loads batched
+  __shared__ float w_s[MAX_SPLITS];
+  __shared__ float den_s;
+  if (d < 32) {
+    float M = -INFINITY;
+    for (int s = d; s < nsplit; s += 32) M = fmaxf(M, base[s * stride]);
+    for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+    float den = 0.f;
+    for (int s = d; s < nsplit; s += 32) {
+      const float m = base[s * stride];
+      const float w = m == -INFINITY ? 0.f : exp2f(m - M);
+      w_s[s] = w;
+      den = fmaf(w, base[s * stride + 1], den);
+    }
+    for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+    if (d == 0) den_s = den;
   }
+  __syncthreads();
+  float num = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < nsplit; ++s) num = fmaf(w_s[s], base[s * stride + 2 + d], num);
+  const float den = den_s;
   out[(static_cast<long long>(b) * H + h) * D + d] = __float2bfloat16(num / den);
 }
 
@@ -312,6 +327,7 @@ inline int split_count(int B, int Hkv, int kv_len) {
   int n = sm_count() / (B * Hkv);
   const int tiles = (kv_len + TILE_ROWS - 1) / TILE_ROWS;
   if (n > tiles) n = tiles;
+  if (n > MAX_SPLITS) n = MAX_SPLITS;
   return n < 1 ? 1 : n;
 }
 
@@ -336,7 +352,13 @@ int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloa
   }
   // both kernels are programmatic dependents of their predecessor: launch latency hides behind the previous kernel's tail
   unsigned int* tickets = nullptr;
-  if (B * Hkv <= MAX_TICKETS) SDAG_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_decode_tickets));
+  static int fused_merge = -1;
+  if (fused_merge < 0) {
+    const char* e = getenv("SDAG_DECODE_SPLIT_MERGE");  // 1: the last split CTA merges instead of decode_merge_kernel
+    fused_merge = (e && atoi(e)) ? 1 : 0;  // measured: the serial tail in 8 CTAs costs 3 us per layer more than the dependent launch
+  }
+  if (fused_merge && B * Hkv <= MAX_TICKETS)
+    SDAG_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_decode_tickets));
   SDAG_CUDA_TRY(launch_pdl(decode_split_kernel<D>, dim3(nsplit, Hkv, B), dim3(THREADS), DecodeSmem<D>::kTotal, st, tk, tv, q,
                            sq_b, sq_h, part, H, Hkv, kv_len, sl2, kv_len_dev, kv_len_dev_stride, out, tickets));
   if (tickets != nullptr) return SDAG_OK;  // the last split CTA of every (b, hkv) merged in place
