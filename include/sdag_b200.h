@@ -199,6 +199,14 @@ int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, v
 int llm_gemv(const void* x, const void* weight, const void* bias, const void* norm_weight, const void* residual,
              void* out, int B, int K, int N, int prologue, float eps, int pair_swiglu, void* stream);
 
+/* The q/k/v projection of a decode step with apply_rotary_pos_emb and the KV-cache write in its epilogue (llm_gemv with
+ * the RMSNorm prologue when norm_weight != NULL, followed by llm_rope_qkv for L = 1, in one launch): weight is the fused
+ * [(H + 2*Hkv)*D, K] q|k|v matrix; q_out [B, 1, H, D]; k_out / v_out, cos / sin and the positions as in llm_rope_qkv. */
+int llm_gemv_rope(const void* x, const void* weight, const void* bias, const void* norm_weight, float eps,
+                  const void* cos, const void* sin, void* q_out, void* k_out, void* v_out, int B, int K, int H,
+                  int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0, const int32_t* pos0_dev,
+                  int pos0_dev_stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Paths B1 / B6 — the sentence encoder behind `ranker.encode(...)` (embed_queries, dense.py:44-65;
  * encode_texts_with_ranker, malicious_selection.py:12-34; compute_doc_knn_for_docs, SDAG.py:46-48):

@@ -50,6 +50,8 @@ SIGNATURES = {
     "llm_rope_qkv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _i32, _vp]),
     "llm_swiglu": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "llm_gemv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "llm_gemv_rope": (_i32, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp,
+                              _i32, _vp]),
     "llm_gemm": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "sdag_full_blockmap_bytes": (_sz, [_i32]),
     "sdag_build_blockmap_full": (_i32, [_vp, _i32, _i32, _vp, _sz, _vp]),

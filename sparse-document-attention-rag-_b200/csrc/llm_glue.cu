@@ -227,11 +227,25 @@ enum GemvPrologue { PRO_NONE = 0, PRO_RMSNORM = 1, PRO_SWIGLU = 2 };
 // R output rows per warp pass (the staged input chunk is reused from registers for all of them): 4 for wide layers,
 // 2 for narrow ones so that every SM still gets warps to run.  `pair_swiglu`: weight rows come in (gate j, up j + N/2)
 // pairs and the epilogue writes out[b][j] = silu(gate) * up — the MLP activation never exists as a separate pass.
-template <int B, int R>
+// q/k/v projection of a decode step with the rotary embedding and the cache write in the epilogue (ROPE = true): the
+// warp's rows come in (d, d + D/2) pairs of one head, so that both partners of a rotation end up in one lane.
+struct RopeArgs {
+  const __nv_bfloat16* cos;  // [positions, D]
+  const __nv_bfloat16* sin;
+  __nv_bfloat16* q_out;      // [B, 1, H, D]
+  __nv_bfloat16* k_out;      // cache [B, Hkv, S_cap, D] (element strides below)
+  __nv_bfloat16* v_out;
+  long long kv_stride_b, kv_stride_h;
+  const int32_t* pos_dev;    // position of the new token: pos_dev[b * pos_dev_stride], or pos_host when null
+  int pos_dev_stride, pos_host;
+  int H, Hkv, D;
+};
+
+template <int B, int R, bool ROPE>
 __global__ void __launch_bounds__(GEMV_THREADS)
 gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ bias,
             const __nv_bfloat16* __restrict__ norm_w, const __nv_bfloat16* __restrict__ resid, __nv_bfloat16* __restrict__ out,
-            int K, int N, int prologue, float eps, int pair_swiglu) {
+            int K, int N, int prologue, float eps, int pair_swiglu, const RopeArgs rope) {
   extern __shared__ __align__(16) uint8_t dyn[];
   __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(dyn);  // [B][K] transformed input
   __shared__ float red[B][GEMV_THREADS / 32];
@@ -242,7 +256,13 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict
   const int half = N / 2;
   // weight row of the warp's r-th row at pass base n0: plain, or interleaved (gate, up) pairs
   auto wrow_of = [&](int n0, int r) -> const uint4* {
-    const int row = pair_swiglu ? ((r & 1) ? half : 0) + (n0 >> 1) + (r >> 1) : n0 + r;
+    int row;
+    if (ROPE) {  // pair index -> (head, i): rows head*D + i and head*D + i + D/2
+      const int pidx = (n0 >> 1) + (r >> 1), hd = rope.D >> 1;
+      row = (pidx / hd) * rope.D + pidx % hd + ((r & 1) ? hd : 0);
+    } else {
+      row = pair_swiglu ? ((r & 1) ? half : 0) + (n0 >> 1) + (r >> 1) : n0 + r;
+    }
     return reinterpret_cast<const uint4*>(W + static_cast<long long>(row) * K);
   };
 
@@ -371,7 +391,41 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         acc[r][b] = sum;
       }
-    if (!pair_swiglu) {
+    if (ROPE) {
+      if (lane < (R / 2) * B) {
+        const int p = lane / B, b = lane % B;
+        float x1 = 0.f, x2 = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < R / 2; ++pp)
+#pragma unroll
+          for (int bb = 0; bb < B; ++bb)
+            if (pp == p && bb == b) x1 = acc[2 * pp][bb], x2 = acc[2 * pp + 1][bb];
+        const int D = rope.D, hd = D >> 1;
+        const int pidx = (n0 >> 1) + p, head = pidx / hd, i = pidx % hd;
+        if (bias) {
+          x1 += __bfloat162float(bias[head * D + i]);
+          x2 += __bfloat162float(bias[head * D + i + hd]);
+        }
+        x1 = bf(x1), x2 = bf(x2);  // nn.Linear output in bf16
+        const int pos = rope.pos_dev ? rope.pos_dev[b * rope.pos_dev_stride] : rope.pos_host;
+        __nv_bfloat16* dst;
+        if (head < rope.H)
+          dst = rope.q_out + (static_cast<long long>(b) * rope.H + head) * D;
+        else if (head < rope.H + rope.Hkv)
+          dst = rope.k_out + b * rope.kv_stride_b + (head - rope.H) * rope.kv_stride_h + static_cast<long long>(pos) * D;
+        else
+          dst = rope.v_out + b * rope.kv_stride_b + (head - rope.H - rope.Hkv) * rope.kv_stride_h + static_cast<long long>(pos) * D;
+        float o1 = x1, o2 = x2;
+        if (head < rope.H + rope.Hkv) {  // apply_rotary_pos_emb in bf16: q*cos + rotate_half(q)*sin, rotate_half = cat(-x2, x1)
+          const __nv_bfloat16* cp = rope.cos + static_cast<long long>(pos) * D;
+          const __nv_bfloat16* sp = rope.sin + static_cast<long long>(pos) * D;
+          o1 = bf(x1 * __bfloat162float(cp[i])) + bf(-x2 * __bfloat162float(sp[i]));
+          o2 = bf(x2 * __bfloat162float(cp[i + hd])) + bf(x1 * __bfloat162float(sp[i + hd]));
+        }
+        dst[i] = __float2bfloat16(o1);
+        dst[i + hd] = __float2bfloat16(o2);
+      }
+    } else if (!pair_swiglu) {
       if (lane < R * B) {
         const int r = lane / B, b = lane % B;
         float sum = 0.f;
@@ -401,35 +455,37 @@ gemv_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict
   }
 }
 
-template <int B, int R>
+template <int B, int R, bool ROPE>
 int launch_gemv_r(const void* x, const void* W, const void* bias, const void* norm_w, const void* resid, void* out, int K, int N,
-                  int prologue, float eps, int pair, int n_sm, cudaStream_t st) {
+                  int prologue, float eps, int pair, int n_sm, cudaStream_t st, const RopeArgs& rope) {
   const size_t smem = static_cast<size_t>(B) * K * 2;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
-    SDAG_CUDA_TRY(cudaFuncSetAttribute(gemv_kernel<B, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(gemv_kernel<B, R, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     configured = smem;
   }
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
   long long ctas = (static_cast<long long>(N) / R + (GEMV_THREADS / 32) - 1) / (GEMV_THREADS / 32);
   if (ctas > static_cast<long long>(n_sm) * per_sm) ctas = static_cast<long long>(n_sm) * per_sm;
   return static_cast<int>(launch_pdl(
-      gemv_kernel<B, R>, dim3(static_cast<unsigned>(ctas)), dim3(GEMV_THREADS), smem, st, static_cast<const __nv_bfloat16*>(x),
+      gemv_kernel<B, R, ROPE>, dim3(static_cast<unsigned>(ctas)), dim3(GEMV_THREADS), smem, st, static_cast<const __nv_bfloat16*>(x),
       static_cast<const __nv_bfloat16*>(W), static_cast<const __nv_bfloat16*>(bias), static_cast<const __nv_bfloat16*>(norm_w),
-      static_cast<const __nv_bfloat16*>(resid), static_cast<__nv_bfloat16*>(out), K, N, prologue, eps, pair));
+      static_cast<const __nv_bfloat16*>(resid), static_cast<__nv_bfloat16*>(out), K, N, prologue, eps, pair, rope));
 }
 
 template <int B>
 int launch_gemv(const void* x, const void* W, const void* bias, const void* norm_w, const void* resid, void* out, int K, int N,
-                int prologue, float eps, int pair, cudaStream_t st) {
+                int prologue, float eps, int pair, cudaStream_t st, const RopeArgs* rope = nullptr) {
   static int n_sm = 0;
   if (n_sm == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
   }
   // narrow layers: two rows per warp pass, so that N / 2 warp passes still cover every SM a few times
-  if (N / 4 < n_sm * 16) return launch_gemv_r<B, 2>(x, W, bias, norm_w, resid, out, K, N, prologue, eps, pair, n_sm, st);
-  return launch_gemv_r<B, 4>(x, W, bias, norm_w, resid, out, K, N, prologue, eps, pair, n_sm, st);
+  const RopeArgs none = {};
+  if (rope) return launch_gemv_r<B, 2, true>(x, W, bias, norm_w, resid, out, K, N, prologue, eps, 0, n_sm, st, *rope);
+  if (N / 4 < n_sm * 16) return launch_gemv_r<B, 2, false>(x, W, bias, norm_w, resid, out, K, N, prologue, eps, pair, n_sm, st, none);
+  return launch_gemv_r<B, 4, false>(x, W, bias, norm_w, resid, out, K, N, prologue, eps, pair, n_sm, st, none);
 }
 
 }  // namespace
@@ -663,5 +719,38 @@ extern "C" int llm_gemv(const void* x, const void* weight, const void* bias, con
     case 2: return launch_gemv<2>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);
     case 3: return launch_gemv<3>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);
     default: return launch_gemv<4>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);
+  }
+}
+
+extern "C" int llm_gemv_rope(const void* x, const void* weight, const void* bias, const void* norm_weight, float eps,
+                             const void* cos, const void* sin, void* q_out, void* k_out, void* v_out, int B, int K, int H,
+                             int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0, const int32_t* pos0_dev,
+                             int pos0_dev_stride, void* stream) {
+  if (!x || !weight || !cos || !sin || !q_out || !k_out || !v_out) return SDAG_ERR_INVALID;
+  if (B <= 0 || K <= 0 || (K % 8) || H <= 0 || Hkv <= 0 || D <= 0 || (D % 2)) return SDAG_ERR_INVALID;
+  if (pos0_dev_stride != 0 && pos0_dev_stride != 1) return SDAG_ERR_INVALID;
+  if (B > 4 || static_cast<size_t>(B) * K * 2 > 200 * 1024) return SDAG_ERR_UNSUPPORTED;
+  RopeArgs r;
+  r.cos = static_cast<const __nv_bfloat16*>(cos);
+  r.sin = static_cast<const __nv_bfloat16*>(sin);
+  r.q_out = static_cast<__nv_bfloat16*>(q_out);
+  r.k_out = static_cast<__nv_bfloat16*>(k_out);
+  r.v_out = static_cast<__nv_bfloat16*>(v_out);
+  r.kv_stride_b = kv_stride_b;
+  r.kv_stride_h = kv_stride_h;
+  r.pos_dev = pos0_dev;
+  r.pos_dev_stride = pos0_dev_stride;
+  r.pos_host = pos0;
+  r.H = H;
+  r.Hkv = Hkv;
+  r.D = D;
+  const int N = (H + 2 * Hkv) * D;
+  const int prologue = norm_weight ? PRO_RMSNORM : PRO_NONE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (B) {
+    case 1: return launch_gemv<1>(x, weight, bias, norm_weight, nullptr, nullptr, K, N, prologue, eps, 0, st, &r);
+    case 2: return launch_gemv<2>(x, weight, bias, norm_weight, nullptr, nullptr, K, N, prologue, eps, 0, st, &r);
+    case 3: return launch_gemv<3>(x, weight, bias, norm_weight, nullptr, nullptr, K, N, prologue, eps, 0, st, &r);
+    default: return launch_gemv<4>(x, weight, bias, norm_weight, nullptr, nullptr, K, N, prologue, eps, 0, st, &r);
   }
 }

@@ -273,11 +273,18 @@ class FusedPrefill:
             def step_fused():
                 resid = inner.embed_tokens(c["tok"]).view(B, hid)
                 for i, ly in enumerate(self.layers):
-                    gemv(resid, ly["wqkv"], ly["bqkv"], ly["w_in"], None, qkv_b, hid, qkv_b.shape[1], 1, ly["eps_in"])
-                    _lib.count_launches(1)
-                    _lib.check(lib.llm_rope_qkv(qkv_b.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kc[i].data_ptr(),
-                                                vc[i].data_ptr(), B, 1, H, Hkv, D, kc[i].stride(0), kc[i].stride(1), 0,
-                                                c["pos"].data_ptr(), 1, _lib.stream_ptr(dev)), "llm_rope_qkv")
+                    if FUSED_ROPE_GEMV:  # q/k/v projection with RMSNorm prologue, RoPE + cache write epilogue: one launch
+                        _lib.count_launches(1)
+                        _lib.check(lib.llm_gemv_rope(resid.data_ptr(), ly["wqkv"].data_ptr(), _lib.ptr(ly["bqkv"]), ly["w_in"].data_ptr(),
+                                                     float(ly["eps_in"]), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kc[i].data_ptr(),
+                                                     vc[i].data_ptr(), B, hid, H, Hkv, D, kc[i].stride(0), kc[i].stride(1), 0,
+                                                     c["pos"].data_ptr(), 1, _lib.stream_ptr(dev)), "llm_gemv_rope")
+                    else:
+                        gemv(resid, ly["wqkv"], ly["bqkv"], ly["w_in"], None, qkv_b, hid, qkv_b.shape[1], 1, ly["eps_in"])
+                        _lib.count_launches(1)
+                        _lib.check(lib.llm_rope_qkv(qkv_b.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kc[i].data_ptr(),
+                                                    vc[i].data_ptr(), B, 1, H, Hkv, D, kc[i].stride(0), kc[i].stride(1), 0,
+                                                    c["pos"].data_ptr(), 1, _lib.stream_ptr(dev)), "llm_rope_qkv")
                     sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out)
                     gemv(attn_out, ly["wo"], ly["bo"], None, resid, res_a, H * D, hid, 0)
                     gemv(res_a, ly["wgu"], None, ly["w_post"], None, gu_b, hid, 2 * inter, 1, ly["eps_post"], pair=1)  # -> act [B, inter]
@@ -366,6 +373,7 @@ class FusedPrefill:
 
 PAIR_GEMM_ALL = os.environ.get("SDAG_PAIR_GEMM", "") == "all"
 PAIR_GEMM_MIN_ROWS = 512  # prefill gate/up projections with at least this many token rows run on llm_gemm (fused SwiGLU)
+FUSED_ROPE_GEMV = os.environ.get("SDAG_NO_FUSED_ROPE", "") != "1"  # decode q/k/v GEMV with the RoPE + cache-write epilogue
 USE_FUSED_GEMV = True  # decode-step linear layers on llm_gemv (B <= 4); False: cuBLAS + stand-alone glue kernels
 
 

@@ -660,3 +660,39 @@ def test_fused_prefill_with_pair_gemm_matches_cublas_path(monkeypatch):
     got, _ = runner.prefill(ids, bm, want_cache=False)
     torch.testing.assert_close(got.float(), ref.float(), atol=5e-2, rtol=5e-2)
     assert (got.argmax(-1) == ref.argmax(-1)).all()
+
+
+@pytest.mark.parametrize("B,bias", [(1, False), (2, True), (4, True)])
+def test_decode_qkv_gemv_with_rope_epilogue_equals_two_launch_form(B, bias):
+    """llm_gemv_rope (q/k/v projection + RoPE + cache write in one launch) is bit-identical to llm_gemv -> llm_rope_qkv."""
+    import sdag_b200._lib as L
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(B)
+    H, Hkv, D, K, S = 4, 2, 64, 512, 96
+    N = (H + 2 * Hkv) * D
+    x = torch.randn(B, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    bq = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16) if bias else None
+    nw = (1 + 0.1 * torch.randn(K, generator=g, device="cuda")).to(torch.bfloat16)
+    ang = torch.rand(S, D, generator=g, device="cuda") * 6.28
+    cos, sin = ang.cos().to(torch.bfloat16), ang.sin().to(torch.bfloat16)
+    pos = torch.tensor([5, 17, 0, 95][:B], dtype=torch.int32, device="cuda")
+    st = L.stream_ptr(x.device)
+
+    def buffers():
+        return (torch.zeros(B, 1, H, D, dtype=torch.bfloat16, device="cuda"),
+                torch.zeros(B, Hkv, S, D, dtype=torch.bfloat16, device="cuda"), torch.zeros(B, Hkv, S, D, dtype=torch.bfloat16, device="cuda"))
+
+    q1, k1, v1 = buffers()
+    qkv = torch.empty(B, N, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.llm_gemv(x.data_ptr(), W.data_ptr(), L.ptr(bq), nw.data_ptr(), 0, qkv.data_ptr(), B, K, N, 1, 1e-5, 0, st), "gemv")
+    L.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q1.data_ptr(), k1.data_ptr(), v1.data_ptr(), B, 1, H, Hkv, D,
+                             k1.stride(0), k1.stride(1), 0, pos.data_ptr(), 1, st), "rope")
+    q2, k2, v2 = buffers()
+    L.check(lib.llm_gemv_rope(x.data_ptr(), W.data_ptr(), L.ptr(bq), nw.data_ptr(), 1e-5, cos.data_ptr(), sin.data_ptr(), q2.data_ptr(),
+                              k2.data_ptr(), v2.data_ptr(), B, K, H, Hkv, D, k2.stride(0), k2.stride(1), 0, pos.data_ptr(), 1, st), "gemv_rope")
+    assert q1.abs().sum() > 0 and k1.abs().sum() > 0 and v1.abs().sum() > 0
+    assert torch.equal(q1, q2) and torch.equal(k1, k2) and torch.equal(v1, v2)
+    assert lib.llm_gemv_rope(x.data_ptr(), W.data_ptr(), 0, nw.data_ptr(), 1e-5, cos.data_ptr(), sin.data_ptr(), q2.data_ptr(),
+                             k2.data_ptr(), v2.data_ptr(), 5, K, H, Hkv, D, k2.stride(0), k2.stride(1), 0, pos.data_ptr(), 1, st) == 1002
