@@ -8,6 +8,8 @@ identifier).  Sub-modules mirror the reference's modules on the two hot paths:
 * ``selection``  — ``src/pipeline/attack/malicious_selection.py``
 * ``generation`` — ``generate_batch_seq2seq`` (attack/content_generation.py) / ``generate_noiso_batch`` (main.py): CARG
 * ``hybrid``     — ``src/pipeline/retrieval/hybrid.py`` (RRF fusion, host only)
+* ``harness``    — the query loop of ``src/pipeline/main.py`` with its answer scoring, per-pair CSV and JSON metrics
+                   (``utils/normalization.py``, ``parsing.py``, ``save_results.py``, ``metrics.py``; host only)
 * ``ranked_list``, ``prompts``, ``datamodels``, ``config`` — the small host-side pieces those call into
 
 All arithmetic runs in ``libsdag_b200.so`` (hand-written CUDA, C ABI in ``include/sdag_b200.h``).

@@ -14,7 +14,7 @@ that are not installable here are replaced by stubs *before* import:
   (so the search arithmetic itself stays "parity unpinned", see oracle/__init__.py).
 
 Outputs (all small): masks.npz, attention.npz, generation.json, knn.json, selector.json, retrieval.json,
-ranked_list.json, hybrid.json, encoder.npz, carg.json, pipeline.json.
+ranked_list.json, hybrid.json, harness.json, encoder.npz, carg.json, pipeline.json.
 """
 from __future__ import annotations
 
@@ -372,6 +372,94 @@ def gen_hybrid():
     print("hybrid:", len(cases), "cases")
 
 
+def harness_inputs():
+    """Seeded synthetic result rows, answer strings and an attack CSV for the evaluation harness (shared with the test)."""
+    rnd = random.Random(23)
+    facts = ["Paris", "the Eiffel Tower", "1889", "Gustave Eiffel", "an iron lattice", "Île-de-France", "A. G. Eiffel & Co."]
+    fakes = ["London", "1901", "a steel arch", "Rome"]
+    filler = ["It rains often.", "The river is long!", "Nobody knows, really.", "An apple a day.", "Towers are tall; bridges are long."]
+    rows = []
+    for q in range(40):
+        gts = rnd.sample(facts, rnd.randint(1, 2))
+        fas = rnd.sample(fakes, rnd.randint(0, 2))
+        docs = []
+        for _ in range(rnd.randint(0, 7)):
+            d = rnd.choice(filler)
+            if rnd.random() < 0.35:
+                d += " " + rnd.choice(gts).upper() + "."
+            docs.append(d)
+        rows.append({
+            "query_id": f"q{q}", "question": f"question {q}?", "short_answers": gts if q % 9 else gts[0],
+            "false_answer": fas if q % 4 else (fas[0] if fas else ""), "malicious_doc": "bad doc" if q % 3 else "",
+            "retrieved_docs": docs if q % 13 else None, "retrieved_doc_ids": [f"d{i}" for i in range(len(docs))],
+            "rag_answer_iso": rnd.choice(gts + fas + ["unknown"]), "rag_answer_noiso": rnd.choice(gts + fas + ["unknown"]),
+            "ground_truth_match_iso": rnd.random() < 0.5, "ground_truth_match_noiso": rnd.random() < 0.4,
+            "false_match_iso": rnd.random() < 0.2, "false_match_noiso": rnd.random() < 0.5,
+        })
+    texts = ["The Eiffel Tower!", "  an  APPLE, a day... ", "Île-de-France", "<think>hmm the answer</think>Paris", None,
+             "Answer: Paris\nbecause", "- Final Answer:  1889  ", "\n\n  \nsecond line\nthird", "<THINK>x</THINK> final answer: Rome",
+             "", "a an the", "naïve café — déjà vu", "A.G. Eiffel & Co."]
+    csv_rows = [
+        ("who built it", "7", '["Gustave Eiffel", "Eiffel"]', "Rome", "doc one"),
+        ("who built it", "7", '["ignored"]', "Rome", "doc two"),
+        ("who built it", "7", "", "London", ""),
+        ("when", "8", "['1889', '1887']", "", "doc three"),
+        ("where", "9", "Paris ||| France", "Berlin", "doc four"),
+        ("what", "10", "iron, steel", " ", "doc five"),
+        ("why", "11", "because", "x", "doc six"),
+        ("when", "8", "1889", "1900", "doc seven"),
+    ]
+    return rows, texts, csv_rows
+
+
+def gen_harness():
+    """Reference evaluation utilities (utils/normalization.py, metrics.py, parsing.py, save_results.py) on seeded synthetic rows."""
+    import contextlib
+    import csv
+    import io
+    import tempfile
+
+    from src.pipeline.utils import metrics as ref_metrics
+    from src.pipeline.utils import normalization as ref_norm
+    from src.pipeline.utils import parsing as ref_parsing
+    from src.pipeline.utils import save_results as ref_save
+
+    rows, texts, csv_rows = harness_inputs()
+    out = {}
+    out["normalize"] = [ref_norm.normalize_answer(t) for t in texts if t is not None]
+    out["extract"] = [ref_norm.extract_final_answer(t) for t in texts]
+    out["exact"] = [[bool(ref_metrics.exact_match(a, b)) for b in texts] for a in texts]
+    out["exact_norm_module"] = [[bool(ref_norm.exact_match(a, b)) for b in texts if b is not None] for a in texts if a is not None]
+    out["parse_list"] = [ref_parsing.parse_list_field(c) for c in [r[2] for r in csv_rows] + [None, "  ", "[1, 2]", "{'a': 1}"]]
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "attack.csv")
+        with open(path, "w", encoding="utf-8", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["query", "query_id", "ground_truth_answers", "false_answer", "malicious_document"])
+            w.writerows(csv_rows)
+        out["load_from_csv"] = [list(x) for x in ref_parsing.load_from_csv(path)]
+        out["load_from_csv_by_id"] = [list(x) for x in ref_parsing.load_from_csv(path, match_field_for_groups="query_id")]
+        full = [dict(r, short_answers=ref_metrics.ensure_list(r["short_answers"]),
+                     false_answer=r["false_answer"] if isinstance(r["false_answer"], str) else " / ".join(r["false_answer"]),
+                     retrieved_docs=r["retrieved_docs"] or []) for r in rows]
+        csv_path = os.path.join(td, "sub", "res.csv")
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            ref_save.save_results(full, csv_path)
+        out["save_results_csv"] = open(csv_path, encoding="utf-8", newline="").read()
+        out["save_results_stdout"] = buf.getvalue()
+    out["retrieval_stats"] = {str(k): ref_metrics.compute_retrieval_ground_truth_stats(rows, k) for k in (1, 3, 5)}
+    out["retrieval_stats_empty"] = ref_metrics.compute_retrieval_ground_truth_stats([], 4)
+    out["overlap"] = ref_metrics.compute_answer_overlap_and_attack_stats(rows)
+    out["overlap_empty"] = ref_metrics.compute_answer_overlap_and_attack_stats([])
+    out["pair_metrics"] = ref_metrics.build_pair_metrics(rows, 5, 2)
+    out["pair_metrics_empty"] = ref_metrics.build_pair_metrics([], 3, 0)
+    out["false_answer_stats"] = ref_metrics.compute_false_answer_stats_for_results(rows)
+    with open(os.path.join(HERE, "harness.json"), "w") as f:
+        json.dump(out, f, indent=1, ensure_ascii=False)
+    print("harness:", len(rows), "rows")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:  # regenerate selected fixtures only: make_golden.py hybrid ...
         torch.manual_seed(0)
@@ -387,6 +475,7 @@ if __name__ == "__main__":
     gen_retrieval()
     gen_ranked_list()
     gen_hybrid()
+    gen_harness()
     gen_encoder()
     gen_carg()
     gen_pipeline()

@@ -1,0 +1,106 @@
+"""Evaluation harness (sdag_b200.harness) against outputs of the reference's own utilities on seeded synthetic rows
+(tests/golden/harness.json, written by tests/golden/make_golden.py: utils/normalization.py, metrics.py, parsing.py,
+save_results.py).  Host logic only."""
+import contextlib
+import csv
+import io
+import json
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    with open(os.path.join(golden_dir, "harness.json"), encoding="utf-8") as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def inputs():
+    # the input generator lives next to the golden script; importing make_golden itself would need /root/reference
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"), encoding="utf-8").read()
+    start = src.index("def harness_inputs():")
+    end = src.index("def gen_harness():")
+    ns = {"random": __import__("random")}
+    exec(src[start:end], ns)
+    return ns["harness_inputs"]()
+
+
+def test_answer_scoring_matches_reference(gold, inputs):
+    from sdag_b200 import harness as h
+
+    _, texts, _ = inputs
+    assert [h.normalize_answer(t) for t in texts if t is not None] == gold["normalize"]
+    assert [h.extract_final_answer(t) for t in texts] == gold["extract"]
+    assert [[h.exact_match(a, b) for b in texts] for a in texts] == gold["exact"]
+    assert [[h.exact_match(a, b) for b in texts if b is not None] for a in texts if a is not None] == gold["exact_norm_module"]
+
+
+def test_attack_csv_loader_matches_reference(gold, inputs, tmp_path):
+    from sdag_b200 import harness as h
+
+    _, _, csv_rows = inputs
+    cells = [r[2] for r in csv_rows] + [None, "  ", "[1, 2]", "{'a': 1}"]
+    assert [h.parse_list_field(c) for c in cells] == gold["parse_list"]
+    path = tmp_path / "attack.csv"
+    with open(path, "w", encoding="utf-8", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["query", "query_id", "ground_truth_answers", "false_answer", "malicious_document"])
+        w.writerows(csv_rows)
+    assert [list(x) for x in h.load_from_csv(str(path))] == gold["load_from_csv"]
+    assert [list(x) for x in h.load_from_csv(str(path), match_field_for_groups="query_id")] == gold["load_from_csv_by_id"]
+    bad = tmp_path / "bad.csv"
+    bad.write_text("query,query_id\nq,1\n")
+    with pytest.raises(ValueError, match="missing required columns"):
+        h.load_from_csv(str(bad))
+
+
+def test_result_csv_is_byte_identical_to_reference(gold, inputs, tmp_path):
+    from sdag_b200 import harness as h
+
+    rows, _, _ = inputs
+    full = [dict(r, short_answers=h.ensure_list(r["short_answers"]),
+                 false_answer=r["false_answer"] if isinstance(r["false_answer"], str) else " / ".join(r["false_answer"]),
+                 retrieved_docs=r["retrieved_docs"] or []) for r in rows]
+    out = tmp_path / "sub" / "res.csv"
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        h.save_results(full, str(out))
+    assert open(out, encoding="utf-8", newline="").read() == gold["save_results_csv"]
+    assert buf.getvalue() == gold["save_results_stdout"]
+
+
+def test_pair_metrics_json_matches_reference(gold, inputs):
+    from sdag_b200 import harness as h
+
+    rows, _, _ = inputs
+
+    def same(a, b):  # same JSON text: keys, key order, values
+        return json.dumps(a, ensure_ascii=False) == json.dumps(b, ensure_ascii=False)
+
+    for k in (1, 3, 5):
+        assert same(h.compute_retrieval_ground_truth_stats(rows, k), gold["retrieval_stats"][str(k)]), k
+    assert same(h.compute_retrieval_ground_truth_stats([], 4), gold["retrieval_stats_empty"])
+    assert same(h.compute_answer_overlap_and_attack_stats(rows), gold["overlap"])
+    assert same(h.compute_answer_overlap_and_attack_stats([]), gold["overlap_empty"])
+    assert same(h.build_pair_metrics(rows, 5, 2), gold["pair_metrics"])
+    assert same(h.build_pair_metrics([], 3, 0), gold["pair_metrics_empty"])
+    assert same(h.compute_false_answer_stats_for_results(rows), gold["false_answer_stats"])
+
+
+def test_pair_specs_and_row_scoring():
+    from sdag_b200 import harness as h
+
+    assert h.build_pair_specs([5, 10, 3], [1, -1]) == [h.PairSpec(5, 1), h.PairSpec(10, -1)]
+    assert h.compute_max_k_needed([h.PairSpec(5, 1), h.PairSpec(10, 0)]) == 10
+    assert h.compute_max_k_needed([h.PairSpec(5, 1)], "doc_corruption") == 6
+    assert h.attack_config_requests_docs(0) is False and h.attack_config_requests_docs([0, 2]) and not h.attack_config_requests_docs("x")
+    row = h.score_answers("q1", "who?", ["Gustave Eiffel"], ["Rome"], ["d a", "d b"], ["1", "2"], ["evil"], 1,
+                          "<think>..</think>Answer: gustave EIFFEL.\nmore", "It was Rome")
+    assert row["rag_answer_iso"] == "gustave EIFFEL." and row["ground_truth_match_iso"] and not row["false_match_iso"]
+    assert row["false_match_noiso"] and not row["ground_truth_match_noiso"] and row["malicious_doc"] == "evil"
+    assert h.score_answers("q", "w", ["x"], [], [], [], ["evil"], 0, "x", "y")["malicious_doc"] == ""

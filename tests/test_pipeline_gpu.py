@@ -80,3 +80,60 @@ def test_qwen2_geometry_runs_through_fused_engine():
     assert torch.equal(got.argmax(-1), ref.argmax(-1))
     out = get_runner(model).generate(ids, bm, 12, None)
     assert out.shape == (2, 13)
+
+
+def test_main_shaped_harness_writes_reference_csv_and_json(golden_dir, tmp_path):
+    """sdag_b200.harness.main over the miniature pipeline: two (TOP_K, ADD_ATTACK_IN_RANK) pairs, the per-pair CSV / JSON
+    files of the reference's main.py; the ISO answers equal the per-query run_rag_with_doc_isolation answers and the
+    metrics equal build_pair_metrics over the CSV's own rows."""
+    import csv
+
+    import sdag_b200.sdag as sdag
+    from sdag_b200 import config, harness
+    from sdag_b200.retrieval import DenseRetriever, FlatIPIndex
+
+    with open(os.path.join(golden_dir, "pipeline.json")) as f:
+        g = json.load(f)
+    tok = synth.make_tokenizer()
+    model = synth.tiny_llama(len(tok)).cuda()
+    ranker = synth.HashRanker()
+    meta = [dict(id=f"d{i}", text=t) for i, t in enumerate(g["corpus"])]
+    emb = np.stack([synth.text_embedding("passage: " + t) for t in g["corpus"]])
+    index = FlatIPIndex(emb.shape[1])
+    index.add(emb)
+    retr = DenseRetriever(ranker, index, meta)
+    nq = len(g["queries"])
+    saved = {k: getattr(config, k) for k in ("TOP_K", "ADD_ATTACK_IN_RANK", "MAX_GEN_TOKENS_RAG", "TEMPERATURE", "BATCH_SIZE_EMBED_Q",
+                                              "MALICIOUS_DOC_SELECTION_STRATEGY", "MAX_MALICIOUS_DOCS_PER_QUERY", "DOC_NEIGHBORS_K")}
+    old_temp = sdag.TEMPERATURE
+    try:
+        config.TOP_K, config.ADD_ATTACK_IN_RANK = [g["top_k"], 2], [g["rank"], 0]
+        config.MAX_GEN_TOKENS_RAG, config.TEMPERATURE, config.BATCH_SIZE_EMBED_Q = 5, 0.0, 3
+        config.MALICIOUS_DOC_SELECTION_STRATEGY, config.MAX_MALICIOUS_DOCS_PER_QUERY = g["strategy"], g["max_docs"]
+        config.DOC_NEIGHBORS_K = g["doc_neighbors_k"]
+        sdag.TEMPERATURE = 0
+        sdag.MAX_GEN_TOKENS_RAG = 5
+        gts = [[w] for w in ("tower", "honey", "paris", "river", "moon", "stone", "apple", "cloud")][:nq]
+        out = harness.main(retriever=retr, llm_model=model, tokenizer=tok, ranker=ranker, queries=g["queries"], short_answers=gts,
+                           query_ids=[f"q{i}" for i in range(nq)], false_answer_groups=[["rome"]] * nq,
+                           malicious_doc_groups=g["candidates"], output_base=str(tmp_path / "run"))
+    finally:
+        for k, v in saved.items():
+            setattr(config, k, v)
+        sdag.TEMPERATURE = old_temp
+    assert set(out) == {(g["top_k"], g["rank"]), (2, 0)}
+    for (k, pos), metrics in out.items():
+        stem = tmp_path / f"run_top_k={k}_attacker_pos={pos}"
+        rows = list(csv.DictReader(open(str(stem) + ".csv", encoding="utf-8", newline="")))
+        assert [r["query_id"] for r in rows] == [f"q{i}" for i in range(nq)] and list(rows[0]) == list(harness.RESULT_FIELDS)
+        assert all(len(r["retrieved_doc_ids"].split("\n")) == k + 1 for r in rows)
+        on_disk = json.load(open(str(stem) + ".json", encoding="utf-8"))
+        assert on_disk["num_queries"] == nq and on_disk["top_k"] == k and on_disk["attack_position_in_rank"] == pos
+        assert on_disk["run_config"]["TOP_K"] == [g["top_k"], 2]
+        gt_iso = sum(int(r["ground_truth_match_iso"]) for r in rows)
+        assert on_disk["answer_match_stats"]["iso"]["ground_truth_match_count"] == gt_iso
+        assert (pos != 0) == any(r["malicious_doc"] for r in rows)
+    # the ISO column of the golden pair is what the per-query reference call answers (first line of the answer)
+    rows = list(csv.DictReader(open(str(tmp_path / f"run_top_k={g['top_k']}_attacker_pos={g['rank']}") + ".csv", encoding="utf-8", newline="")))
+    agree = sum(harness.extract_final_answer(want) == r["rag_answer_iso"] for want, r in zip(g["answers"], rows))
+    assert agree >= nq - 1, (agree, [r["rag_answer_iso"] for r in rows], g["answers"])
