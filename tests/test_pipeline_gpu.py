@@ -126,14 +126,27 @@ def test_main_shaped_harness_writes_reference_csv_and_json(golden_dir, tmp_path)
         stem = tmp_path / f"run_top_k={k}_attacker_pos={pos}"
         rows = list(csv.DictReader(open(str(stem) + ".csv", encoding="utf-8", newline="")))
         assert [r["query_id"] for r in rows] == [f"q{i}" for i in range(nq)] and list(rows[0]) == list(harness.RESULT_FIELDS)
-        assert all(len(r["retrieved_doc_ids"].split("\n")) == k + 1 for r in rows)
+        # the pool is the first k + 1 documents of a retrieval done once at the deepest k (main.py:153-169, 433-437)
+        assert all(len(r["retrieved_doc_ids"].split("\n")) == min(k + 1, g["top_k"]) for r in rows)
         on_disk = json.load(open(str(stem) + ".json", encoding="utf-8"))
         assert on_disk["num_queries"] == nq and on_disk["top_k"] == k and on_disk["attack_position_in_rank"] == pos
         assert on_disk["run_config"]["TOP_K"] == [g["top_k"], 2]
         gt_iso = sum(int(r["ground_truth_match_iso"]) for r in rows)
         assert on_disk["answer_match_stats"]["iso"]["ground_truth_match_count"] == gt_iso
         assert (pos != 0) == any(r["malicious_doc"] for r in rows)
-    # the ISO column of the golden pair is what the per-query reference call answers (first line of the answer)
+    # the ISO column is what the per-query entry point answers for the same pool (first line of the answer)
+    from sdag_b200.selection import select_malicious_docs_for_batch
+
     rows = list(csv.DictReader(open(str(tmp_path / f"run_top_k={g['top_k']}_attacker_pos={g['rank']}") + ".csv", encoding="utf-8", newline="")))
-    agree = sum(harness.extract_final_answer(want) == r["rag_answer_iso"] for want, r in zip(g["answers"], rows))
-    assert agree >= nq - 1, (agree, [r["rag_answer_iso"] for r in rows], g["answers"])
+    rb = retr.retrieve_batch(g["queries"], max_k_needed=g["top_k"], embed_batch_size=3)
+    chosen = select_malicious_docs_for_batch(ranker, rb.docs_texts_full, g["candidates"], g["strategy"], g["max_docs"])
+    old_temp, sdag.TEMPERATURE = sdag.TEMPERATURE, 0
+    try:
+        want = [sdag.run_rag_with_doc_isolation(model=model, tokenizer=tok, query=q, malicious_docs=mal, retrieved_docs=docs[: g["top_k"] + 1],
+                                                max_new_tokens=5, device="cuda", add_attack_in_rank=g["rank"], ranker=ranker,
+                                                doc_neighbors_k=g["doc_neighbors_k"])
+                for q, docs, mal in zip(g["queries"], rb.docs_texts_full, chosen)]
+    finally:
+        sdag.TEMPERATURE = old_temp
+    assert [harness.extract_final_answer(w) for w in want] == [r["rag_answer_iso"] for r in rows]
+    assert [r["malicious_doc"] for r in rows] == [" ||| ".join(c) for c in chosen]
