@@ -39,6 +39,7 @@ def sustained(fn, flops, seconds=1.5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tokens", type=int, default=21248)
+    ap.add_argument("--only", default="", help="run one shape by name (qkv, o, gate_up, gate_up+swiglu, down)")
     ap.add_argument("--sustain", action="store_true", help="also report TFLOP/s of 1.5 s back-to-back runs")
     args = ap.parse_args()
     lib = _lib.load()
@@ -48,6 +49,8 @@ def main():
     torch.manual_seed(0)
     for name, N, K, epi in (("qkv", 6144, 4096, 0), ("o", 4096, 4096, 0), ("gate_up", 28672, 4096, 0),
                             ("gate_up+swiglu", 28672, 4096, 1), ("down", 4096, 14336, 0)):
+        if args.only and name != args.only:
+            continue
         x = torch.randn(M, K, device=dev, dtype=torch.bfloat16) * 0.5
         w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.02
         n_out = N // 2 if epi else N
