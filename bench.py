@@ -188,6 +188,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import sdag_b200._lib as L_
+    import sdag_b200.llama_runner as llama_runner
     import sdag_b200.sdag as sdag
     from sdag_b200.retrieval import FlatIPIndex, ShardedFlatIPIndex
 
@@ -243,6 +244,7 @@ def run_b200(args):
         sampler.start()
         if collect_attn:
             sdag._profile_events = []
+            llama_runner._gemm_events = []
         launches0 = L_.launch_count
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -256,7 +258,11 @@ def run_b200(args):
         if collect_attn:
             evs, sdag._profile_events = sdag._profile_events, None
             attn_ms = [a.elapsed_time(b) for a, b in evs]
+            gevs, llama_runner._gemm_events = llama_runner._gemm_events, None
+            gemm_samples[:] = [(a.elapsed_time(b), rows) for a, b, rows in gevs]
         return max_over_ranks(ms), clocks, L_.launch_count - launches0, attn_ms
+
+    gemm_samples = []  # (ms, token rows) of the gate/up llm_gemm launches of the last timed run
 
     def bad_clocks(c):
         return any(r in c.get("reasons", []) for r in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"))
@@ -302,6 +308,19 @@ def run_b200(args):
 
     dense_tiles = dense_tiles_rate()
 
+    # the launch that takes the largest share of the step (ncu launch list: ~50 %): the gate/up projection with the
+    # SwiGLU epilogue on this repo's CTA-pair GEMM, timed live with CUDA events inside the timed region above
+    step_dominant = None
+    if gemm_samples:
+        inter, hid = model.config.intermediate_size, model.config.hidden_size
+        g_ms = sum(m for m, _ in gemm_samples) / len(gemm_samples)
+        g_fl = sum(2.0 * r * 2 * inter * hid for _, r in gemm_samples) / len(gemm_samples)
+        step_dominant = {"kernel": "llm_gemm_kernel<SWIGLU> (gate/up projection + SwiGLU epilogue, tcgen05 cta_group::2)",
+                         "bound": "tensor", "launch_ms": g_ms, "flops_per_launch": g_fl,
+                         "achieved": g_fl / (g_ms / 1000.0) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": g_fl / (g_ms / 1000.0) / 1e12 / peak,
+                         "share_of_step": g_ms * len(gemm_samples) / args.steps / (ms / args.steps)}
+
     carg = None
     if args.carg:
         ms_c, _, _, _ = timed(lambda: step_resident(None), args.steps, args.warmup)
@@ -317,8 +336,9 @@ def run_b200(args):
             "prompts_per_step_per_gpu": B, "tokens_per_step": tokens_per_step, "layers": args.layers,
             "partition": "independent query batches per GPU, weights replicated, no collective",
             "cache": "inputs larger than L2 (16 GB of weights stream through every step)",
-            "linear_layers": "cuBLAS via torch (plain library GEMMs); attention, block map, RMSNorm / RoPE+KV write / "
-                             "SwiGLU glue: this repo's kernels (llama_runner.FusedPrefill)",
+            "linear_layers": "gate/up projection + SwiGLU on this repo's CTA-pair tcgen05 GEMM (llm_gemm); q/k/v, o, down on cuBLAS "
+                             "via torch (plain library GEMMs); attention, block map, RMSNorm / RoPE+KV write glue: this repo's "
+                             "kernels (llama_runner.FusedPrefill)",
             "remeasured_for_clocks": remeasured,
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
@@ -327,7 +347,8 @@ def run_b200(args):
                      "traffic": 508.5e6 * B / 8 if B == 8 else None,
                      "kernel": "sdag_prefill_kernel<128> (+ v_colsum, v_mean) per layer launch",
                      "launch_ms": attn_avg_ms, "flops_per_launch": attn_flops_per_launch,
-                     "peak_source": pk["_source"] + ", bf16 sustained", "unmasked_tiles": dense_tiles},
+                     "peak_source": pk["_source"] + ", bf16 sustained", "unmasked_tiles": dense_tiles,
+                     "step_dominant_kernel": step_dominant},
         "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": int(ids_host.numel() * 8 + B * 28 * 4),
                 "d2h_bytes_per_step": B * 8, "api": "sdag_b200.sdag.prefill_batch (pinned host ids -> first tokens on host)"},
         "gpu_launches": launches, "clocks": clocks,

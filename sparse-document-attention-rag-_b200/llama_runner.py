@@ -174,8 +174,15 @@ class FusedPrefill:
         _lib.count_launches(1)
         if rows >= PAIR_GEMM_MIN_ROWS and self.inter % 8 == 0:
             # gate/up GEMM on CTA pairs with the SwiGLU in its epilogue: the [rows, 2*inter] intermediate is never written
+            ev = None
+            if _gemm_events is not None:  # bench.py: CUDA-event timing of the gate/up launches, on their stream
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             _lib.check(lib.llm_gemm(normed.data_ptr(), normed.stride(0), ly["wgu"].data_ptr(), 0, act.data_ptr(), self.inter,
                                     rows, 2 * self.inter, self.hidden, 1, _lib.stream_ptr(normed.device)), "llm_gemm")
+            if ev is not None:
+                ev[1].record()
+                _gemm_events.append(ev + (rows,))
         else:
             gu = F.linear(normed, ly["wgu"])
             _lib.check(lib.llm_swiglu(gu.data_ptr(), act.data_ptr(), rows, self.inter, _lib.stream_ptr(gu.device)), "llm_swiglu")
@@ -371,6 +378,7 @@ class FusedPrefill:
         return c["gen"][:, : done + 1].clone()
 
 
+_gemm_events = None  # set to a list to collect (start, end, rows) around each prefill gate/up llm_gemm launch
 PAIR_GEMM_ALL = os.environ.get("SDAG_PAIR_GEMM", "") == "all"
 PAIR_GEMM_MIN_ROWS = 512  # prefill gate/up projections with at least this many token rows run on llm_gemm (fused SwiGLU)
 FUSED_ROPE_GEMV = os.environ.get("SDAG_NO_FUSED_ROPE", "") != "1"  # decode q/k/v GEMV with the RoPE + cache-write epilogue
