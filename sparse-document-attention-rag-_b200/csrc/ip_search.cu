@@ -36,6 +36,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024;
 constexpr int SORT_MAX = 2048;
 constexpr int SCAN_SLICES = 32;
+constexpr int SELECT_MAX_K = 32;  // tighten: k-th best by k max-extraction rounds up to this k, bitonic sort above
 // |bf16(x).bf16(q) - x.q| <= (2u + u^2) |x||q| with u = 2^-8, plus fp32 accumulation slack
 constexpr float ERR_COEF = 0.0078125f + 0.00048828125f;
 
@@ -424,7 +425,8 @@ tighten_kernel(SearchState st, int k, int force_cnt, const float* __restrict__ m
     n = st.cap;
   }
   Cand* cq = st.cand + static_cast<long long>(q) * st.cap;
-  const int P = pow2_at_least(n < 1 ? 1 : n);
+  const bool select = k <= SELECT_MAX_K;  // small k: k rounds of block-wide max instead of a full sort
+  const int P = select ? n : pow2_at_least(n < 1 ? 1 : n);
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     unsigned long long key = 0;
     if (i < n) {
@@ -435,22 +437,56 @@ tighten_kernel(SearchState st, int k, int force_cnt, const float* __restrict__ m
   }
   if (threadIdx.x == 0) n_keep_s = 0;
   __syncthreads();
-  bitonic_sort_desc(keys, P);
   float thr = st.thr[q];
+  unsigned long long kth_key = 0;
+  if (select) {
+    // keys are distinct (one row appears once): the r-th largest is the largest key below the (r-1)-th largest
+    __shared__ unsigned long long round_max[2];
+    if (n >= k) {
+      unsigned long long below = ~0ull;
+      for (int r = 0; r < k; ++r) {
+        if (threadIdx.x == 0) round_max[r & 1] = 0;
+        __syncthreads();
+        unsigned long long loc = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const unsigned long long key = keys[i];
+          if (key < below && key > loc) loc = key;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, loc, o);
+          loc = other > loc ? other : loc;
+        }
+        if ((threadIdx.x & 31) == 0 && loc) atomicMax(&round_max[r & 1], loc);
+        __syncthreads();
+        below = round_max[r & 1];  // the other slot is reset at the top of the next round, after this barrier
+      }
+      kth_key = below;
+    }
+  } else {
+    bitonic_sort_desc(keys, P);
+    if (n >= k) kth_key = keys[k - 1];
+  }
   if (n >= k) {
-    const float kth = unorderable(static_cast<uint32_t>(keys[k - 1] >> 32));
+    const float kth = unorderable(static_cast<uint32_t>(kth_key >> 32));
     const float e = ERR_COEF * st.qnorm[q] * (*max_norm);
     thr = fmaxf(thr, kth - 2.f * e);
   }
-  int keep = 0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float s = unorderable(static_cast<uint32_t>(keys[i] >> 32));
-    if (s >= thr) {
-      cq[i] = Cand{s, static_cast<int32_t>(keys[i] & 0xffffffffu)};
-      ++keep;
+  if (select) {  // survivors in any order (every consumer re-orders them)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float s = unorderable(static_cast<uint32_t>(keys[i] >> 32));
+      if (s >= thr) cq[atomicAdd(&n_keep_s, 1)] = Cand{s, static_cast<int32_t>(keys[i] & 0xffffffffu)};
     }
+  } else {
+    int keep = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float s = unorderable(static_cast<uint32_t>(keys[i] >> 32));
+      if (s >= thr) {
+        cq[i] = Cand{s, static_cast<int32_t>(keys[i] & 0xffffffffu)};
+        ++keep;
+      }
+    }
+    if (keep) atomicAdd(&n_keep_s, keep);  // sorted descending: the kept entries form a prefix
   }
-  if (keep) atomicAdd(&n_keep_s, keep);  // sorted descending: the kept entries form a prefix
   __syncthreads();
   if (threadIdx.x == 0) {
     st.thr[q] = thr;
