@@ -104,3 +104,62 @@ def test_pair_specs_and_row_scoring():
     assert row["rag_answer_iso"] == "gustave EIFFEL." and row["ground_truth_match_iso"] and not row["false_match_iso"]
     assert row["false_match_noiso"] and not row["ground_truth_match_noiso"] and row["malicious_doc"] == "evil"
     assert h.score_answers("q", "w", ["x"], [], [], [], ["evil"], 0, "x", "y")["malicious_doc"] == ""
+
+
+def test_main_loop_partitions_queries_across_ranks(tmp_path, monkeypatch):
+    """harness.main with ``query_slice`` (the query-parallel multi-GPU split, no collective): two ranks' CSV rows together are
+    the single-rank run's rows; retrieval happens once per batch at the deepest k; every pair gets its own files."""
+    import csv as _csv
+
+    from sdag_b200 import config, harness as h
+    from sdag_b200.datamodels import RetrievalBatch
+    import sdag_b200.selection as selection
+
+    nq = 11
+    queries = [f"what is item {i}?" for i in range(nq)]
+    calls = []
+
+    class FakeRetriever:
+        def retrieve_batch(self, qs, max_k_needed, embed_batch_size):
+            calls.append((tuple(qs), max_k_needed, embed_batch_size))
+            docs = [[f"{q} doc{j}" + (" answer" + q.split()[3] if j == 1 else "") for j in range(max_k_needed)] for q in qs]
+            ids = [[f"{q}-{j}" for j in range(max_k_needed)] for q in qs]
+            return RetrievalBatch(q_embs=[None] * len(qs), docs_texts_full=docs, ids_full=ids,
+                                  scores_full=[[1.0 / (j + 1) for j in range(max_k_needed)] for _ in qs])
+
+    def fake_pair(*, pair, batch_qids, batch_qs, batch_gts, retrieval_docs_full, retrieval_ids_full, false_groups_batch,
+                  chosen_mals_batch, **kw):
+        return [h.score_answers(qid, q, gts, fas, docs[: pair.top_k + 1], ids[: pair.top_k + 1], mals, pair.attacker_pos,
+                                f"Answer: {gts[0]}" if int(qid[1:]) % 2 else "unknown", f"{fas[0]} it is")
+                for qid, q, gts, fas, docs, ids, mals in zip(batch_qids, batch_qs, batch_gts, false_groups_batch, retrieval_docs_full,
+                                                             retrieval_ids_full, chosen_mals_batch)]
+
+    monkeypatch.setattr(h, "run_pair_malicious_doc_attack_for_batch", fake_pair)
+    monkeypatch.setattr(selection, "select_malicious_docs_for_batch",
+                        lambda ranker, retrieved_docs_batch_full, malicious_doc_groups_batch, strategy, max_docs: [g[:max_docs] for g in malicious_doc_groups_batch])
+    monkeypatch.setattr(config, "TOP_K", [3, 5])
+    monkeypatch.setattr(config, "ADD_ATTACK_IN_RANK", [1, 0])
+    monkeypatch.setattr(config, "BATCH_SIZE_EMBED_Q", 4)
+    common = dict(retriever=FakeRetriever(), llm_model=None, tokenizer=None, ranker=None, queries=queries,
+                  short_answers=[[f"answer{i}?"] for i in range(nq)], query_ids=[f"q{i}" for i in range(nq)],
+                  false_answer_groups=[["wrong"]] * nq, malicious_doc_groups=[[f"mal{i}a", f"mal{i}b"] for i in range(nq)])
+    full = h.main(output_base=str(tmp_path / "all"), **common)
+    assert set(full) == {(3, 1), (5, 0)} and all(c[1] == 5 and len(c[0]) <= 4 for c in calls) and len(calls) == 3
+    parts = [h.main(output_base=str(tmp_path / f"rank{r}"), query_slice=range(r, nq, 2), **common) for r in range(2)]
+
+    def rows(stem, k, pos):
+        return list(_csv.DictReader(open(f"{stem}_top_k={k}_attacker_pos={pos}.csv", encoding="utf-8", newline="")))
+
+    for k, pos in full:
+        whole = {r["query_id"]: r for r in rows(tmp_path / "all", k, pos)}
+        split = {r["query_id"]: r for rank in range(2) for r in rows(tmp_path / f"rank{rank}", k, pos)}
+        assert split == whole and len(whole) == nq
+        assert sum(p[(k, pos)]["num_queries"] for p in parts) == nq
+        iso = full[(k, pos)]["answer_match_stats"]["iso"]
+        assert iso["ground_truth_match_count"] == nq // 2 and full[(k, pos)]["answer_match_stats"]["no_iso"]["false_answer_match_count"] == nq
+        assert sum(p[(k, pos)]["answer_match_stats"]["iso"]["ground_truth_match_count"] for p in parts) == nq // 2
+        # the second retrieved document holds the ground truth -> every query sits in the "exactly 1 relevant document" bucket at rank 2
+        bucket = full[(k, pos)]["retrieval_ground_truth_stats"]["per_k_exact_match_buckets"]["1"]
+        assert bucket["queries_with_exactly_k_ground_truth_docs_count"] == nq
+        assert list(bucket["single_relevant_doc_rank_distribution"]) == ["2"]
+    assert h.main(output_base=str(tmp_path / "none"), query_slice=[], **common) == {}
