@@ -336,9 +336,9 @@ def run_b200(args):
             "prompts_per_step_per_gpu": B, "tokens_per_step": tokens_per_step, "layers": args.layers,
             "partition": "independent query batches per GPU, weights replicated, no collective",
             "cache": "inputs larger than L2 (16 GB of weights stream through every step)",
-            "linear_layers": "gate/up projection + SwiGLU on this repo's CTA-pair tcgen05 GEMM (llm_gemm); q/k/v, o, down on cuBLAS "
-                             "via torch (plain library GEMMs); attention, block map, RMSNorm / RoPE+KV write glue: this repo's "
-                             "kernels (llama_runner.FusedPrefill)",
+            "linear_layers": "gate/up projection + SwiGLU and q/k/v projection + RoPE + KV write on this repo's CTA-pair tcgen05 GEMM "
+                             "(llm_gemm, llm_gemm_rope); o and down projections on cuBLAS via torch (plain library GEMMs); "
+                             "attention, block map, RMSNorm: this repo's kernels (llama_runner.FusedPrefill)",
             "remeasured_for_clocks": remeasured,
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

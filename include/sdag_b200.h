@@ -191,6 +191,13 @@ int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* st
 #define LLM_GEMM_SWIGLU 1
 int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
              int N, int K, int epilogue, void* stream);
+/* The prefill's q/k/v projection with apply_rotary_pos_emb and the KV-cache write in the GEMM epilogue (llm_gemm on the
+ * fused [(H + 2*Hkv)*D, K] q|k|v weight followed by llm_rope_qkv, in one launch; the [B*L, (H+2Hkv)*D] intermediate is
+ * never written): x [B*L, K] rows ldx apart, token row b*L + l sits at position pos0 + l; q_out [B, L, H, D]; k_out /
+ * v_out, cos / sin as in llm_rope_qkv.  D = 64 or 128, H and Hkv multiples of 256 / D (SDAG_ERR_UNSUPPORTED otherwise). */
+int llm_gemm_rope(const void* x, int64_t ldx, const void* weight, const void* bias, const void* cos, const void* sin,
+                  void* q_out, void* k_out, void* v_out, int B, int L, int H, int Hkv, int D, int K,
+                  int64_t kv_stride_b, int64_t kv_stride_h, int pos0, void* stream);
 /* Decode-step linear layer (SDAG.py:191-211, one token per prompt, B <= 4): out [B,N] = xin [B,K] . weight[N,K]^T
  * (+ bias) (+ residual [B,N]), weight rows streamed once.  prologue 0: xin = x [B,K]; 1: xin = RMSNorm(x) *
  * norm_weight (eps); 2: x is a gate|up row [B,2K] and xin = silu(gate) * up.  pair_swiglu != 0: weight is a

@@ -40,7 +40,16 @@ struct Params {
   int up_offset;  // SwiGLU: first up row (= I)
   int group_n;    // weight tiles per raster group
   uint64_t hint_x, hint_w;  // L2 eviction priorities of the two operand streams
+  // LLM_GEMM_ROPE: weight = fused q|k|v rows, token row m = (prompt m / L, position pos0 + m % L)
+  const __nv_bfloat16* cos;  // [positions, D]
+  const __nv_bfloat16* sin;
+  __nv_bfloat16* q_out;      // [B, L, H, D]
+  __nv_bfloat16* k_out;      // cache [B, Hkv, S_cap, D], element strides kv_stride_b / kv_stride_h
+  __nv_bfloat16* v_out;
+  long long kv_stride_b, kv_stride_h;
+  int L, H, Hkv, D, pos0;
 };
+constexpr int LLM_GEMM_ROPE_EPI = 2;  // internal epilogue id of llm_gemm_rope
 
 struct Unit {
   int mt, nt;
@@ -201,7 +210,95 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_wait(&acc_full[a], (ui >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem + lane_addr + a * TNP;
-      if (EPI == LLM_GEMM_SWIGLU) {
+      if (EPI == LLM_GEMM_ROPE_EPI) {
+        // apply_rotary_pos_emb + cache write: a tile holds whole heads (256 / D of them); the partners d and d + D/2 of a
+        // rotation sit D/2 accumulator columns apart in this thread's row.  Roundings as in rope_qkv_kernel (llm_glue.cu).
+        const int D = p.D, half = D >> 1, heads_per_tile = TNP / D;
+        const long long m_odd = m_even + 1;
+        const int b_e = static_cast<int>(m_even / p.L), l_e = static_cast<int>(m_even % p.L);
+        const int b_o = static_cast<int>(m_odd / p.L), l_o = static_cast<int>(m_odd % p.L);
+        const int my_l = (lane & 1) ? l_o : l_e;
+        const __nv_bfloat16* cosr = p.cos + static_cast<long long>(p.pos0 + my_l) * D;
+        const __nv_bfloat16* sinr = p.sin + static_cast<long long>(p.pos0 + my_l) * D;
+        const bool my_ok = (lane & 1) ? ok_odd : ok_even;
+#pragma unroll 1
+        for (int hh = 0; hh < heads_per_tile; ++hh) {
+          const int head = un.nt * heads_per_tile + hh;
+          if (head >= p.H + 2 * p.Hkv) break;
+          __nv_bfloat16 *base_e, *base_o;
+          if (head < p.H) {
+            base_e = p.q_out + ((ok_even ? m_even : 0) * p.H + head) * D;
+            base_o = p.q_out + ((ok_odd ? m_odd : 0) * p.H + head) * D;
+          } else {
+            const bool is_k = head < p.H + p.Hkv;
+            __nv_bfloat16* cache = is_k ? p.k_out : p.v_out;
+            const int hk = head - p.H - (is_k ? 0 : p.Hkv);
+            base_e = cache + (ok_even ? b_e : 0) * p.kv_stride_b + hk * p.kv_stride_h + static_cast<long long>(p.pos0 + (ok_even ? l_e : 0)) * D;
+            base_o = cache + (ok_odd ? b_o : 0) * p.kv_stride_b + hk * p.kv_stride_h + static_cast<long long>(p.pos0 + (ok_odd ? l_o : 0)) * D;
+          }
+          const bool rotate = head < p.H + p.Hkv;
+#pragma unroll 1
+          for (int c = 0; c < half / 32; ++c) {
+            uint32_t xa[32], xb[32];
+            const int d0 = c * 32;
+            tmem_ld_32x32b_x32(tacc + hh * D + d0, xa);
+            tmem_ld_32x32b_x32(tacc + hh * D + half + d0, xb);
+            tmem_ld_wait();
+            uint32_t o1[16], o2[16];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {  // 8 elements at a time
+              float x1[8], x2[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                x1[e] = __uint_as_float(xa[8 * v + e]);
+                x2[e] = __uint_as_float(xb[8 * v + e]);
+              }
+              if (BIAS) {
+                const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(p.bias + head * D + d0) + v);
+                const uint4 b2 = __ldg(reinterpret_cast<const uint4*>(p.bias + head * D + half + d0) + v);
+                const uint32_t w1[4] = {b1.x, b1.y, b1.z, b1.w}, w2[4] = {b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w1[j]));
+                  const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w2[j]));
+                  x1[2 * j] += f1.x, x1[2 * j + 1] += f1.y, x2[2 * j] += f2.x, x2[2 * j + 1] += f2.y;
+                }
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x1[e] = bf_round(x1[e]), x2[e] = bf_round(x2[e]);  // nn.Linear output in bf16
+              float r1[8], r2[8];
+              if (rotate && my_ok) {
+                const uint4 cl = __ldg(reinterpret_cast<const uint4*>(cosr + d0) + v), ch = __ldg(reinterpret_cast<const uint4*>(cosr + half + d0) + v);
+                const uint4 sl = __ldg(reinterpret_cast<const uint4*>(sinr + d0) + v), sh = __ldg(reinterpret_cast<const uint4*>(sinr + half + d0) + v);
+                const uint32_t cw[4] = {cl.x, cl.y, cl.z, cl.w}, chw[4] = {ch.x, ch.y, ch.z, ch.w};
+                const uint32_t sw[4] = {sl.x, sl.y, sl.z, sl.w}, shw[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 c1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&cw[j]));
+                  const float2 c2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&chw[j]));
+                  const float2 s1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sw[j]));
+                  const float2 s2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&shw[j]));
+                  // rotate_half(x) = cat(-x[D/2:], x[:D/2])
+                  r1[2 * j] = bf_round(x1[2 * j] * c1.x) + bf_round(-x2[2 * j] * s1.x);
+                  r1[2 * j + 1] = bf_round(x1[2 * j + 1] * c1.y) + bf_round(-x2[2 * j + 1] * s1.y);
+                  r2[2 * j] = bf_round(x2[2 * j] * c2.x) + bf_round(x1[2 * j] * s2.x);
+                  r2[2 * j + 1] = bf_round(x2[2 * j + 1] * c2.y) + bf_round(x1[2 * j + 1] * s2.y);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r1[e] = x1[e], r2[e] = x2[e];
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                o1[4 * v + j] = pack_bf16x2(r1[2 * j], r1[2 * j + 1]);
+                o2[4 * v + j] = pack_bf16x2(r2[2 * j], r2[2 * j + 1]);
+              }
+            }
+            store_chunk(base_e, base_o, ok_even, ok_odd, d0, D, o1, lane);
+            store_chunk(base_e, base_o, ok_even, ok_odd, half + d0, D, o2, lane);
+          }
+        }
+      } else if (EPI == LLM_GEMM_SWIGLU) {
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {  // (half, 32-column chunk): gate at half*128 + chunk*32, up 64 columns further
           uint32_t g[32], v[32];
@@ -271,23 +368,8 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 1) tmem_dealloc_2cta(tmem, 512);
 }
 
-}  // namespace
-
-extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
-                        int N, int K, int epilogue, void* stream) {
-  if (!x || !weight || !out || M < 0 || N <= 0 || K <= 0) return SDAG_ERR_INVALID;
-  if (epilogue != LLM_GEMM_PLAIN && epilogue != LLM_GEMM_SWIGLU) return SDAG_ERR_INVALID;
-  if ((K % 8) || (ldx % 8) || (ldo % 8) || ldx < K) return SDAG_ERR_INVALID;  // 16-byte rows for TMA and the stores
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out)) & 15)
-    return SDAG_ERR_INVALID;
-  const bool swiglu = epilogue == LLM_GEMM_SWIGLU;
-  if (swiglu && ((N % 16) || bias)) return SDAG_ERR_INVALID;
-  if (!swiglu && (N % 8)) return SDAG_ERR_INVALID;
-  const int n_out = swiglu ? N / 2 : N;
-  if (ldo < n_out) return SDAG_ERR_INVALID;
-  if (M == 0) return SDAG_OK;
-  if (M > (1ll << 31) - 512) return SDAG_ERR_UNSUPPORTED;
-
+// Shared host part: tensor maps, raster parameters, launch.  `p` arrives with the epilogue-specific fields filled in.
+int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, int K, int epi, Params& p, cudaStream_t st) {
   CUtensorMap tmX, tmW;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
@@ -307,21 +389,19 @@ extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const vo
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_SWIGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int dev = 0;
     SDAG_CUDA_TRY(cudaGetDevice(&dev));
     SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
-  Params p;
-  p.bias = static_cast<const __nv_bfloat16*>(bias);
-  p.out = static_cast<__nv_bfloat16*>(out);
-  p.ldo = ldo;
+  const bool swiglu = epi == LLM_GEMM_SWIGLU;
   p.M = M;
-  p.n_out = n_out;
   p.n_mt = static_cast<int>((M + 2 * TMH - 1) / (2 * TMH));
-  p.n_nt = swiglu ? (n_out + 127) / 128 : (N + TNP - 1) / TNP;
+  p.n_nt = swiglu ? (p.n_out + 127) / 128 : (N + TNP - 1) / TNP;
   p.kblocks = (K + KB - 1) / KB;
-  p.up_offset = n_out;
+  p.up_offset = p.n_out;
   // raster group: as many weight tiles as stay L2-resident (~60 MB, loaded EVICT_LAST) while the token tiles stream past
   // them; EVICT_FIRST on the token rows was measured to hurt (bit 0 of the knob) and stays off
   static int group_env = -1, hint_env = -1;
@@ -338,13 +418,76 @@ extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const vo
   p.hint_w = (hint_env & 2) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
   const long long units = static_cast<long long>(p.n_mt) * p.n_nt;
   const long long pairs = units < n_sm / 2 ? units : n_sm / 2;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned grid = static_cast<unsigned>(2 * pairs);
   if (swiglu)
     llm_gemm_kernel<LLM_GEMM_SWIGLU, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
-  else if (bias)
+  else if (epi == LLM_GEMM_ROPE_EPI && p.bias)
+    llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (epi == LLM_GEMM_ROPE_EPI)
+    llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (p.bias)
     llm_gemm_kernel<LLM_GEMM_PLAIN, true><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   else
     llm_gemm_kernel<LLM_GEMM_PLAIN, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
+                        int N, int K, int epilogue, void* stream) {
+  if (!x || !weight || !out || M < 0 || N <= 0 || K <= 0) return SDAG_ERR_INVALID;
+  if (epilogue != LLM_GEMM_PLAIN && epilogue != LLM_GEMM_SWIGLU) return SDAG_ERR_INVALID;
+  if ((K % 8) || (ldx % 8) || (ldo % 8) || ldx < K) return SDAG_ERR_INVALID;  // 16-byte rows for TMA and the stores
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return SDAG_ERR_INVALID;
+  const bool swiglu = epilogue == LLM_GEMM_SWIGLU;
+  if (swiglu && ((N % 16) || bias)) return SDAG_ERR_INVALID;
+  if (!swiglu && (N % 8)) return SDAG_ERR_INVALID;
+  const int n_out = swiglu ? N / 2 : N;
+  if (ldo < n_out) return SDAG_ERR_INVALID;
+  if (M == 0) return SDAG_OK;
+  if (M > (1ll << 31) - 512) return SDAG_ERR_UNSUPPORTED;
+  Params p = {};
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.n_out = n_out;
+  return run_gemm(x, ldx, weight, M, N, K, epilogue, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int llm_gemm_rope(const void* x, int64_t ldx, const void* weight, const void* bias, const void* cos, const void* sin,
+                             void* q_out, void* k_out, void* v_out, int B, int L, int H, int Hkv, int D, int K,
+                             int64_t kv_stride_b, int64_t kv_stride_h, int pos0, void* stream) {
+  if (!x || !weight || !cos || !sin || !q_out || !k_out || !v_out) return SDAG_ERR_INVALID;
+  if (B < 0 || L <= 0 || H <= 0 || Hkv <= 0 || K <= 0 || pos0 < 0) return SDAG_ERR_INVALID;
+  if ((K % 8) || (ldx % 8) || ldx < K || (kv_stride_b % 8) || (kv_stride_h % 8)) return SDAG_ERR_INVALID;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(q_out) |
+       reinterpret_cast<uintptr_t>(k_out) | reinterpret_cast<uintptr_t>(v_out) | reinterpret_cast<uintptr_t>(cos) |
+       reinterpret_cast<uintptr_t>(sin) | reinterpret_cast<uintptr_t>(bias)) & 15)
+    return SDAG_ERR_INVALID;
+  // a 256-column tile must hold whole heads of one kind
+  if (D != 64 && D != 128) return SDAG_ERR_UNSUPPORTED;
+  const int heads_per_tile = TNP / D;
+  if ((H % heads_per_tile) || (Hkv % heads_per_tile)) return SDAG_ERR_UNSUPPORTED;
+  const int64_t M = static_cast<int64_t>(B) * L;
+  if (M == 0) return SDAG_OK;
+  if (M > (1ll << 31) - 512) return SDAG_ERR_UNSUPPORTED;
+  Params p = {};
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.cos = static_cast<const __nv_bfloat16*>(cos);
+  p.sin = static_cast<const __nv_bfloat16*>(sin);
+  p.q_out = static_cast<__nv_bfloat16*>(q_out);
+  p.k_out = static_cast<__nv_bfloat16*>(k_out);
+  p.v_out = static_cast<__nv_bfloat16*>(v_out);
+  p.kv_stride_b = kv_stride_b;
+  p.kv_stride_h = kv_stride_h;
+  p.L = L;
+  p.H = H;
+  p.Hkv = Hkv;
+  p.D = D;
+  p.pos0 = pos0;
+  const int N = (H + 2 * Hkv) * D;
+  p.n_out = N;
+  return run_gemm(x, ldx, weight, M, N, K, LLM_GEMM_ROPE_EPI, p, static_cast<cudaStream_t>(stream));
 }

@@ -136,8 +136,10 @@ class FusedPrefill:
             cache = DynamicCache(config=model.config) if _accepts_config(DynamicCache) else DynamicCache()
         last_rows = torch.arange(B, device=dev) * L + ((lengths - 1) if lengths is not None else (L - 1))
         n_layers = len(self.layers)
+        per_tile = 256 // D
+        fused_qkv = (FUSED_ROPE_GEMM and T >= PAIR_GEMM_MIN_ROWS and H % per_tile == 0 and Hkv % per_tile == 0
+                     and self.hidden % 8 == 0)
         for i, ly in enumerate(self.layers):
-            qkv = _linear(normed, ly["wqkv"], ly["bqkv"])
             q = torch.empty((B, L, H, D), dtype=torch.bfloat16, device=dev)
             if kv is not None:
                 kbuf, vbuf = kc_all[i], vc_all[i]
@@ -146,10 +148,16 @@ class FusedPrefill:
                 kbuf = k = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
                 vbuf = v = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
             _lib.count_launches(1)
-            _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kbuf.data_ptr(),
-                                        vbuf.data_ptr(), B, L, H, Hkv, D, kbuf.stride(0), kbuf.stride(1), 0, 0, 0, stream),
-                       "llm_rope_qkv")
-            del qkv
+            if fused_qkv:  # q/k/v projection on the CTA-pair GEMM with RoPE + cache write in its epilogue
+                _lib.check(lib.llm_gemm_rope(normed.data_ptr(), normed.stride(0), ly["wqkv"].data_ptr(), _lib.ptr(ly["bqkv"]),
+                                             cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kbuf.data_ptr(), vbuf.data_ptr(), B, L, H,
+                                             Hkv, D, self.hidden, kbuf.stride(0), kbuf.stride(1), 0, stream), "llm_gemm_rope")
+            else:
+                qkv = _linear(normed, ly["wqkv"], ly["bqkv"])
+                _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kbuf.data_ptr(),
+                                            vbuf.data_ptr(), B, L, H, Hkv, D, kbuf.stride(0), kbuf.stride(1), 0, 0, 0, stream),
+                           "llm_rope_qkv")
+                del qkv
             if cache is not None:
                 _cache_adopt(cache, k, v, i)
             attn = sdag.sdag_prefill_attention(q.transpose(1, 2), k, v, blockmap, ly["scaling"],
@@ -381,6 +389,7 @@ class FusedPrefill:
 _gemm_events = None  # set to a list to collect (start, end, rows) around each prefill gate/up llm_gemm launch
 PAIR_GEMM_ALL = os.environ.get("SDAG_PAIR_GEMM", "") == "all"
 PAIR_GEMM_MIN_ROWS = 512  # prefill gate/up projections with at least this many token rows run on llm_gemm (fused SwiGLU)
+FUSED_ROPE_GEMM = os.environ.get("SDAG_NO_FUSED_ROPE_GEMM", "") != "1"  # prefill q/k/v GEMM with the RoPE + cache-write epilogue
 FUSED_ROPE_GEMV = os.environ.get("SDAG_NO_FUSED_ROPE", "") != "1"  # decode q/k/v GEMV with the RoPE + cache-write epilogue
 USE_FUSED_GEMV = True  # decode-step linear layers on llm_gemv (B <= 4); False: cuBLAS + stand-alone glue kernels
 

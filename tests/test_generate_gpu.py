@@ -696,3 +696,41 @@ def test_decode_qkv_gemv_with_rope_epilogue_equals_two_launch_form(B, bias):
     assert torch.equal(q1, q2) and torch.equal(k1, k2) and torch.equal(v1, v2)
     assert lib.llm_gemv_rope(x.data_ptr(), W.data_ptr(), 0, nw.data_ptr(), 1e-5, cos.data_ptr(), sin.data_ptr(), q2.data_ptr(),
                              k2.data_ptr(), v2.data_ptr(), 5, K, H, Hkv, D, k2.stride(0), k2.stride(1), 0, pos.data_ptr(), 1, st) == 1002
+
+
+@pytest.mark.parametrize("B,L,H,Hkv,D,K,bias,pos0", [(2, 300, 4, 2, 128, 256, False, 0), (3, 130, 8, 4, 64, 192, True, 5), (1, 700, 2, 2, 128, 64, True, 0)])
+def test_prefill_qkv_gemm_with_rope_epilogue_equals_two_launch_form(B, L, H, Hkv, D, K, bias, pos0):
+    """llm_gemm_rope (q/k/v projection + RoPE + cache write in the GEMM epilogue) vs llm_gemm -> llm_rope_qkv: same
+    accumulators, same roundings, so the three outputs are bit-identical; cache rows outside [pos0, pos0 + L) stay untouched."""
+    import sdag_b200._lib as L_
+
+    lib = L_.load()
+    g = torch.Generator(device="cuda").manual_seed(B * L)
+    N, M, S = (H + 2 * Hkv) * D, B * L, pos0 + L + 7
+    x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    bq = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16) if bias else None
+    ang = torch.rand(S, D, generator=g, device="cuda") * 6.28
+    cos, sin = ang.cos().to(torch.bfloat16), ang.sin().to(torch.bfloat16)
+    st = L_.stream_ptr(x.device)
+
+    def buffers():
+        return (torch.full((B, L, H, D), 3.0, dtype=torch.bfloat16, device="cuda"),
+                torch.full((B, Hkv, S, D), 3.0, dtype=torch.bfloat16, device="cuda"), torch.full((B, Hkv, S, D), 3.0, dtype=torch.bfloat16, device="cuda"))
+
+    q1, k1, v1 = buffers()
+    qkv = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    L_.check(lib.llm_gemm(x.data_ptr(), K, W.data_ptr(), L_.ptr(bq), qkv.data_ptr(), N, M, N, K, 0, st), "gemm")
+    L_.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q1.data_ptr(), k1.data_ptr(), v1.data_ptr(), B, L, H, Hkv, D,
+                              k1.stride(0), k1.stride(1), pos0, 0, 0, st), "rope")
+    q2, k2, v2 = buffers()
+    L_.check(lib.llm_gemm_rope(x.data_ptr(), K, W.data_ptr(), L_.ptr(bq), cos.data_ptr(), sin.data_ptr(), q2.data_ptr(), k2.data_ptr(),
+                               v2.data_ptr(), B, L, H, Hkv, D, K, k2.stride(0), k2.stride(1), pos0, st), "gemm_rope")
+    assert torch.equal(q1, q2) and torch.equal(k1, k2) and torch.equal(v1, v2)
+    assert (k2[:, :, :pos0] == 3.0).all() and (k2[:, :, pos0 + L:] == 3.0).all() and (v2[:, :, pos0 + L:] == 3.0).all()
+    assert not (q2 == 3.0).all()
+    # geometry the tiles cannot hold: 3 heads of 128 (odd), head_dim 96
+    assert lib.llm_gemm_rope(x.data_ptr(), K, W.data_ptr(), 0, cos.data_ptr(), sin.data_ptr(), q2.data_ptr(), k2.data_ptr(), v2.data_ptr(),
+                             B, L, 3, 1, 128, K, k2.stride(0), k2.stride(1), 0, st) == 1002
+    assert lib.llm_gemm_rope(x.data_ptr(), K, W.data_ptr(), 0, cos.data_ptr(), sin.data_ptr(), q2.data_ptr(), k2.data_ptr(), v2.data_ptr(),
+                             B, L, H, Hkv, 96, K, k2.stride(0), k2.stride(1), 0, st) == 1002
