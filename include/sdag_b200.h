@@ -189,6 +189,7 @@ int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* st
  * [M, 2*I] intermediate is never written. */
 #define LLM_GEMM_PLAIN 0
 #define LLM_GEMM_SWIGLU 1
+#define LLM_GEMM_GELU 2 /* out = gelu(x W^T + bias), erf form, applied to the bf16-rounded linear output (BertIntermediate) */
 int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
              int N, int K, int epilogue, void* stream);
 /* The prefill's q/k/v projection with apply_rotary_pos_emb and the KV-cache write in the GEMM epilogue (llm_gemm on the

@@ -41,3 +41,19 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.numAttrs = use_pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// x * Phi(x) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf, i.e. <= 0.75e-7 * |x| on the result —
+// three orders of magnitude below a bf16 ulp of the output wherever the output is not itself below 1e-6): one reciprocal,
+// one exponential and five FMAs instead of erff's two divergent polynomial branches, which made this pass compute-bound.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erfc_z = p * t * __expf(-z * z);           // 1 - erf(|x| / sqrt 2)
+  const float phi = x >= 0.f ? 1.f - 0.5f * erfc_z : 0.5f * erfc_z;
+  return x * phi;
+}
+

@@ -5,6 +5,7 @@
 // weight rows (B) per 64-wide k-block in shared memory, the fp32 accumulators (2 x 256 columns, double buffered) live in
 // each CTA's TMEM.  The epilogue converts straight out of TMEM:
 //   LLM_GEMM_PLAIN   out = bf16(acc + bias)
+//   LLM_GEMM_GELU    out = bf16(gelu_erf(bf16(acc + bias)))   (the encoder's BertIntermediate)
 //   LLM_GEMM_SWIGLU  W = [gate; up] rows (N = 2*I): every MMA holds 128 gate rows and the 128 matching up rows, and
 //                    out[M, I] = bf16(bf16(silu(g)) * u) with g, u rounded to bf16 first — the roundings of LlamaMLP with
 //                    a bf16 gate_proj / up_proj — so the [M, 2*I] intermediate never reaches HBM.
@@ -49,7 +50,7 @@ struct Params {
   long long kv_stride_b, kv_stride_h;
   int L, H, Hkv, D, pos0;
 };
-constexpr int LLM_GEMM_ROPE_EPI = 2;  // internal epilogue id of llm_gemm_rope
+constexpr int LLM_GEMM_ROPE_EPI = 100;  // internal epilogue id of llm_gemm_rope
 
 struct Unit {
   int mt, nt;
@@ -67,6 +68,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// plain epilogues: the linear output in bf16, for LLM_GEMM_GELU followed by the erf-GELU of that bf16 value (BertIntermediate)
+template <int EPI>
+__device__ __forceinline__ uint32_t pack_out(float a, float b) {
+  if (EPI == LLM_GEMM_GELU) return pack_bf16x2(gelu_erf(bf_round(a)), gelu_erf(bf_round(b)));
+  return pack_bf16x2(a, b);
+}
 
 // One 32-column bf16 chunk (64 bytes) of this thread's output row.  Lane pairs exchange halves so that every store
 // instruction of the warp writes whole 32-byte sectors (even lane: first 16 bytes, odd lane: the other 16) instead of
@@ -334,7 +341,7 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
-                  o[4 * i + j] = pack_bf16x2(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
+                  o[4 * i + j] = pack_out<EPI>(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
                 }
               }
             } else {  // ragged last tile: 8-column groups (N % 8 == 0), zero bias past the edge
@@ -346,13 +353,13 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
-                  o[4 * i + j] = pack_bf16x2(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
+                  o[4 * i + j] = pack_out<EPI>(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
                 }
               }
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            for (int i = 0; i < 16; ++i) o[i] = pack_out<EPI>(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
           }
           store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
         }
@@ -389,6 +396,8 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_SWIGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     int dev = 0;
@@ -425,6 +434,10 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (epi == LLM_GEMM_ROPE_EPI)
     llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (epi == LLM_GEMM_GELU && p.bias)
+    llm_gemm_kernel<LLM_GEMM_GELU, true><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (epi == LLM_GEMM_GELU)
+    llm_gemm_kernel<LLM_GEMM_GELU, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (p.bias)
     llm_gemm_kernel<LLM_GEMM_PLAIN, true><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   else
@@ -437,7 +450,7 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
 extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
                         int N, int K, int epilogue, void* stream) {
   if (!x || !weight || !out || M < 0 || N <= 0 || K <= 0) return SDAG_ERR_INVALID;
-  if (epilogue != LLM_GEMM_PLAIN && epilogue != LLM_GEMM_SWIGLU) return SDAG_ERR_INVALID;
+  if (epilogue != LLM_GEMM_PLAIN && epilogue != LLM_GEMM_SWIGLU && epilogue != LLM_GEMM_GELU) return SDAG_ERR_INVALID;
   if ((K % 8) || (ldx % 8) || (ldo % 8) || ldx < K) return SDAG_ERR_INVALID;  // 16-byte rows for TMA and the stores
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out)) & 15)
     return SDAG_ERR_INVALID;

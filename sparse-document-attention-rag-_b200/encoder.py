@@ -48,6 +48,9 @@ def full_blockmap(lengths_dev: torch.Tensor, max_L: int):
     return bm
 
 
+PAIR_GEMM_MIN_ROWS = 512  # token rows from which the intermediate projection runs on llm_gemm (fused bias + GELU)
+
+
 def _layernorm(x, residual, weight, bias, eps):
     lib = _lib.load()
     out = torch.empty_like(x)
@@ -119,9 +122,17 @@ class BertEncoderRunner:
             ctx = sdag.sdag_prefill_attention(q, k, v, bm, scaling, ragged=True).view(T, hid)
             del qkv
             x = _layernorm(F.linear(ctx, ly["wo"], ly["bo"]), x, ly["ln1_w"], ly["ln1_b"], ly["eps1"])
-            inter = F.linear(x, ly["wi"], ly["bi"])
             _lib.count_launches(1)
-            _lib.check(lib.enc_gelu(inter.data_ptr(), inter.data_ptr(), inter.numel(), _lib.stream_ptr(dev)), "enc_gelu")
+            wi = ly["wi"]
+            if (PAIR_GEMM_MIN_ROWS <= x.shape[0] and x.is_contiguous() and wi.is_contiguous() and wi.shape[0] % 8 == 0
+                    and wi.shape[1] % 8 == 0):
+                # intermediate projection on the CTA-pair GEMM with bias + GELU in its epilogue (same roundings as the two-step form)
+                inter = torch.empty((x.shape[0], wi.shape[0]), dtype=torch.bfloat16, device=dev)
+                _lib.check(lib.llm_gemm(x.data_ptr(), x.stride(0), wi.data_ptr(), _lib.ptr(ly["bi"]), inter.data_ptr(), wi.shape[0],
+                                        x.shape[0], wi.shape[0], wi.shape[1], 2, _lib.stream_ptr(dev)), "llm_gemm gelu")
+            else:
+                inter = F.linear(x, wi, ly["bi"])
+                _lib.check(lib.enc_gelu(inter.data_ptr(), inter.data_ptr(), inter.numel(), _lib.stream_ptr(dev)), "enc_gelu")
             x = _layernorm(F.linear(inter, ly["wd"], ly["bd"]), x, ly["ln2_w"], ly["ln2_b"], ly["eps2"])
         return x.view(B, L, hid)
 

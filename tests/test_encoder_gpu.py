@@ -133,3 +133,25 @@ def test_ranker_plugs_into_reference_shaped_functions(golden_dir):
     assert sel.shape == (3, index.d)
     nbrs = sdag.compute_doc_knn_for_docs(ranker, docs[:5], 2)
     assert len(nbrs) == 5 and all(len(n) == 2 and i not in n for i, n in enumerate(nbrs))
+
+
+@pytest.mark.parametrize("M,N,K", [(600, 512, 128), (1030, 264, 72)])
+def test_gemm_gelu_epilogue_equals_linear_then_gelu(M, N, K):
+    """llm_gemm with the GELU epilogue (BertIntermediate in one launch) vs llm_gemm -> enc_gelu: bit-identical; vs torch's
+    erf GELU of the fp32 linear output: bf16 tolerance."""
+    import sdag_b200._lib as L
+
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(M)
+    x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    st = L.stream_ptr(x.device)
+    fused = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.llm_gemm(x.data_ptr(), K, W.data_ptr(), b.data_ptr(), fused.data_ptr(), N, M, N, K, 2, st), "gelu epilogue")
+    two = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.llm_gemm(x.data_ptr(), K, W.data_ptr(), b.data_ptr(), two.data_ptr(), N, M, N, K, 0, st), "plain")
+    L.check(lib.enc_gelu(two.data_ptr(), two.data_ptr(), two.numel(), st), "enc_gelu")
+    assert torch.equal(fused, two)
+    ref = torch.nn.functional.gelu(torch.nn.functional.linear(x.float(), W.float(), b.float()).to(torch.bfloat16).float())
+    torch.testing.assert_close(fused.float(), ref, atol=2e-2, rtol=2e-2)
