@@ -215,6 +215,10 @@ int llm_gemv_rope(const void* x, const void* weight, const void* bias, const voi
                   int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0, const int32_t* pos0_dev,
                   int pos0_dev_stride, void* stream);
 
+/* Hint: pull `bytes` at `ptr` (16-byte aligned) into L2.  The generation engine (SDAG.py:191-211 decode loop) launches it
+ * on a side stream for the next layer's o_proj weights while the decode attention kernels run. */
+int llm_prefetch_l2(const void* ptr, size_t bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Paths B1 / B6 — the sentence encoder behind `ranker.encode(...)` (embed_queries, dense.py:44-65;
  * encode_texts_with_ranker, malicious_selection.py:12-34; compute_doc_knn_for_docs, SDAG.py:46-48):
