@@ -375,6 +375,172 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 1) tmem_dealloc_2cta(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide-tile variant (experiment, SDAG_GEMM_WIDE=1; PLAIN without bias and SWIGLU only): a pair tile of 256 token rows x
+// 512 weight rows.  The 128 token rows a CTA loads per k-block feed two MMAs (N = 256 each), so the L2 -> SM bytes per FLOP
+// drop to 0.75x of the 256 x 256 tile.  All 512 TMEM columns hold one accumulator set; the two 256-column halves are handed
+// to the epilogue and back separately, so the next tile's first MMAs (half 0) overlap the draining of half 1.
+// ------------------------------------------------------------------------------------------------
+constexpr int W_STAGES = 4;
+constexpr int W_STAGE_BYTES = A_BYTES + 4 * BQ_BYTES;  // token rows + two MMAs' worth of weight rows (2 x 2 boxes of 64)
+constexpr int W_SMEM_BYTES = W_STAGES * W_STAGE_BYTES + 1024;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+llm_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[W_STAGES], empty[W_STAGES], acc_full, acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  if (tid == 0) {
+    for (int s = 0; s < W_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    mbar_init(&acc_empty[0], 8);
+    mbar_init(&acc_empty[1], 8);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(&tmem_base_s, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const long long n_units = static_cast<long long>(p.n_mt) * p.n_nt;
+  const long long pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    const uint32_t lead_full0 = mapa_shared(smem_u32(&full[0]), 0);
+    uint32_t it = 0;
+    for (long long u = pair; u < n_units; u += n_pairs) {
+      const Unit un = unit_of(u, p);
+      const int m0 = un.mt * 2 * TMH + static_cast<int>(rank) * TMH;
+      int w[4];  // first weight rows of the four 64-row boxes: (MMA 0: box 0, 1), (MMA 1: box 0, 1)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (EPI == LLM_GEMM_SWIGLU) {
+          w[2 * j] = un.nt * 256 + j * 128 + static_cast<int>(rank) * 64;  // gate rows
+          w[2 * j + 1] = p.up_offset + w[2 * j];                           // the matching up rows
+        } else {
+          w[2 * j] = un.nt * 512 + j * 256 + static_cast<int>(rank) * 128;
+          w[2 * j + 1] = w[2 * j] + 64;
+        }
+      }
+      for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+        const int s = it % W_STAGES;
+        mbar_wait(&empty[s], ((it / W_STAGES) & 1) ^ 1);
+        const uint32_t lead_full = lead_full0 + s * 8;
+        uint8_t* sa = smem + s * W_STAGE_BYTES;
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(&full[s], 2 * W_STAGE_BYTES);
+          tma_load_2d_2sm_hint(sa, &tmX, lead_full, kb * KB, m0, p.hint_x);
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            tma_load_2d_2sm_hint(sa + A_BYTES + b * BQ_BYTES, &tmW, lead_full, kb * KB, w[b], p.hint_w);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      const uint32_t idesc = umma_idesc_bf16_f32(2 * TMH, TNP, 0, 0);
+      uint32_t it = 0, ui = 0;
+      for (long long u = pair; u < n_units; u += n_pairs, ++ui) {
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % W_STAGES;
+          mbar_wait(&full[s], (it / W_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * W_STAGE_BYTES);
+          const uint64_t da = umma_smem_desc_sw128(sa, 16, 1024);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (kb == 0) {  // half j of the accumulator must have been drained by the previous tile's epilogue
+              mbar_wait(&acc_empty[j], (ui & 1) ^ 1);
+              tc_fence_after();
+            }
+            const uint64_t db = umma_smem_desc_sw128(sa + A_BYTES + j * 2 * BQ_BYTES, 16, 1024);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < KB / 16; ++kk)
+                umma_ss_2cta(tmem + j * TNP, da + ((kk * 32) >> 4), db + ((kk * 32) >> 4), idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
+            umma_commit_2cta(&empty[s], 3);
+            if (kb == p.kblocks - 1) umma_commit_2cta(&acc_full, 3);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t ui = 0;
+    for (long long u = pair; u < n_units; u += n_pairs, ++ui) {
+      const Unit un = unit_of(u, p);
+      const long long m_even = static_cast<long long>(un.mt) * 2 * TMH + static_cast<long long>(rank) * TMH + quarter * 32 + (lane & ~1);
+      const bool ok_even = m_even < p.M, ok_odd = m_even + 1 < p.M;
+      __nv_bfloat16* row_even = p.out + (ok_even ? m_even : 0) * p.ldo;
+      __nv_bfloat16* row_odd = p.out + (ok_odd ? m_even + 1 : 0) * p.ldo;
+      mbar_wait(&acc_full, ui & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t tacc = tmem + lane_addr + j * TNP;
+        if (EPI == LLM_GEMM_SWIGLU) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t g[32], v[32];
+            const int hc = (c >> 1) * 128 + (c & 1) * 32;
+            tmem_ld_32x32b_x32(tacc + hc, g);
+            tmem_ld_32x32b_x32(tacc + hc + 64, v);
+            tmem_ld_wait();
+            const int col0 = un.nt * 256 + j * 128 + (c >> 1) * 64 + (c & 1) * 32;
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float g0 = bf_round(__uint_as_float(g[2 * i])), g1 = bf_round(__uint_as_float(g[2 * i + 1]));
+              const float u0 = bf_round(__uint_as_float(v[2 * i])), u1 = bf_round(__uint_as_float(v[2 * i + 1]));
+              o[i] = pack_bf16x2(bf_round(g0 / (1.f + __expf(-g0))) * u0, bf_round(g1 / (1.f + __expf(-g1))) * u1);
+            }
+            store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < TNP / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tacc + c * 32, r);
+            tmem_ld_wait();
+            uint32_t o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            store_chunk(row_even, row_odd, ok_even, ok_odd, un.nt * 512 + j * TNP + c * 32, p.n_out, o, lane);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[j]), 0));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem, 512);
+}
+
 // Shared host part: tensor maps, raster parameters, launch.  `p` arrives with the epilogue-specific fields filled in.
 int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, int K, int epi, Params& p, cudaStream_t st) {
   CUtensorMap tmX, tmW;
@@ -406,9 +572,20 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     configured = true;
   }
   const bool swiglu = epi == LLM_GEMM_SWIGLU;
+  static int wide_env = -1;
+  if (wide_env < 0) {
+    const char* e = getenv("SDAG_GEMM_WIDE");  // experiment: 256 x 512 pair tiles
+    wide_env = (e && atoi(e)) ? 1 : 0;
+    if (wide_env) {
+      SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_wide_kernel<LLM_GEMM_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
+      SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_wide_kernel<LLM_GEMM_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
+    }
+  }
+  const bool wide = wide_env && (swiglu || (epi == LLM_GEMM_PLAIN && !p.bias));
   p.M = M;
   p.n_mt = static_cast<int>((M + 2 * TMH - 1) / (2 * TMH));
   p.n_nt = swiglu ? (p.n_out + 127) / 128 : (N + TNP - 1) / TNP;
+  if (wide) p.n_nt = (p.n_nt + 1) / 2;
   p.kblocks = (K + KB - 1) / KB;
   p.up_offset = p.n_out;
   // raster group: as many weight tiles as stay L2-resident (~60 MB, loaded EVICT_LAST) while the token tiles stream past
@@ -420,7 +597,7 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     const char* h = getenv("SDAG_GEMM_HINTS");
     hint_env = h ? atoi(h) : 2;
   }
-  int gn = static_cast<int>((60ll << 20) / (static_cast<long long>(swiglu ? 256 : TNP) * K * 2));
+  int gn = static_cast<int>((60ll << 20) / (static_cast<long long>(swiglu ? 256 : TNP) * (wide ? 2 : 1) * K * 2));
   gn = gn < 2 ? 2 : (gn > GROUP_N ? GROUP_N : gn);
   p.group_n = group_env > 0 ? group_env : gn;
   p.hint_x = (hint_env & 1) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
@@ -428,7 +605,11 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
   const long long units = static_cast<long long>(p.n_mt) * p.n_nt;
   const long long pairs = units < n_sm / 2 ? units : n_sm / 2;
   const unsigned grid = static_cast<unsigned>(2 * pairs);
-  if (swiglu)
+  if (wide && swiglu)
+    llm_gemm_wide_kernel<LLM_GEMM_SWIGLU><<<grid, 192, W_SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (wide)
+    llm_gemm_wide_kernel<LLM_GEMM_PLAIN><<<grid, 192, W_SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (swiglu)
     llm_gemm_kernel<LLM_GEMM_SWIGLU, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (epi == LLM_GEMM_ROPE_EPI && p.bias)
     llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);

@@ -734,3 +734,32 @@ def test_prefill_qkv_gemm_with_rope_epilogue_equals_two_launch_form(B, L, H, Hkv
                              B, L, 3, 1, 128, K, k2.stride(0), k2.stride(1), 0, st) == 1002
     assert lib.llm_gemm_rope(x.data_ptr(), K, W.data_ptr(), 0, cos.data_ptr(), sin.data_ptr(), q2.data_ptr(), k2.data_ptr(), v2.data_ptr(),
                              B, L, H, Hkv, 96, K, k2.stride(0), k2.stride(1), 0, st) == 1002
+
+
+def test_prefill_gemm_wide_tile_variant_in_subprocess():
+    """The 256 x 512 pair-tile variant of llm_gemm (SDAG_GEMM_WIDE=1, read once per process) against torch on a plain and a
+    SwiGLU shape with ragged edges."""
+    import subprocess
+    import sys
+
+    code = r'''
+import torch, sdag_b200._lib as L
+lib = L.load(); st = L.stream_ptr(torch.device("cuda:0"))
+g = torch.Generator(device="cuda").manual_seed(3)
+for M, N, K, epi in ((700, 1288, 200, 0), (1000, 1040, 136, 1), (300, 512, 64, 0)):
+    x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    n_out = N // 2 if epi else N
+    out = torch.full((M + 2, n_out + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.llm_gemm(x.data_ptr(), K, W.data_ptr(), 0, out.data_ptr(), out.stride(0), M, N, K, epi, st), "llm_gemm wide")
+    y = torch.nn.functional.linear(x.float(), W.float()).to(torch.bfloat16)
+    ref = torch.nn.functional.silu(y[:, :n_out]) * y[:, n_out:] if epi else y
+    torch.testing.assert_close(out[:M, :n_out].float(), ref.float(), atol=3e-2, rtol=3e-2)
+    assert (out[:M, :n_out] == ref).float().mean() > 0.9
+    assert (out[M:] == 7.0).all() and (out[:, n_out:] == 7.0).all()
+print("wide ok")
+'''
+    env = dict(os.environ, SDAG_GEMM_WIDE="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "wide ok" in r.stdout, r.stdout + r.stderr
