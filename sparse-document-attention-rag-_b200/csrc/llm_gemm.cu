@@ -384,9 +384,10 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 constexpr int W_STAGES = 4;
 constexpr int W_STAGE_BYTES = A_BYTES + 4 * BQ_BYTES;  // token rows + two MMAs' worth of weight rows (2 x 2 boxes of 64)
 constexpr int W_SMEM_BYTES = W_STAGES * W_STAGE_BYTES + 1024;
+constexpr int W_THREADS = 320;  // producer warp, MMA warp, eight epilogue warps
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W_THREADS, 1)
 llm_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -485,7 +486,10 @@ llm_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     }
   } else {
+    // eight epilogue warps: warps 2-5 drain accumulator half 0, warps 6-9 half 1 (TMEM lane quarter = warp % 4), so both
+    // halves return to the MMA issuer after half the drain time
     const int quarter = warp & 3;
+    const int j = (warp - 2) >> 2;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t ui = 0;
     for (long long u = pair; u < n_units; u += n_pairs, ++ui) {
@@ -496,8 +500,7 @@ llm_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       __nv_bfloat16* row_odd = p.out + (ok_odd ? m_even + 1 : 0) * p.ldo;
       mbar_wait(&acc_full, ui & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < 2; ++j) {
+      {
         const uint32_t tacc = tmem + lane_addr + j * TNP;
         if (EPI == LLM_GEMM_SWIGLU) {
 #pragma unroll 1
@@ -606,9 +609,9 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
   const long long pairs = units < n_sm / 2 ? units : n_sm / 2;
   const unsigned grid = static_cast<unsigned>(2 * pairs);
   if (wide && swiglu)
-    llm_gemm_wide_kernel<LLM_GEMM_SWIGLU><<<grid, 192, W_SMEM_BYTES, st>>>(tmX, tmW, p);
+    llm_gemm_wide_kernel<LLM_GEMM_SWIGLU><<<grid, W_THREADS, W_SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (wide)
-    llm_gemm_wide_kernel<LLM_GEMM_PLAIN><<<grid, 192, W_SMEM_BYTES, st>>>(tmX, tmW, p);
+    llm_gemm_wide_kernel<LLM_GEMM_PLAIN><<<grid, W_THREADS, W_SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (swiglu)
     llm_gemm_kernel<LLM_GEMM_SWIGLU, false><<<grid, 192, SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (epi == LLM_GEMM_ROPE_EPI && p.bias)
