@@ -17,6 +17,10 @@ def test_library_exports_every_declared_symbol():
     header = open(os.path.join(root, "include", "sdag_b200.h")).read()
     declared = set(re.findall(r"^\s*(?:int|size_t|const char\*)\s+(\w+)\s*\(", header, flags=re.M))
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    # the ctypes table and the header agree on the number of parameters of every entry point
+    for name, params in re.findall(r"^\s*(?:int|size_t|const char\*)\s+(\w+)\s*\(([^;]*?)\)\s*;", header, flags=re.M | re.S):
+        n_params = 0 if params.strip() in ("", "void") else params.count(",") + 1
+        assert n_params == len(L.SIGNATURES[name][1]), (name, n_params, len(L.SIGNATURES[name][1]))
     if not os.path.exists(L.LIB_PATH):
         import __graft_entry__
 
