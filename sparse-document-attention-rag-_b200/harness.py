@@ -9,8 +9,8 @@ Mirrored names (same arguments, same output formats):
 * per-pair CSV — ``save_results``                                                      (utils/save_results.py:7-93)
 * per-pair JSON — ``compute_retrieval_ground_truth_stats`` / ``compute_answer_overlap_and_attack_stats`` /
   ``build_pair_metrics`` / ``compute_false_answer_stats_for_results``                  (utils/metrics.py:53-423)
-* the loop — ``build_pair_specs`` / ``compute_max_k_needed`` / ``run_pair_malicious_doc_attack_for_batch`` / ``main``
-  (main.py:109-169, 385-549, 702-858)
+* the loop — ``load_json_config`` / ``apply_json_config`` / ``load_queries_unified`` / ``build_pair_specs`` /
+  ``compute_max_k_needed`` / ``run_pair_malicious_doc_attack_for_batch`` / ``main``  (main.py:44-198, 385-549, 702-858)
 
 Not here (other subsystems of the reference, SURVEY.md §7 "out of scope"): the Discern / RAGDefender defenses (the pool
 passes through as with ``DEFENSE_BACKEND="none"``), the ``doc_corruption`` variant and LLM-written attack content —
@@ -286,6 +286,53 @@ def compute_false_answer_stats_for_results(results: List[Dict[str, Any]]) -> Dic
         tally.update(str(x) for x in (value if isinstance(value, list) else [value]) if x)
     return {"unique_false_answers": len(tally),
             "top_10": [{"false_answer": fa, "count": c} for fa, c in tally.most_common(10)]}
+
+
+# ------------------------------------------------------------------------------------------------------
+# run configuration and query set
+# ------------------------------------------------------------------------------------------------------
+def load_json_config(json_path: Optional[str]) -> Dict[str, Any]:
+    """A JSON object of config overrides (main.py:44-71); a missing path or unreadable file gives ``{}`` with a note."""
+    if not json_path or not os.path.exists(json_path):
+        print(f"Config JSON not found or path is empty: {json_path}")
+        return {}
+    try:
+        with open(json_path, "r", encoding="utf-8") as f:
+            loaded = json.load(f)
+    except Exception as exc:  # same leniency as the reference: a broken file is reported, not raised
+        print(f"Error loading JSON config from {json_path}: {exc}")
+        return {}
+    print(f"Loaded config from JSON: {json_path}")
+    return loaded
+
+
+def apply_json_config(json_config: Optional[Dict[str, Any]]) -> None:
+    """Set every key of ``json_config`` that names an existing knob of ``sdag_b200.config`` (main.py:74-102: unknown keys are
+    reported and skipped, values are taken as they are)."""
+    for key, value in (json_config or {}).items():
+        if hasattr(config, key):
+            setattr(config, key, value)
+            print(f"Config: {key} = {value}")
+        else:
+            print(f"Warning: JSON config key '{key}' does not exist in config module. Skipping.")
+
+
+@dataclass
+class QueryData:
+    """The query set of a run (main.py:172-198): aligned lists, attack presets per query."""
+    query_ids: List[str]
+    questions: List[str]
+    short_answers: List[List[str]]
+    false_answer_groups: Optional[List[List[str]]] = None
+    malicious_doc_groups: Optional[List[List[str]]] = None
+
+
+def load_queries_unified(csv_input_path: str) -> QueryData:
+    """Queries, ground truths and attack presets from the attack CSV (the reference's only implemented source)."""
+    questions, short_answers, false_groups, mal_groups, query_ids = load_from_csv(csv_input_path)
+    print(f"Loaded {len(questions)} queries (grouped by query_id) from CSV: {csv_input_path}")
+    return QueryData(query_ids=query_ids, questions=questions, short_answers=short_answers,
+                     false_answer_groups=false_groups, malicious_doc_groups=mal_groups)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -163,3 +163,30 @@ def test_main_loop_partitions_queries_across_ranks(tmp_path, monkeypatch):
         assert bucket["queries_with_exactly_k_ground_truth_docs_count"] == nq
         assert list(bucket["single_relevant_doc_rank_distribution"]) == ["2"]
     assert h.main(output_base=str(tmp_path / "none"), query_slice=[], **common) == {}
+
+
+def test_json_config_and_query_set(tmp_path, monkeypatch, inputs):
+    import csv as _csv
+
+    from sdag_b200 import config, harness as h
+
+    monkeypatch.setattr(config, "TOP_K", [5])
+    monkeypatch.setattr(config, "DOC_NEIGHBORS_K", 0)
+    cfg = tmp_path / "run.json"
+    cfg.write_text(json.dumps({"TOP_K": [3, 10], "DOC_NEIGHBORS_K": 2, "NOT_A_KNOB": 1}))
+    h.apply_json_config(h.load_json_config(str(cfg)))
+    assert config.TOP_K == [3, 10] and config.DOC_NEIGHBORS_K == 2 and not hasattr(config, "NOT_A_KNOB")
+    assert h.load_json_config(str(tmp_path / "missing.json")) == {} and h.load_json_config(None) == {}
+    (tmp_path / "broken.json").write_text("{not json")
+    assert h.load_json_config(str(tmp_path / "broken.json")) == {}
+    h.apply_json_config({})
+    _, _, csv_rows = inputs
+    path = tmp_path / "attack.csv"
+    with open(path, "w", encoding="utf-8", newline="") as f:
+        w = _csv.writer(f)
+        w.writerow(["query", "query_id", "ground_truth_answers", "false_answer", "malicious_document"])
+        w.writerows(csv_rows)
+    qd = h.load_queries_unified(str(path))
+    assert qd.questions == ["who built it", "when", "where", "what", "why"] and qd.query_ids == ["7", "8", "9", "10", "11"]
+    assert qd.false_answer_groups[0] == ["Rome", "London"] and qd.malicious_doc_groups[1] == ["doc three", "doc seven"]
+    assert h.export_config_dict()["TOP_K"] == [3, 10]
