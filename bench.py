@@ -5,10 +5,13 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (port, bounded sample)
 
-One JSON line on stdout (rank 0).  Primary metric = SDAG prefill tokens/s on BASELINE config 2 (Llama-3-8B
+One JSON line on stdout (rank 0).  Primary metric = SDAG prefill tokens/s on BASELINE configs[1] (Llama-3-8B
 geometry, bf16, random init, TOP_K=10 x 256-token documents, DOC_NEIGHBORS_K=0, L = 2642); the dense top-k QPS
-over the 10M x 1024 corpus rides along under "secondary".  A "step" is one SDAG prefill of a batch of prompts
-(+ one 4096-query search batch for the secondary metric, timed separately).
+over the 10M x 1024 corpus (configs[2]) rides along under "secondary"; configs[4] (long context + decode), configs[3]
+(retrieval + selection + generation, query-parallel) and configs[0] (CPU-scale end to end) under "config5", "config4",
+"config1"; the same prompts through Hugging Face on the same GPU with the reference's dense mask under "same_gpu_hf".
+A "step" is one SDAG prefill of a batch of prompts (+ one 4096-query search batch for the secondary metric, timed
+separately).
 
 Multi-GPU: SDAG prefill is partitioned by independent query batches — no collective, weak scaling; the
 retrieval corpus is sharded by rows over the ranks with one all-gather + merge (fixed 10M rows: strong scaling).
@@ -29,6 +32,7 @@ sys.path.insert(0, ROOT)
 METRIC = "SDAG prefill tok/s (Llama-3-8B, k=10)"
 SECONDARY_METRIC = "dense top-k QPS, 10M x 1024 corpus"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+CONFIG2_LAYOUT = (48, 10, 256, 1, 24)
 
 
 def parse_args():
@@ -44,6 +48,12 @@ def parse_args():
     ap.add_argument("--topk", type=int, default=10)
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hf", action="store_true", help="skip the same-GPU Hugging Face baseline")
+    ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip configs[3] / configs[0] (encoder + retrieval + generation)")
+    ap.add_argument("--config4-queries", type=int, default=0,
+                    help="NQ attack queries for configs[3]; 0 = min(1000, 125 per GPU) so that 8 GPUs run the set as written")
+    ap.add_argument("--pipeline-docs", type=int, default=100_000)
     ap.add_argument("--carg", action="store_true", help="also time plain causal (CARG) prefill through the same kernels")
     return ap.parse_args()
 
@@ -58,6 +68,18 @@ def peaks():
     p = dict(FALLBACK_PEAKS)
     p["_source"] = "fallback (B200_PROFILING.md)"
     return p
+
+
+def measured_traffic(key: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of that kernel
+    (profiles/ncu_traffic.json: {key: {"dram_bytes": ..., "source": "profiles/<summary>.md"}}); None when not captured."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get(key)
+        return (float(rec["dram_bytes"]), rec.get("source")) if rec else (None, None)
+    except (OSError, ValueError, KeyError, TypeError):
+        return None, None
 
 
 class ClockSampler:
@@ -122,6 +144,18 @@ def dist_env():
     return rank, local, world
 
 
+def config2_dict(batch: int, layers: int, world: int) -> dict:
+    """The workload both arms measure (identical in the b200 and the reference line)."""
+    Lp = synthetic_layout(*CONFIG2_LAYOUT)[0]
+    return {
+        "workload": "configs[1]: SDAG prefill, Llama-3-8B geometry (32 layers, 32 q / 8 kv heads, d=128) bf16 random-init, "
+                    "TOP_K=10 x 256-token docs, DOC_NEIGHBORS_K=0, L=2642 (S=48, 1 gap token per doc, 24 QA tokens)",
+        "prompts_per_step_per_gpu": batch, "tokens_per_step": batch * Lp * world, "layers": layers,
+        "partition": "independent query batches per GPU, weights replicated, no collective",
+        "cache": "inputs larger than L2 (16 GB of weights stream through every step)",
+    }
+
+
 # ------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU path (port), bounded sample per step
 # ------------------------------------------------------------------------------------------------------
@@ -131,7 +165,7 @@ def run_reference(args):
         return
     from oracle.cpu_reference import SdagPrefillCpu, flat_ip_cpu
 
-    L, S, spans, qa = synthetic_layout(48, 10, 256, 1, 24)
+    L, S, spans, qa = synthetic_layout(*CONFIG2_LAYOUT)
     job = SdagPrefillCpu(L, S, spans, qa, n_layers=1, vocab_div=8)
     for _ in range(args.warmup):
         job.step()
@@ -145,20 +179,23 @@ def run_reference(args):
     value = L / mean_pp
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * mean_pp, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch * L * max(world, 1) / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: SDAG prefill, Llama-3-8B geometry random-init, TOP_K=10 x 256-token docs, "
-                               "DOC_NEIGHBORS_K=0, L=2642 (S=48, 1 gap token per doc, 24 QA tokens), batch of 1 (reference loop)",
-                   "device": "host CPU", "sampled_step_seconds": wall / max(args.steps, 1)},
-        "cpu_baseline": {"value": value, "unit": "tok/s", "cores": job.threads, "kind": "port", "sample": job.describe(last)},
+        "config": config2_dict(args.batch, args.layers, max(world, 1)),
+        "extrapolated": True,
+        "extrapolation": f"every step runs a bounded sample ({job.n_layers} of {job.full_layers} decoder layers + 1/{job.vocab_div} of the "
+                         f"LM head, one prompt); value and ms_per_step are that sample scaled linearly to the full model and to "
+                         f"{args.batch} prompts per step; measured wall time per sampled step: {wall / max(args.steps, 1):.2f} s",
+        "cpu_baseline": {"value": value, "unit": "tok/s", "cores": job.threads, "kind": "port", "sample": job.describe(last),
+                         "extrapolated": True, "mask_builder": job.mask_source},
         "e2e": {"value": value, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     if not args.no_secondary:
         r = flat_ip_cpu(100_000, 1024, args.queries, args.topk, args.corpus_rows)
-        line["secondary"] = {"metric": SECONDARY_METRIC, "value": r["qps"], "unit": "queries/s",
+        line["secondary"] = {"metric": SECONDARY_METRIC, "value": r["qps"], "unit": "queries/s", "extrapolated": True,
                              "cpu_baseline": {"value": r["qps"], "unit": "queries/s", "cores": r["threads"], "kind": "port",
-                                              "sample": r["sample"]}}
+                                              "sample": r["sample"], "extrapolated": True}}
     print(json.dumps(line), flush=True)
 
 
@@ -184,6 +221,7 @@ def build_llama(layers: int, device):
 
 
 def run_b200(args):
+    os.environ.setdefault("SDAG_STRICT", "1")  # leaving the fast path (HF fallback, eager decode, cuBLAS) is an error here
     import torch
     import torch.distributed as dist
 
@@ -191,6 +229,7 @@ def run_b200(args):
     import sdag_b200.llama_runner as llama_runner
     import sdag_b200.sdag as sdag
     from sdag_b200.retrieval import FlatIPIndex, ShardedFlatIPIndex
+    from tools import workloads
 
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
@@ -201,6 +240,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=device)
     L_.load()
     pk = peaks()
+    peak = pk.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
+    peak_burst = pk.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"])
+    peak_hbm = pk.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"])
 
     def barrier():
         if world > 1:
@@ -215,9 +257,10 @@ def run_b200(args):
         return float(t.item())
 
     # ---------------- SDAG prefill, config 2 ----------------
-    Lp, S, spans, qa = synthetic_layout(48, 10, 256, 1, 24)
+    Lp, S, spans, qa = synthetic_layout(*CONFIG2_LAYOUT)
     B = args.batch
     model = sdag.prepare_model(build_llama(args.layers, device))
+    runner = llama_runner.get_runner(model)
     g = torch.Generator().manual_seed(42 + rank)
     ids_host = torch.randint(0, 128000, (B, Lp), generator=g, dtype=torch.int64).pin_memory()
     layouts = [sdag.SdagLayout(Lp, S, spans, qa) for _ in range(B)]
@@ -225,8 +268,9 @@ def run_b200(args):
     bm = sdag.build_blockmap(layouts, device)
     hdr = bm.header(0)
     assert hdr["status"] == 0 and hdr["pairs"] == 516148, hdr  # P of SURVEY.md §8d for this layout
-    H, D = 32, 128
+    H, Hkv, D = 32, 8, 128
     attn_flops_per_launch = 4.0 * D * hdr["pairs"] * H * B  # algorithmic: 4*D*P*H per prompt per layer
+    attn_bytes_per_launch = float(B) * (2 * H + 2 * Hkv) * Lp * D * 2  # q + out (H heads) + k + v (Hkv heads), bf16, once each
 
     def step_resident(meta):
         logits, _ = sdag.prefill_forward(model, ids_dev, meta)
@@ -236,13 +280,15 @@ def run_b200(args):
         toks, _ = sdag.prefill_batch(model, ids_host, layouts, device)
         return toks
 
-    def timed(fn, steps, warmup, collect_attn=False):
+    gemm_samples = []  # (ms, name, rows, N, K) of the prefill GEMM launches of the last timed run
+
+    def timed(fn, steps, warmup, collect=False):
         for _ in range(warmup):
             fn()
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
-        if collect_attn:
+        if collect:
             sdag._profile_events = []
             llama_runner._gemm_events = []
         launches0 = L_.launch_count
@@ -255,34 +301,44 @@ def run_b200(args):
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
         attn_ms = None
-        if collect_attn:
+        if collect:
             evs, sdag._profile_events = sdag._profile_events, None
             attn_ms = [a.elapsed_time(b) for a, b in evs]
             gevs, llama_runner._gemm_events = llama_runner._gemm_events, None
-            gemm_samples[:] = [(a.elapsed_time(b), rows) for a, b, rows in gevs]
+            gemm_samples[:] = [(a.elapsed_time(b), name, rows, N, K) for a, b, name, rows, N, K in gevs]
         return max_over_ranks(ms), clocks, L_.launch_count - launches0, attn_ms
-
-    gemm_samples = []  # (ms, token rows) of the gate/up llm_gemm launches of the last timed run
 
     def bad_clocks(c):
         return any(r in c.get("reasons", []) for r in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"))
 
-    ms, clocks, launches, attn_ms = timed(lambda: step_resident(bm), args.steps, args.warmup, collect_attn=True)
+    ms, clocks, launches, attn_ms = timed(lambda: step_resident(bm), args.steps, args.warmup, collect=True)
     remeasured = False
     if bad_clocks(clocks):
-        ms, clocks, launches, attn_ms = timed(lambda: step_resident(bm), args.steps, max(args.warmup, 3), collect_attn=True)
+        ms, clocks, launches, attn_ms = timed(lambda: step_resident(bm), args.steps, max(args.warmup, 3), collect=True)
         remeasured = True
     tokens_per_step = B * Lp * world
     value = tokens_per_step * args.steps / (ms / 1000.0)
+    step_ms = ms / args.steps
     attn_avg_ms = sum(attn_ms) / len(attn_ms)
-    achieved = attn_flops_per_launch / (attn_avg_ms / 1000.0) / 1e12
-    peak = pk.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"])
 
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, args.warmup)
     e2e_value = tokens_per_step * args.steps / (ms_e2e / 1000.0)
 
-    # the same kernel on unmasked (dense causal) tiles: north_star's ">= 60 % of dense bf16 tensor peak on the unmasked
-    # tiles" — 4 prompts x 8192 tokens, 32 heads, inputs (403 MB of q/k/v/out) larger than L2, CUDA events on the stream
+    # every projection of the step by CUDA events (on the launching stream, inside the timed region above)
+    projections = {}
+    for name in sorted({s[1] for s in gemm_samples}):
+        sel = [s for s in gemm_samples if s[1] == name and s[2] >= 512]  # full-size launches (the last layer runs on B rows)
+        if not sel:
+            continue
+        p_ms = sum(s[0] for s in sel) / len(sel)
+        p_fl = sum(2.0 * s[2] * s[3] * s[4] for s in sel) / len(sel)
+        projections[name] = {"launch_ms": p_ms, "flops_per_launch": p_fl, "achieved": p_fl / (p_ms / 1000.0) / 1e12,
+                             "frac": p_fl / (p_ms / 1000.0) / 1e12 / peak, "launches_per_step": len(sel) / args.steps,
+                             "share_of_step": p_ms * len(sel) / args.steps / step_ms}
+    dom_name = max(projections, key=lambda n: projections[n]["share_of_step"]) if projections else None
+
+    # the same attention kernel on unmasked (dense causal) tiles: north_star's ">= 60 % of dense bf16 tensor peak on the
+    # unmasked tiles" — 4 prompts x 8192 tokens, 32 heads, inputs (403 MB of q/k/v/out) larger than L2, CUDA events
     def dense_tiles_rate():
         Ld, Bd = 8192, 4
         gq = torch.Generator(device=device).manual_seed(1)
@@ -302,62 +358,82 @@ def run_b200(args):
         torch.cuda.synchronize()
         ms_d = a.elapsed_time(b) / 10
         fl = 4.0 * D * pairs * H * Bd
-        return {"workload": "dense causal, 4 x 8192 tokens, 32 q / 8 kv heads, d=128 (no masked tiles to skip)",
+        return {"workload": "dense causal, 4 x 8192 tokens, 32 q / 8 kv heads, d=128 (no masked tiles to skip)", "bound": "tensor",
                 "launch_ms": ms_d, "flops_per_launch": fl, "achieved": fl / (ms_d / 1000.0) / 1e12, "peak": peak,
-                "unit": "TFLOP/s", "frac": fl / (ms_d / 1000.0) / 1e12 / peak}
+                "unit": "TFLOP/s", "frac": fl / (ms_d / 1000.0) / 1e12 / peak, "frac_of_burst_peak": fl / (ms_d / 1000.0) / 1e12 / peak_burst}
 
     dense_tiles = dense_tiles_rate()
-
-    # the launch that takes the largest share of the step (ncu launch list: ~50 %): the gate/up projection with the
-    # SwiGLU epilogue on this repo's CTA-pair GEMM, timed live with CUDA events inside the timed region above
-    step_dominant = None
-    if gemm_samples:
-        inter, hid = model.config.intermediate_size, model.config.hidden_size
-        g_ms = sum(m for m, _ in gemm_samples) / len(gemm_samples)
-        g_fl = sum(2.0 * r * 2 * inter * hid for _, r in gemm_samples) / len(gemm_samples)
-        step_dominant = {"kernel": "llm_gemm_kernel<SWIGLU> (gate/up projection + SwiGLU epilogue, tcgen05 cta_group::2)",
-                         "bound": "tensor", "launch_ms": g_ms, "flops_per_launch": g_fl,
-                         "achieved": g_fl / (g_ms / 1000.0) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                         "frac": g_fl / (g_ms / 1000.0) / 1e12 / peak,
-                         "share_of_step": g_ms * len(gemm_samples) / args.steps / (ms / args.steps)}
 
     carg = None
     if args.carg:
         ms_c, _, _, _ = timed(lambda: step_resident(None), args.steps, args.warmup)
         carg = tokens_per_step * args.steps / (ms_c / 1000.0)
 
+    # the attention launch of this workload: 156 FLOP per byte is below the ridge (208), so HBM is the binding roof
+    attn_traffic, attn_traffic_src = measured_traffic(f"sdag_prefill_cfg2_b{B}")
+    attn_gbs = attn_bytes_per_launch / (attn_avg_ms / 1000.0) / 1e9
+    attn_tf = attn_flops_per_launch / (attn_avg_ms / 1000.0) / 1e12
+    sdag_attention = {"kernel": "sdag_prefill_kernel<128> (+ v_colsum, v_mean) per layer launch", "bound": "hbm",
+                      "achieved": attn_gbs, "peak": peak_hbm, "unit": "GB/s", "frac": attn_gbs / peak_hbm,
+                      "bytes_per_launch": attn_bytes_per_launch, "traffic": attn_traffic, "traffic_source": attn_traffic_src,
+                      "launch_ms": attn_avg_ms, "share_of_step": attn_avg_ms * len(attn_ms) / args.steps / step_ms,
+                      "tensor": {"flops_per_launch": attn_flops_per_launch, "achieved": attn_tf, "peak": peak, "unit": "TFLOP/s",
+                                 "frac": attn_tf / peak},
+                      "note": "4*D*P*H*B FLOP over (2H + 2Hkv)*L*D*2*B bytes = 156 FLOP/B < ridge 208: HBM-bound on this layout"}
+    if dom_name is not None:
+        dom = projections[dom_name]
+        dom_traffic, dom_traffic_src = measured_traffic(f"llm_gemm_{dom_name}")
+        roofline = {"bound": "tensor", "achieved": dom["achieved"], "peak": peak, "unit": "TFLOP/s", "frac": dom["frac"],
+                    "traffic": dom_traffic, "traffic_source": dom_traffic_src,
+                    "kernel": f"llm_gemm ({dom_name}; tcgen05 cta_group::2) — the launch with the largest share of the step",
+                    "launch_ms": dom["launch_ms"], "flops_per_launch": dom["flops_per_launch"], "share_of_step": dom["share_of_step"],
+                    "frac_of_burst_peak": dom["achieved"] / peak_burst}
+    else:
+        roofline = dict(sdag_attention)
+    roofline.update({"peak_source": pk["_source"] + ", bf16 sustained (burst %.1f) / HBM %.1f GB/s" % (peak_burst, peak_hbm),
+                     "sdag_attention": sdag_attention, "unmasked_tiles": dense_tiles, "projections": projections})
+
+    cfg = config2_dict(B, args.layers, world)  # identical to the reference arm's
     line = {
         "metric": METRIC, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {
-            "workload": "configs[1]: SDAG prefill, Llama-3-8B geometry (32 layers, 32 q / 8 kv heads, d=128) bf16 random-init, "
-                        "TOP_K=10 x 256-token docs, DOC_NEIGHBORS_K=0, L=2642 (S=48, 1 gap token per doc, 24 QA tokens)",
-            "prompts_per_step_per_gpu": B, "tokens_per_step": tokens_per_step, "layers": args.layers,
-            "partition": "independent query batches per GPU, weights replicated, no collective",
-            "cache": "inputs larger than L2 (16 GB of weights stream through every step)",
-            "linear_layers": "gate/up projection + SwiGLU and q/k/v projection + RoPE + KV write on this repo's CTA-pair tcgen05 GEMM "
-                             "(llm_gemm, llm_gemm_rope); o and down projections on cuBLAS via torch (plain library GEMMs); "
-                             "attention, block map, RMSNorm: this repo's kernels (llama_runner.FusedPrefill)",
-            "remeasured_for_clocks": remeasured,
-        },
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 8 prompts
-                     # (profiles/r01_ncu_sdag_prefill_cfg2.md); algorithmic q+k+v+out bytes are 433 MB
-                     "traffic": 508.5e6 * B / 8 if B == 8 else None,
-                     "kernel": "sdag_prefill_kernel<128> (+ v_colsum, v_mean) per layer launch",
-                     "launch_ms": attn_avg_ms, "flops_per_launch": attn_flops_per_launch,
-                     "peak_source": pk["_source"] + ", bf16 sustained", "unmasked_tiles": dense_tiles,
-                     "step_dominant_kernel": step_dominant},
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": cfg, "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": int(ids_host.numel() * 8 + B * 28 * 4),
-                "d2h_bytes_per_step": B * 8, "api": "sdag_b200.sdag.prefill_batch (pinned host ids -> first tokens on host)"},
+                "d2h_bytes_per_step": B * 8 + B * 4,
+                "api": "sdag_b200.sdag.prefill_batch (pinned host ids -> first tokens on host; block-map status words read back)"},
         "gpu_launches": launches, "clocks": clocks,
+        "path": runner.path if runner is not None else "Hugging Face forward + sdag_b200 attention hook",
+        "remeasured_for_clocks": remeasured,
     }
     if carg is not None:
         line["carg_tok_s"] = carg
 
+    # ---------------- the fair "before": Hugging Face on the same GPU with the reference's dense mask ----------------
+    if not args.no_hf:
+        hf = workloads.same_gpu_hf(model, ids_dev, (Lp, S, spans, qa), prompts=min(4, B))
+        hf["speedup_vs_sdpa"] = value / world / hf["sdpa_tok_s"]
+        hf["speedup_vs_eager"] = value / world / hf["eager_tok_s"]
+        hf["note"] = "per-GPU tok/s of this repo's path divided by HF tok/s on the same GPU, same ids, same 32-layer weights"
+        line["same_gpu_hf"] = hf
+
+    # ---------------- config 5: 32k-token prompt with neighbours, prefill + decode ----------------
+    if not args.no_config5 and args.layers == 32:
+        line["config5"] = workloads.config5(model, device, 128, peak, peak_hbm)
+        if runner is not None:
+            runner.__dict__.pop("_ctx", None)  # drop the 32k decode context (KV cache) before the corpus is generated
+
+    # ---------------- configs 4 and 1: encoder + retrieval + selection + generation, query-parallel ----------------
+    if not args.no_pipeline and args.layers == 32:
+        pipe = workloads.Pipeline(device, rank, world, n_docs=args.pipeline_docs)
+        n_q = args.config4_queries or min(1000, 125 * world)
+        line["config4"] = workloads.config4(pipe, model, n_q)
+        if runner is not None:
+            runner.__dict__.pop("_ctx", None)
+        line["config1"] = workloads.config1(pipe, device)
+        del pipe
+
     # free the model before the retrieval corpus is generated
-    del model
+    del model, runner
     torch.cuda.empty_cache()
 
     # ---------------- dense top-k, config 3 ----------------
@@ -388,8 +464,11 @@ def run_b200(args):
         est_ms = max_over_ranks(max(p0.elapsed_time(p1), 0.05))
         s_steps = int(max(3, min(args.steps, 10), min(200, -(-600.0 // est_ms))))
 
+        timed_out = {}
+
         def search_resident():
-            return index.search_device(xq_dev, k)
+            timed_out["s"], timed_out["i"] = index.search_device(xq_dev, k)
+            return timed_out["s"]
 
         def search_e2e():
             s, i = index.search_device(xq_host.to(device, non_blocking=True), k)
@@ -402,11 +481,12 @@ def run_b200(args):
         ach = flops / (ms_s / s_steps / 1000.0) / 1e12
         stats = index.local.last_stats.cpu().tolist()
 
-        # full-size parity: 8 sampled queries brute-forced in fp32 over this rank's whole shard (plain torch, chunked),
-        # against the kernel path's local top-k — ids must match (exact ties aside), scores to 1e-5 relative
-        def full_size_check(n_check=8):
+        # Full-size parity ON WHAT WAS TIMED: sampled rows of the output of the last timed Q-query search (the CTA-pair
+        # kernel ip_gemm_filter_kernel_2cta whenever Q >= 256) against an fp32 brute force over the whole corpus in plain
+        # torch (chunked; per shard, then all-gathered and merged by (score desc, id asc) when the corpus is sharded):
+        # ids must match (fp32 near-ties aside), scores to 1e-5 relative.
+        def full_size_check(n_check=16):
             sel = torch.linspace(0, Q - 1, n_check, device=device).long()
-            s_k, i_k = index.local.search_device(xq_dev[sel], k)
             best_s = torch.full((n_check, k), -float("inf"), device=device)
             best_i = torch.full((n_check, k), -1, dtype=torch.int64, device=device)
             for r0 in range(0, n_local, 1 << 20):
@@ -415,11 +495,22 @@ def run_b200(args):
                 cs, ci = torch.cat([best_s, sc], dim=1).topk(k, dim=1)
                 ids = torch.cat([best_i, torch.arange(r0, r1, device=device).expand(n_check, -1) + lo], dim=1)
                 best_s, best_i = cs, ids.gather(1, ci)
+            if world > 1:
+                gs = [torch.empty_like(best_s) for _ in range(world)]
+                gi = [torch.empty_like(best_i) for _ in range(world)]
+                dist.all_gather(gs, best_s)
+                dist.all_gather(gi, best_i)
+                cat_s, cat_i = torch.cat(gs, dim=1), torch.cat(gi, dim=1)
+                order = torch.argsort(cat_i, dim=1, stable=True)  # id ascending first, then a stable sort by score descending
+                cat_s, cat_i = cat_s.gather(1, order), cat_i.gather(1, order)
+                order = torch.argsort(cat_s, dim=1, descending=True, stable=True)[:, :k]
+                best_s, best_i = cat_s.gather(1, order), cat_i.gather(1, order)
+            s_k, i_k = timed_out["s"][sel], timed_out["i"][sel]
             same = (best_i == i_k)
             rel = ((best_s - s_k).abs() / best_s.abs().clamp(min=1e-12)).max()
-            # a mismatching id is acceptable only where the two scores tie to fp32 summation-order noise
             tie_ok = ((best_s - s_k).abs() <= 2e-6 * best_s.abs()) | same
-            return {"queries": n_check, "rows": n_local, "ids_equal_frac": float(same.float().mean()),
+            return {"checked": "rows of the timed search output", "queries": n_check, "timed_batch_queries": Q,
+                    "kernel": "2cta" if Q > 128 else "1cta", "corpus_rows": N, "ids_equal_frac": float(same.float().mean()),
                     "all_ids_equal_or_tied": bool(tie_ok.all()), "max_rel_score_err": float(rel)}
 
         parity = full_size_check()
@@ -433,7 +524,9 @@ def run_b200(args):
             "config": {"workload": f"configs[2]: {N} x {d} fp32 synthetic corpus (unit Gaussian rows) + bf16 shadow, "
                                    f"{Q}-query batch, k={k}, rows sharded over {world} GPU(s)",
                        "candidates_per_query": stats[1] / Q, "overflow_queries": stats[0]},
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "traffic": measured_traffic("ip_gemm_filter_2cta")[0],
+                         "frac_of_burst_peak": ach / peak_burst,
                          "kernel": "ip_gemm_filter_kernel_2cta (whole ip_search timed)",
                          "note": "peak is the cuBLAS bf16 figure measured on this pool; the CTA-pair kernel can exceed it (nominal dense bf16 2250)", "peak_source": pk["_source"] + ", bf16 sustained"},
             "e2e": {"value": Q * s_steps / (ms_se / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4,
@@ -443,16 +536,19 @@ def run_b200(args):
         del index, x
         torch.cuda.empty_cache()
 
+    line["fallbacks"] = dict(L_.fallbacks)
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_reference import flat_ip_cpu, sdag_prefill_cpu
 
         r = sdag_prefill_cpu(Lp, S, spans, qa, n_layers=1, vocab_div=8)
-        line["cpu_baseline"] = {"value": r["tok_per_s"], "unit": "tok/s", "cores": r["threads"], "kind": "port", "sample": r["sample"]}
+        line["cpu_baseline"] = {"value": r["tok_per_s"], "unit": "tok/s", "cores": r["threads"], "kind": "port", "sample": r["sample"],
+                                "extrapolated": True, "mask_builder": r["mask_builder"]}
         if "secondary" in line:
             r2 = flat_ip_cpu(100_000, 1024, args.queries, args.topk, args.corpus_rows)
             line["secondary"]["cpu_baseline"] = {"value": r2["qps"], "unit": "queries/s", "cores": r2["threads"], "kind": "port",
-                                                 "sample": r2["sample"]}
+                                                 "sample": r2["sample"], "extrapolated": True}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

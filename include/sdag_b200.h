@@ -144,6 +144,13 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
 /* Merge G per-shard results [G,Q,k] (e.g. after ncclAllGather) into the global top-k, same order. */
 int topk_merge(const float* scores, const int64_t* ids, int G, int Q, int k, float* out_scores,
                int64_t* out_ids, void* stream);
+/* The exchange step of the sharded search with ONE buffer per rank: topk_pack writes the local result as
+ * n = Q*k records of three int32 {score bits, id low word, id high word}; after one ncclAllGather of those records
+ * (rank-major [G,Q,k,3]) topk_merge_packed merges them into the global top-k with topk_merge's order rule (score
+ * descending, then id ascending, padding ids -1 last).  Replaces faiss' single-index heap over the whole corpus,
+ * dense.py:83, when the corpus rows are partitioned over GPUs. */
+int topk_pack(const float* scores, const int64_t* ids, int64_t n, void* records, void* stream);
+int topk_merge_packed(const void* records, int G, int Q, int k, float* out_scores, int64_t* out_ids, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Path B — selector.  Replaces the numeric core of _select_malicious_docs_for_query,
@@ -192,6 +199,13 @@ int llm_swiglu(const void* gate_up, void* out, int64_t rows, int inter, void* st
 #define LLM_GEMM_GELU 2 /* out = gelu(x W^T + bias), erf form, applied to the bf16-rounded linear output (BertIntermediate) */
 int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
              int N, int K, int epilogue, void* stream);
+/* The same GEMM with the residual add of the decoder / encoder layer in its epilogue:
+ * out = bf16(bf16(x W^T + bias) + residual) — `hidden_states = residual + self.o_proj(...)` and
+ * `residual + self.mlp(...)` of LlamaDecoderLayer.forward (HF modeling_llama.py, reached from SDAG.py:175-176), and the
+ * `dense(x) + input_tensor` of BertSelfOutput / BertOutput in the encoder.  residual [M, N] rows ldr elements apart
+ * (ldr % 8 == 0, 16-byte aligned); it may alias `out` (every element is read and written by the same thread). */
+int llm_gemm_residual(const void* x, int64_t ldx, const void* weight, const void* bias, const void* residual,
+                      int64_t ldr, void* out, int64_t ldo, int64_t M, int N, int K, void* stream);
 /* The prefill's q/k/v projection with apply_rotary_pos_emb and the KV-cache write in the GEMM epilogue (llm_gemm on the
  * fused [(H + 2*Hkv)*D, K] q|k|v weight followed by llm_rope_qkv, in one launch; the [B*L, (H+2Hkv)*D] intermediate is
  * never written): x [B*L, K] rows ldx apart, token row b*L + l sits at position pos0 + l; q_out [B, L, H, D]; k_out /

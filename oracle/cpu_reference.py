@@ -23,6 +23,34 @@ import numpy as np
 import torch
 
 
+def reference_mask_builder():
+    """(builder, provenance): the reference's own ``build_blocked_causal_mask_full`` (SDAG.py:68-127), imported unmodified
+    when ``/root/reference`` is present (this container; ``sentence_transformers`` is stubbed — only its name is needed
+    at import, SDAG.py:7); on the GPU box, where the reference cannot travel, the restatement below, which is held to the
+    reference's masks bit for bit by tests/test_oracle_golden.py (``test_cpu_reference_mask_equals_reference_builder``)."""
+    import sys
+    import types
+
+    root = "/root/reference"
+    if os.path.isdir(os.path.join(root, "src", "pipeline")):
+        try:
+            if "sentence_transformers" not in sys.modules:
+                stub = types.ModuleType("sentence_transformers")
+                stub.SentenceTransformer = object
+                sys.modules["sentence_transformers"] = stub
+            if root not in sys.path:
+                sys.path.insert(0, root)
+            from src.pipeline.sparse_attention_RAG.SDAG import build_blocked_causal_mask_full as ref_build
+
+            def build(L, S, spans, qa_start):
+                return ref_build(L, 0, S, list(spans), qa_start, "cpu", None)
+
+            return build, "reference function (SDAG.py:68-127), imported"
+        except Exception:  # any import problem of the reference tree: use the restatement
+            pass
+    return reference_style_mask, "restatement of SDAG.py:104-125 (row-by-row slice writes), pinned to the reference's masks"
+
+
 def reference_style_mask(L: int, S: int, spans: Sequence[Tuple[int, int]], qa_start: int) -> torch.Tensor:
     """The reference's algorithmic shape: O(L) separate row-slice writes into a dense bool [L, L]."""
     m = torch.zeros(L, L, dtype=torch.bool)
@@ -50,6 +78,7 @@ class SdagPrefillCpu:
 
         self.L, self.S, self.spans, self.qa_start = L, S, spans, qa_start
         self.n_layers, self.vocab_div, self.full_layers = n_layers, vocab_div, full_layers
+        self.build_mask, self.mask_source = reference_mask_builder()
         self.threads = threads or os.cpu_count() or 1
         torch.set_num_threads(self.threads)
         vocab = 128256
@@ -64,7 +93,7 @@ class SdagPrefillCpu:
     def step(self) -> Dict:
         """One sample pass; returns its parts in seconds and the extrapolated per-prompt time."""
         t0 = time.perf_counter()
-        mask = reference_style_mask(self.L, self.S, self.spans, self.qa_start)
+        mask = self.build_mask(self.L, self.S, self.spans, self.qa_start)
         neg = torch.finfo(torch.float32).min
         bias = torch.zeros(self.L, self.L, dtype=torch.float32).masked_fill(~mask, neg)[None, None]
         t_mask = time.perf_counter() - t0
@@ -89,7 +118,7 @@ class SdagPrefillCpu:
 def sdag_prefill_cpu(L: int, S: int, spans, qa_start: int, **kw) -> Dict:
     job = SdagPrefillCpu(L, S, spans, qa_start, **kw)
     r = job.step()
-    r.update(tok_per_s=L / r["seconds_per_prompt"], threads=job.threads, sample=job.describe(r))
+    r.update(tok_per_s=L / r["seconds_per_prompt"], threads=job.threads, sample=job.describe(r), mask_builder=job.mask_source)
     return r
 
 

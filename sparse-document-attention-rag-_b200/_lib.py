@@ -5,6 +5,7 @@ There is no fallback: if the library is missing or a call fails, an exception is
 from __future__ import annotations
 
 import ctypes as C
+import logging
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -44,6 +45,8 @@ SIGNATURES = {
     "ip_search_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ip_search": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "topk_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "topk_pack": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "topk_merge_packed": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "centroid_select": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "doc_knn": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "llm_rmsnorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
@@ -55,6 +58,7 @@ SIGNATURES = {
     "llm_gemv_rope": (_i32, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp,
                               _i32, _vp]),
     "llm_gemm": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
+    "llm_gemm_residual": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp]),
     "sdag_full_blockmap_bytes": (_sz, [_i32]),
     "sdag_build_blockmap_full": (_i32, [_vp, _i32, _i32, _vp, _sz, _vp]),
     "enc_layernorm": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
@@ -96,9 +100,37 @@ def ptr(t) -> int:
 
 
 def stream_ptr(device=None) -> int:
+    """Raw ``cudaStream_t`` of torch's current stream on ``device``.  The library launches on the CUDA *current* device
+    (tensor maps, ``cudaFuncSetAttribute``, the SM count are per device), so the tensor's device is made current here —
+    every launch site fetches its stream through this function right before the call."""
     import torch
 
+    if device is not None:
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is not None and dev.index != torch.cuda.current_device():
+            torch.cuda.set_device(dev)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+# Every place the host code leaves its fast path (fused engine unavailable for a model, CUDA-graph capture failed, ...)
+# reports here: counted, logged once per reason, and an error under SDAG_STRICT=1 — so a 3x performance cliff cannot
+# pass silently (bench.py prints the table; tests/bench run strict).
+fallbacks: dict = {}
+_log = logging.getLogger("sdag_b200")
+
+
+def strict() -> bool:
+    return os.environ.get("SDAG_STRICT", "") == "1"
+
+
+def note_fallback(where: str, reason: str, exc: BaseException = None) -> None:
+    key = f"{where}: {reason}"
+    first = key not in fallbacks
+    fallbacks[key] = fallbacks.get(key, 0) + 1
+    if strict():
+        raise SdagB200Error(f"SDAG_STRICT=1 and the fast path was left at {key}") from exc
+    if first:
+        _log.warning("sdag_b200 fallback at %s%s", key, f" ({exc!r})" if exc is not None else "")
 
 
 # kernels launched through this binding since import (bench.py reports it as "gpu_launches")

@@ -14,6 +14,27 @@
     if (e__ != cudaSuccess) return static_cast<int>(e__); \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are per-device facts: launch sites keep a small table
+// indexed by device ordinal instead of a process-wide "configured" flag, so a second GPU used from the same process gets its
+// own opt-in.  device_slot() returns the current device's ordinal (callers make the tensor's device current).
+constexpr int SDAG_MAX_DEVICES = 64;
+inline int device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= SDAG_MAX_DEVICES) return -1;
+  return dev;
+}
+inline int device_sm_count() {
+  static int n_sm[SDAG_MAX_DEVICES] = {};
+  const int dev = device_slot();
+  if (dev < 0) return 148;
+  if (n_sm[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    n_sm[dev] = n;
+  }
+  return n_sm[dev];
+}
+
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start
 // while its predecessor in the stream is still draining; it must call pdl_wait() before touching anything the
 // predecessor wrote (or still reads).  pdl_trigger() in the predecessor lets the dependent grid be scheduled as soon as

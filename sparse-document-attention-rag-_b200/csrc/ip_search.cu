@@ -36,6 +36,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024;
 constexpr int SORT_MAX = 2048;
 constexpr int SCAN_SLICES = 32;
+constexpr long long IP_FAST_GROWTH_ROWS = 65536;  // the swept prefix grows x4 per epoch below this many rows, x2 above
 constexpr int SELECT_MAX_K = 32;  // tighten: k-th best by k max-extraction rounds up to this k, bitonic sort above
 // |bf16(x).bf16(q) - x.q| <= (2u + u^2) |x||q| with u = 2^-8, plus fp32 accumulation slack
 constexpr float ERR_COEF = 0.0078125f + 0.00048828125f;
@@ -494,6 +495,102 @@ tighten_kernel(SearchState st, int k, int force_cnt, const float* __restrict__ m
   }
 }
 
+// Same step for the epochs after the first, one WARP per query: by then a list holds a few dozen survivors, and a
+// 256-thread block per query with 2k block-wide barriers (the kernel above) spends ~60 us per epoch on 4096 queries —
+// the fixed cost that limits the sharded search.  Up to 256 candidates are held in registers (8 per lane); the k-th best
+// comes from k rounds of a warp-wide 64-bit max over the keys below the previous round's, survivors are compacted with
+// ballots.  Longer lists (rare: clustered data) take the same rounds straight from global memory, chunk by chunk.
+constexpr int TW_PER_LANE = 8;
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+    v = other > v ? other : v;
+  }
+  return v;
+}
+__global__ void __launch_bounds__(256)
+tighten_warp_kernel(SearchState st, int Q, int k, const float* __restrict__ max_norm) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  int n = st.cnt[q];
+  if (n > st.cap) {
+    if (lane == 0) st.overflow[q] = 1;
+    n = st.cap;
+  }
+  Cand* cq = st.cand + static_cast<long long>(q) * st.cap;
+  float thr = st.thr[q];
+  auto key_of = [](const Cand c) {
+    return (static_cast<unsigned long long>(orderable(c.score)) << 32) | static_cast<uint32_t>(c.row);
+  };
+  if (n <= 32 * TW_PER_LANE) {
+    unsigned long long keys[TW_PER_LANE];
+#pragma unroll
+    for (int j = 0; j < TW_PER_LANE; ++j) {
+      const int i = lane + 32 * j;
+      keys[j] = i < n ? key_of(cq[i]) : 0ull;
+    }
+    if (n >= k) {
+      unsigned long long below = ~0ull;
+      for (int r = 0; r < k; ++r) {  // keys are distinct: the r-th largest is the largest key below the (r-1)-th largest
+        unsigned long long loc = 0;
+#pragma unroll
+        for (int j = 0; j < TW_PER_LANE; ++j)
+          if (keys[j] < below && keys[j] > loc) loc = keys[j];
+        below = warp_max_u64(loc);
+      }
+      const float kth = unorderable(static_cast<uint32_t>(below >> 32));
+      thr = fmaxf(thr, kth - 2.f * ERR_COEF * st.qnorm[q] * (*max_norm));
+    }
+    int keep = 0;
+    __syncwarp();  // every lane holds its candidates in registers before the list is rewritten in place
+#pragma unroll
+    for (int j = 0; j < TW_PER_LANE; ++j) {
+      const float s = unorderable(static_cast<uint32_t>(keys[j] >> 32));
+      const bool ok = (lane + 32 * j) < n && s >= thr;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) cq[keep + __popc(m & ((1u << lane) - 1u))] = Cand{s, static_cast<int32_t>(keys[j] & 0xffffffffu)};
+      keep += __popc(m);
+    }
+    if (lane == 0) {
+      st.thr[q] = thr;
+      st.cnt[q] = keep;
+    }
+    return;
+  }
+  // long list: the same selection with the keys re-read from global memory (L2) in every round
+  if (n >= k) {
+    unsigned long long below = ~0ull;
+    for (int r = 0; r < k; ++r) {
+      unsigned long long loc = 0;
+      for (int i = lane; i < n; i += 32) {
+        const unsigned long long key = key_of(cq[i]);
+        if (key < below && key > loc) loc = key;
+      }
+      below = warp_max_u64(loc);
+    }
+    const float kth = unorderable(static_cast<uint32_t>(below >> 32));
+    thr = fmaxf(thr, kth - 2.f * ERR_COEF * st.qnorm[q] * (*max_norm));
+  }
+  int keep = 0;
+  for (int base = 0; base < n; base += 32) {  // in-place compaction: chunk c is read whole before its survivors are
+    const int i = base + lane;                // written, and they land at or below the chunk's own first index
+    Cand c = Cand{-INFINITY, -1};
+    if (i < n) c = cq[i];
+    const bool ok = i < n && c.score >= thr;
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    __syncwarp();
+    if (ok) cq[keep + __popc(m & ((1u << lane) - 1u))] = c;
+    keep += __popc(m);
+    __syncwarp();
+  }
+  if (lane == 0) {
+    st.thr[q] = thr;
+    st.cnt[q] = keep;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // exact fp32 dot of one corpus row with the query held in shared memory (one warp)
 // ------------------------------------------------------------------------------------------------
@@ -685,6 +782,60 @@ topk_merge_kernel(const float* __restrict__ scores, const long long* __restrict_
   }
 }
 
+// Local results as 12-byte records {f32 score bits, id lo, id hi} so that the shards exchange ONE buffer (one all-gather
+// instead of one for the scores and one for the ids), and the merge of the gathered records [G][Q][k].
+__global__ void __launch_bounds__(256)
+topk_pack_kernel(const float* __restrict__ scores, const long long* __restrict__ ids, long long n, int32_t* __restrict__ out) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const long long id = ids[i];
+  out[3 * i] = __float_as_int(scores[i]);
+  out[3 * i + 1] = static_cast<int32_t>(id & 0xffffffffll);
+  out[3 * i + 2] = static_cast<int32_t>(id >> 32);
+}
+
+__global__ void __launch_bounds__(128)
+topk_merge_packed_kernel(const int32_t* __restrict__ rec, int G, int Q, int k, float* __restrict__ out_scores,
+                         long long* __restrict__ out_ids) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  const int n = G * k;
+  float* s = reinterpret_cast<float*>(dyn);
+  long long* id = reinterpret_cast<long long*>(dyn + ((n * 4 + 15) & ~15));
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int g = i / k, j = i % k;
+    const int32_t* r = rec + ((static_cast<long long>(g) * Q + q) * k + j) * 3;
+    s[i] = __int_as_float(r[0]);
+    id[i] = static_cast<long long>(static_cast<uint32_t>(r[1])) | (static_cast<long long>(r[2]) << 32);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float si = s[i];
+    const long long ii = id[i];
+    const bool pad_i = ii < 0;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {  // same order rule as topk_merge_kernel: real before padding, score desc, id asc
+      const float sj = s[j];
+      const long long ij = id[j];
+      const bool pad_j = ij < 0;
+      bool better;
+      if (pad_i != pad_j)
+        better = pad_i;
+      else if (sj != si)
+        better = sj > si;
+      else if (ij != ii)
+        better = ij < ii;
+      else
+        better = j < i;
+      rank += better;
+    }
+    if (rank < k) {
+      out_scores[static_cast<long long>(q) * k + rank] = pad_i ? -FLT_MAX : si;
+      out_ids[static_cast<long long>(q) * k + rank] = pad_i ? -1 : ii;
+    }
+  }
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WorkspaceLayout {
@@ -772,22 +923,23 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
       uint32_t box[2] = {KB, TN / 2};
       if (make_tmap(&tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, corpus_bf16, dims, str, box)) return SDAG_ERR_DRIVER;
     }
-    static bool configured = false;
-    static int n_sm = 148;
-    if (!configured) {
+    static bool configured[SDAG_MAX_DEVICES] = {};
+    const int dev = device_slot();
+    if (dev < 0) return SDAG_ERR_UNSUPPORTED;
+    if (!configured[dev]) {
       SDAG_CUDA_TRY(cudaFuncSetAttribute(ip_gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
       SDAG_CUDA_TRY(cudaFuncSetAttribute(ip_gemm_filter_kernel_2cta, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
-      int dev = 0;
-      SDAG_CUDA_TRY(cudaGetDevice(&dev));
-      SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-      configured = true;
+      configured[dev] = true;
     }
+    const int n_sm = device_sm_count();
     GemmParams gp;
     gp.st = state;
     gp.Q = Q;
     gp.n_qt = w.q_pad / TM;
     gp.kblocks = d / KB;
-    // first epoch: positional dump of up to cap/2 rows (multiple of TN), then doubling spans
+    // first epoch: positional dump of up to cap/2 rows (multiple of TN); then the swept prefix grows x4 per epoch while
+    // the epochs are too small to fill the machine (below 64 k rows the launch + tighten cost dominates, and a looser
+    // threshold only means ~100 survivors per query), x2 afterwards (survivors make the filter epilogue take its slow path)
     long long begin = 0;
     long long span = cand_cap / 2 / TN * TN;
     if (span < TN) span = TN;
@@ -809,11 +961,14 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
         const int grid = static_cast<int>(units < n_sm ? units : n_sm);
         ip_gemm_filter_kernel<<<grid, 192, GEMM_SMEM, st>>>(tmA, tmB, gp);
       }
-      tighten_kernel<<<Q, 256, 0, st>>>(state, k, first ? static_cast<int>(end - begin) : -1, max_norm_dev);
+      if (first)  // every list holds the whole dumped span: block per query
+        tighten_kernel<<<Q, 256, 0, st>>>(state, k, static_cast<int>(end - begin), max_norm_dev);
+      else        // a few dozen survivors per list: warp per query
+        tighten_warp_kernel<<<(Q + 7) / 8, 256, 0, st>>>(state, Q, k, max_norm_dev);
       SDAG_CUDA_TRY(cudaGetLastError());
-      if (!first) span *= 2;
       first = false;
       begin = end;
+      span = begin < IP_FAST_GROWTH_ROWS ? 3 * begin : begin;
       ++epochs;
     }
     (void)epochs;
@@ -824,6 +979,24 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
                                                                  static_cast<const __nv_bfloat16*>(corpus_bf16), d, k,
                                                                  id_offset, out_scores, reinterpret_cast<long long*>(out_ids),
                                                                  stats_dev);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int topk_pack(const float* scores, const int64_t* ids, int64_t n, void* records, void* stream) {
+  if (!scores || !ids || !records || n < 0) return SDAG_ERR_INVALID;
+  if (n == 0) return SDAG_OK;
+  topk_pack_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, reinterpret_cast<const long long*>(ids), n, static_cast<int32_t*>(records));
+  return static_cast<int>(cudaGetLastError());
+}
+
+int topk_merge_packed(const void* records, int G, int Q, int k, float* out_scores, int64_t* out_ids, void* stream) {
+  if (!records || !out_scores || !out_ids || G <= 0 || Q <= 0 || k <= 0) return SDAG_ERR_INVALID;
+  const size_t n = static_cast<size_t>(G) * k;
+  const size_t smem = ((n * 4 + 15) & ~size_t(15)) + n * 8;
+  if (smem > 48 * 1024) return SDAG_ERR_UNSUPPORTED;
+  topk_merge_packed_kernel<<<Q, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const int32_t*>(records), G, Q, k, out_scores, reinterpret_cast<long long*>(out_ids));
   return static_cast<int>(cudaGetLastError());
 }
 

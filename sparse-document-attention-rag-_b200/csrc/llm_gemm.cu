@@ -32,6 +32,8 @@ constexpr int GROUP_N = 16;  // most weight tiles per raster group (one wave of 
 
 struct Params {
   const __nv_bfloat16* bias;  // [N] or null
+  const __nv_bfloat16* resid; // [M, ldr] or null (plain epilogue): out = bf16(bf16(acc + bias) + resid); may alias out
+  long long ldr;
   __nv_bfloat16* out;
   long long ldo;  // elements
   long long M;
@@ -73,6 +75,25 @@ template <int EPI>
 __device__ __forceinline__ uint32_t pack_out(float a, float b) {
   if (EPI == LLM_GEMM_GELU) return pack_bf16x2(gelu_erf(bf_round(a)), gelu_erf(bf_round(b)));
   return pack_bf16x2(a, b);
+}
+
+// Residual add of the plain epilogue, on this thread's own row: v <- bf16(bf16(v) + resid[col0 + i]) — the two roundings of
+// `residual + linear(x)` with a bf16 linear output (LlamaDecoderLayer, BertSelfOutput / BertOutput).  64 contiguous bytes per
+// thread; columns past n_out (ragged last tile, N % 8 == 0) are left alone.
+__device__ __forceinline__ void add_residual(float (&v)[32], const __nv_bfloat16* rrow, int col0, int n_out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (col0 + 8 * i + 8 <= n_out) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(rrow + col0 + 8 * i));
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
+        v[8 * i + 2 * j] = bf_round(bf_round(v[8 * i + 2 * j]) + f.x);
+        v[8 * i + 2 * j + 1] = bf_round(bf_round(v[8 * i + 2 * j + 1]) + f.y);
+      }
+    }
+  }
 }
 
 // One 32-column bf16 chunk (64 bytes) of this thread's output row.  Lane pairs exchange halves so that every store
@@ -324,43 +345,36 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
         }
       } else {
+        const long long m_own = m_even + (lane & 1);
+        const __nv_bfloat16* rrow = (p.resid && m_own < p.M) ? p.resid + m_own * p.ldr : nullptr;
 #pragma unroll 1
         for (int c = 0; c < TNP / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tacc + c * 32, r);
           tmem_ld_wait();
           const int col0 = un.nt * TNP + c * 32;
-          uint32_t o[16];
-          if (BIAS) {
-            if (col0 + 32 <= p.n_out) {
-              const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+          float v[32];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint4 bv = __ldg(bp + i);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (BIAS) {  // 8-column groups (N % 8 == 0); nothing is added past the edge of a ragged last tile
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (col0 + 8 * i + 8 <= p.n_out) {
+                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + 8 * i));
                 const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
-                  o[4 * i + j] = pack_out<EPI>(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
-                }
-              }
-            } else {  // ragged last tile: 8-column groups (N % 8 == 0), zero bias past the edge
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                uint4 bv = make_uint4(0u, 0u, 0u, 0u);
-                if (col0 + 8 * i + 8 <= p.n_out) bv = __ldg(reinterpret_cast<const uint4*>(p.bias + col0 + 8 * i));
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 bf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
-                  o[4 * i + j] = pack_out<EPI>(__uint_as_float(r[8 * i + 2 * j]) + bf.x, __uint_as_float(r[8 * i + 2 * j + 1]) + bf.y);
+                  v[8 * i + 2 * j] += bf.x;
+                  v[8 * i + 2 * j + 1] += bf.y;
                 }
               }
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = pack_out<EPI>(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
           }
+          if (rrow) add_residual(v, rrow, col0, p.n_out);
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = pack_out<EPI>(v[2 * i], v[2 * i + 1]);
           store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
         }
       }
@@ -521,15 +535,27 @@ llm_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
           }
         } else {
+          const long long m_own = m_even + (lane & 1);
+          const __nv_bfloat16* rrow = (p.resid && m_own < p.M) ? p.resid + m_own * p.ldr : nullptr;
 #pragma unroll 1
           for (int c = 0; c < TNP / 32; ++c) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(tacc + c * 32, r);
             tmem_ld_wait();
+            const int col0 = un.nt * 512 + j * TNP + c * 32;
             uint32_t o[16];
+            if (rrow) {
+              float v[32];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-            store_chunk(row_even, row_odd, ok_even, ok_odd, un.nt * 512 + j * TNP + c * 32, p.n_out, o, lane);
+              for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+              add_residual(v, rrow, col0, p.n_out);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            }
+            store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
           }
         }
         tc_fence_before();
@@ -559,9 +585,10 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     uint32_t box[2] = {KB, 64};
     if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, weight, dims, str, box)) return SDAG_ERR_DRIVER;
   }
-  static bool configured = false;
-  static int n_sm = 148;
-  if (!configured) {
+  static bool configured[SDAG_MAX_DEVICES] = {};
+  const int dev = device_slot();
+  if (dev < 0) return SDAG_ERR_UNSUPPORTED;
+  if (!configured[dev]) {
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_SWIGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -569,22 +596,22 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    int dev = 0;
-    SDAG_CUDA_TRY(cudaGetDevice(&dev));
-    SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_wide_kernel<LLM_GEMM_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_wide_kernel<LLM_GEMM_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
+    configured[dev] = true;
   }
+  const int n_sm = device_sm_count();
   const bool swiglu = epi == LLM_GEMM_SWIGLU;
-  static int wide_env = -1;
-  if (wide_env < 0) {
-    const char* e = getenv("SDAG_GEMM_WIDE");  // experiment: 256 x 512 pair tiles
-    wide_env = (e && atoi(e)) ? 1 : 0;
-    if (wide_env) {
-      SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_wide_kernel<LLM_GEMM_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
-      SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_wide_kernel<LLM_GEMM_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
-    }
+  // 256 x 512 pair tiles move 0.75x the L2 -> SM bytes per FLOP but cannot double-buffer the accumulator: measured faster
+  // where the main loop is long enough to hide the exposed epilogue (K = 14336 down projection: 1322 -> 1395 TFLOP/s
+  // sustained, cuBLAS 1407) and slower at K = 4096 (o, gate/up).  SDAG_GEMM_WIDE=0 / 1 forces one form (experiments).
+  static int wide_env = -2;
+  if (wide_env == -2) {
+    const char* e = getenv("SDAG_GEMM_WIDE");
+    wide_env = e ? (atoi(e) ? 1 : 0) : -1;
   }
-  const bool wide = wide_env && (swiglu || (epi == LLM_GEMM_PLAIN && !p.bias));
+  const bool wide_ok = swiglu || (epi == LLM_GEMM_PLAIN && !p.bias);
+  const bool wide = wide_ok && (wide_env >= 0 ? wide_env == 1 : (!swiglu && K >= 8192 && M >= 2048));
   p.M = M;
   p.n_mt = static_cast<int>((M + 2 * TMH - 1) / (2 * TMH));
   p.n_nt = swiglu ? (p.n_out + 127) / 128 : (N + TNP - 1) / TNP;
@@ -631,10 +658,12 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
 
 }  // namespace
 
-extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
-                        int N, int K, int epilogue, void* stream) {
+static int llm_gemm_impl(const void* x, int64_t ldx, const void* weight, const void* bias, const void* residual, int64_t ldr,
+                         void* out, int64_t ldo, int64_t M, int N, int K, int epilogue, void* stream) {
   if (!x || !weight || !out || M < 0 || N <= 0 || K <= 0) return SDAG_ERR_INVALID;
   if (epilogue != LLM_GEMM_PLAIN && epilogue != LLM_GEMM_SWIGLU && epilogue != LLM_GEMM_GELU) return SDAG_ERR_INVALID;
+  if (residual && (epilogue != LLM_GEMM_PLAIN || (ldr % 8) || ldr < N || (reinterpret_cast<uintptr_t>(residual) & 15)))
+    return SDAG_ERR_INVALID;
   if ((K % 8) || (ldx % 8) || (ldo % 8) || ldx < K) return SDAG_ERR_INVALID;  // 16-byte rows for TMA and the stores
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out)) & 15)
     return SDAG_ERR_INVALID;
@@ -647,10 +676,23 @@ extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const vo
   if (M > (1ll << 31) - 512) return SDAG_ERR_UNSUPPORTED;
   Params p = {};
   p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.resid = static_cast<const __nv_bfloat16*>(residual);
+  p.ldr = ldr;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.n_out = n_out;
   return run_gemm(x, ldx, weight, M, N, K, epilogue, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int llm_gemm(const void* x, int64_t ldx, const void* weight, const void* bias, void* out, int64_t ldo, int64_t M,
+                        int N, int K, int epilogue, void* stream) {
+  return llm_gemm_impl(x, ldx, weight, bias, nullptr, 0, out, ldo, M, N, K, epilogue, stream);
+}
+
+extern "C" int llm_gemm_residual(const void* x, int64_t ldx, const void* weight, const void* bias, const void* residual,
+                                 int64_t ldr, void* out, int64_t ldo, int64_t M, int N, int K, void* stream) {
+  if (!residual) return SDAG_ERR_INVALID;
+  return llm_gemm_impl(x, ldx, weight, bias, residual, ldr, out, ldo, M, N, K, LLM_GEMM_PLAIN, stream);
 }
 
 extern "C" int llm_gemm_rope(const void* x, int64_t ldx, const void* weight, const void* bias, const void* cos, const void* sin,

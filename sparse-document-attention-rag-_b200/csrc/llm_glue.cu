@@ -163,10 +163,12 @@ int llm_rmsnorm(const void* x, const void* residual, const void* weight, void* s
   if (rows == 0) return SDAG_OK;
   constexpr int THREADS = 256;
   const size_t smem = static_cast<size_t>(dim) * 2;
-  static bool cfg = false;
-  if (!cfg && smem > 48 * 1024) {
+  static bool cfg[SDAG_MAX_DEVICES] = {};
+  const int dev = device_slot();
+  if (dev < 0) return SDAG_ERR_UNSUPPORTED;
+  if (!cfg[dev] && smem > 48 * 1024) {
     SDAG_CUDA_TRY(cudaFuncSetAttribute(rmsnorm_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    cfg = true;
+    cfg[dev] = true;
   }
   rmsnorm_kernel<THREADS><<<static_cast<unsigned>(rows), THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(residual),
@@ -459,10 +461,12 @@ template <int B, int R, bool ROPE>
 int launch_gemv_r(const void* x, const void* W, const void* bias, const void* norm_w, const void* resid, void* out, int K, int N,
                   int prologue, float eps, int pair, int n_sm, cudaStream_t st, const RopeArgs& rope) {
   const size_t smem = static_cast<size_t>(B) * K * 2;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[SDAG_MAX_DEVICES] = {};
+  const int dev = device_slot();
+  if (dev < 0) return SDAG_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024 && smem > configured[dev]) {
     SDAG_CUDA_TRY(cudaFuncSetAttribute(gemv_kernel<B, R, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
+    configured[dev] = smem;
   }
   const int per_sm = smem > 100 * 1024 ? 1 : (smem > 64 * 1024 ? 2 : 3);
   long long ctas = (static_cast<long long>(N) / R + (GEMV_THREADS / 32) - 1) / (GEMV_THREADS / 32);
@@ -476,11 +480,7 @@ int launch_gemv_r(const void* x, const void* W, const void* bias, const void* no
 template <int B>
 int launch_gemv(const void* x, const void* W, const void* bias, const void* norm_w, const void* resid, void* out, int K, int N,
                 int prologue, float eps, int pair, cudaStream_t st, const RopeArgs* rope = nullptr) {
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
-  }
+  const int n_sm = device_sm_count();
   // narrow layers: two rows per warp pass, so that N / 2 warp passes still cover every SM a few times
   const RopeArgs none = {};
   if (rope) return launch_gemv_r<B, 2, true>(x, W, bias, norm_w, resid, out, K, N, prologue, eps, 0, n_sm, st, *rope);
@@ -677,16 +677,14 @@ int launch_gemv_mma(const void* x, const void* W, const void* bias, const void* 
     if (prologue == PRO_NONE) rows_staged = 0;
   }
   const size_t smem = static_cast<size_t>(rows_staged) * (K + 32) * 2 + red_bytes;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static size_t configured[SDAG_MAX_DEVICES] = {};
+  const int dev = device_slot();
+  if (dev < 0) return SDAG_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024 && smem > configured[dev]) {
     SDAG_CUDA_TRY(cudaFuncSetAttribute(gemv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
+    configured[dev] = smem;
   }
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm = 148;
-  }
+  const int n_sm = device_sm_count();
   const int per_sm = smem > 110 * 1024 ? 1 : (smem > 72 * 1024 ? 2 : 3);
   long long ctas = N / 16;
   if (ctas > static_cast<long long>(n_sm) * per_sm) ctas = static_cast<long long>(n_sm) * per_sm;

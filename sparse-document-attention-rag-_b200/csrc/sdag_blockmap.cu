@@ -51,48 +51,37 @@ __global__ void __launch_bounds__(256) dense_mask_kernel(const int32_t* __restri
                                                          int nbr_k, uint8_t* __restrict__ mask, int L) {
   const Layout lay = read_layout(lay_raw, max_docs, nbr_k);
   const int i = blockIdx.x;
-  __shared__ int iv_lo[2 + SDAG_MAX_DOCS * 2];
-  __shared__ int iv_hi[2 + SDAG_MAX_DOCS * 2];
-  __shared__ int n_iv;
+  // documents whose span holds row i (one for layouts the prompt builder produces; overlapping spans may give several —
+  // bounded by n_docs <= SDAG_MAX_DOCS, so nothing is ever dropped), then every element evaluates the predicate itself
+  __shared__ int docs_of_row[SDAG_MAX_DOCS];
+  __shared__ int n_docs_of_row;
   if (threadIdx.x == 0) {
     int n = 0;
-    const int s_rows = min(max(lay.S, 0), L);
-    if (i < s_rows) {  // SDAG.py:107-108
-      iv_lo[n] = 0;
-      iv_hi[n++] = i + 1;
-    }
-    const int qa0 = max(lay.qa, 0);
-    if (i >= qa0) {  // SDAG.py:124-125
-      iv_lo[n] = 0;
-      iv_hi[n++] = i + 1;
-    }
-    const int s_cols = py_clip(lay.S, L);
-    for (int d = 0; d < lay.n_docs; ++d) {  // SDAG.py:113-122
+    for (int d = 0; d < lay.n_docs && d < SDAG_MAX_DOCS; ++d) {  // SDAG.py:113-116 (row range of the slice assignment)
       const int ds = lay.spans[2 * d], de = lay.spans[2 * d + 1];
-      if (i < max(ds, 0) || i >= min(de, L)) continue;
-      if (n + 2 + lay.nbr_k > 2 + SDAG_MAX_DOCS * 2) break;
-      iv_lo[n] = 0;
-      iv_hi[n++] = s_cols;
-      iv_lo[n] = py_clip(ds, L);
-      iv_hi[n++] = i + 1;
-      if (lay.use_nbrs) {
-        for (int t = 0; t < lay.nbr_k; ++t) {
-          const int nb = lay.nbrs[d * lay.nbr_k + t];
+      if (i >= max(ds, 0) && i < min(de, L)) docs_of_row[n++] = d;
+    }
+    n_docs_of_row = n;
+  }
+  __syncthreads();
+  const int n = n_docs_of_row;
+  const bool causal_row = i < min(max(lay.S, 0), L) || i >= max(lay.qa, 0);  // SDAG.py:107-108, 124-125
+  const int s_cols = py_clip(lay.S, L);
+  uint8_t* row = mask + static_cast<size_t>(i) * L;
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    bool a = causal_row && j <= i;
+    for (int t = 0; t < n && !a; ++t) {
+      const int d = docs_of_row[t];
+      a = j < s_cols || (j >= py_clip(lay.spans[2 * d], L) && j <= i);  // SDAG.py:117-118
+      if (!a && lay.use_nbrs) {
+        for (int u = 0; u < lay.nbr_k && !a; ++u) {  // SDAG.py:119-122
+          const int nb = lay.nbrs[d * lay.nbr_k + u];
           if (nb < 0 || nb >= lay.n_docs) continue;
-          iv_lo[n] = py_clip(lay.spans[2 * nb], L);
-          iv_hi[n++] = py_clip(lay.spans[2 * nb + 1], L);
+          a = j >= py_clip(lay.spans[2 * nb], L) && j < py_clip(lay.spans[2 * nb + 1], L);
         }
       }
     }
-    n_iv = n;
-  }
-  __syncthreads();
-  const int n = n_iv;
-  uint8_t* row = mask + static_cast<size_t>(i) * L;
-  for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    uint8_t a = 0;
-    for (int t = 0; t < n; ++t) a |= (j >= iv_lo[t] && j < iv_hi[t]) ? 1 : 0;
-    row[j] = a;
+    row[j] = a ? 1 : 0;
   }
 }
 

@@ -313,13 +313,7 @@ decode_merge_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
+  return device_sm_count();
 }
 
 // One CTA per SM (the ring takes the whole shared memory): as many splits as fill the SMs once, never more than tiles.
@@ -344,11 +338,13 @@ template <int D>
 int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloat16* q, int64_t sq_b, int64_t sq_h,
                   float* part, __nv_bfloat16* out, int B, int H, int Hkv, int kv_len, int nsplit, float sl2,
                   const int32_t* kv_len_dev, int kv_len_dev_stride, cudaStream_t st) {
-  static bool cfg = false;
-  if (!cfg) {
+  static bool cfg[SDAG_MAX_DEVICES] = {};
+  const int dev = device_slot();
+  if (dev < 0) return SDAG_ERR_UNSUPPORTED;
+  if (!cfg[dev]) {
     SDAG_CUDA_TRY(cudaFuncSetAttribute(decode_split_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        DecodeSmem<D>::kTotal));
-    cfg = true;
+    cfg[dev] = true;
   }
   // both kernels are programmatic dependents of their predecessor: launch latency hides behind the previous kernel's tail
   unsigned int* tickets = nullptr;

@@ -921,16 +921,15 @@ int make_map_4d(CUtensorMap* m, const void* base, int D, int rows, int heads, in
 template <int D>
 int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtensorMap& tq32, const CUtensorMap& tk,
                    const CUtensorMap& tv, const PrefillParams& p, int cap_qtiles, cudaStream_t st) {
-  static bool configured = false;
-  static int n_sm = 148;
+  static bool configured[SDAG_MAX_DEVICES] = {};
   const int smem = Smem<D>::kTotal > 100 * 1024 ? Smem<D>::kTotal : 100 * 1024;  // cap residency at 2 CTAs / SM (TMEM)
-  if (!configured) {
+  const int dev = device_slot();
+  if (dev < 0) return SDAG_ERR_UNSUPPORTED;
+  if (!configured[dev]) {
     SDAG_CUDA_TRY(cudaFuncSetAttribute(sdag_prefill_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int dev = 0;
-    SDAG_CUDA_TRY(cudaGetDevice(&dev));
-    SDAG_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
+    configured[dev] = true;
   }
+  const int n_sm = device_sm_count();
   const long long n_items = static_cast<long long>(cap_qtiles) * p.H * p.B;
   if (n_items <= 0) return SDAG_ERR_INVALID;
   const long long grid = n_items < 2ll * n_sm ? n_items : 2ll * n_sm;

@@ -48,7 +48,31 @@ def full_blockmap(lengths_dev: torch.Tensor, max_L: int):
     return bm
 
 
-PAIR_GEMM_MIN_ROWS = 512  # token rows from which the intermediate projection runs on llm_gemm (fused bias + GELU)
+def _linear(x, w, bias, residual=None, epilogue: int = 0):
+    """bf16 ``F.linear`` on this library's CTA-pair GEMM: plain (+ bias), + residual (``llm_gemm_residual``: the
+    ``dense(x) + input_tensor`` of BertSelfOutput / BertOutput, bf16 roundings kept), or bias + erf-GELU (``epilogue=2``,
+    BertIntermediate)."""
+    lib = _lib.load()
+    N, K = w.shape
+    ok = (x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.is_contiguous() and N % 8 == 0 and K % 8 == 0
+          and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0
+          and (residual is None or (residual.stride(1) == 1 and residual.stride(0) % 8 == 0)))
+    if not ok:
+        _lib.note_fallback("encoder._linear", "operand layout not accepted by llm_gemm: cuBLAS")
+        y = F.linear(x, w, bias)
+        if epilogue == 2:
+            _lib.check(lib.enc_gelu(y.data_ptr(), y.data_ptr(), y.numel(), _lib.stream_ptr(y.device)), "enc_gelu")
+        return y if residual is None else y + residual
+    out = torch.empty((x.shape[0], N), dtype=torch.bfloat16, device=x.device)
+    _lib.count_launches(1)
+    if residual is None:
+        _lib.check(lib.llm_gemm(x.data_ptr(), x.stride(0), w.data_ptr(), _lib.ptr(bias), out.data_ptr(), N, x.shape[0], N, K,
+                                epilogue, _lib.stream_ptr(x.device)), "llm_gemm")
+    else:
+        _lib.check(lib.llm_gemm_residual(x.data_ptr(), x.stride(0), w.data_ptr(), _lib.ptr(bias), residual.data_ptr(),
+                                         residual.stride(0), out.data_ptr(), N, x.shape[0], N, K, _lib.stream_ptr(x.device)),
+                   "llm_gemm_residual")
+    return out
 
 
 def _layernorm(x, residual, weight, bias, eps):
@@ -116,24 +140,15 @@ class BertEncoderRunner:
         bm = full_blockmap(lengths, L)
         scaling = float(D) ** -0.5
         for ly in self.layers:
-            qkv = F.linear(x, ly["wqkv"], ly["bqkv"]).view(B, L, 3, H, D)
+            qkv = _linear(x, ly["wqkv"], ly["bqkv"]).view(B, L, 3, H, D)
             # strided views straight into the fused projection: q [B,H,L,D], k / v [B,H,L,D] (no copies, TMA takes strides)
             q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
             ctx = sdag.sdag_prefill_attention(q, k, v, bm, scaling, ragged=True).view(T, hid)
             del qkv
-            x = _layernorm(F.linear(ctx, ly["wo"], ly["bo"]), x, ly["ln1_w"], ly["ln1_b"], ly["eps1"])
-            _lib.count_launches(1)
-            wi = ly["wi"]
-            if (PAIR_GEMM_MIN_ROWS <= x.shape[0] and x.is_contiguous() and wi.is_contiguous() and wi.shape[0] % 8 == 0
-                    and wi.shape[1] % 8 == 0):
-                # intermediate projection on the CTA-pair GEMM with bias + GELU in its epilogue (same roundings as the two-step form)
-                inter = torch.empty((x.shape[0], wi.shape[0]), dtype=torch.bfloat16, device=dev)
-                _lib.check(lib.llm_gemm(x.data_ptr(), x.stride(0), wi.data_ptr(), _lib.ptr(ly["bi"]), inter.data_ptr(), wi.shape[0],
-                                        x.shape[0], wi.shape[0], wi.shape[1], 2, _lib.stream_ptr(dev)), "llm_gemm gelu")
-            else:
-                inter = F.linear(x, wi, ly["bi"])
-                _lib.check(lib.enc_gelu(inter.data_ptr(), inter.data_ptr(), inter.numel(), _lib.stream_ptr(dev)), "enc_gelu")
-            x = _layernorm(F.linear(inter, ly["wd"], ly["bd"]), x, ly["ln2_w"], ly["ln2_b"], ly["eps2"])
+            # dense + bias + residual in the GEMM epilogue; LayerNorm then reads one tensor
+            x = _layernorm(_linear(ctx, ly["wo"], ly["bo"], residual=x), None, ly["ln1_w"], ly["ln1_b"], ly["eps1"])
+            inter = _linear(x, ly["wi"], ly["bi"], epilogue=2)  # bias + GELU epilogue (same roundings as the two-step form)
+            x = _layernorm(_linear(inter, ly["wd"], ly["bd"], residual=x), None, ly["ln2_w"], ly["ln2_b"], ly["eps2"])
         return x.view(B, L, hid)
 
 

@@ -29,10 +29,26 @@ def _split_rows(enc) -> List[torch.Tensor]:
     return [row[m.bool()] for row, m in zip(ids, mask)]
 
 
+def _eos_ids(tokenizer, model) -> List[int]:
+    """Every id ``model.generate`` stops on: ``generation_config.eos_token_id`` — an int or a list (Llama-3.1-Instruct
+    ships [128001, 128008, 128009]); content_generation.py:79-87 passes no ``eos_token_id``, so HF takes the generation
+    config's, and generates to ``max_new_tokens`` when that is unset.  Models without a generation config fall back to the
+    tokenizer's id."""
+    gc = getattr(model, "generation_config", None)
+    src = getattr(gc, "eos_token_id", None) if gc is not None else getattr(tokenizer, "eos_token_id", None)
+    ids: List[int] = []
+    for v in (src if isinstance(src, (list, tuple)) else [src]):
+        if v is not None and int(v) not in ids:
+            ids.append(int(v))
+    return ids
+
+
 def _cut_at_eos(ids: List[int], eos) -> List[int]:
     """``model.generate`` finishes a sequence at its first EOS (the first new token included) and pads after it."""
-    if eos is not None and eos in ids:
-        return ids[: ids.index(eos) + 1]
+    stops = set(eos if isinstance(eos, (list, tuple, set)) else ([] if eos is None else [eos]))
+    for pos, t in enumerate(ids):
+        if t in stops:
+            return ids[: pos + 1]
     return ids
 
 
@@ -51,7 +67,8 @@ def _generate_one_via_hook(model, row: torch.Tensor, max_tokens: int, eos, tempe
     logits, past = sdag.prefill_forward(model, row.unsqueeze(0), None)
     nxt = pick(logits)
     out = [int(nxt)]
-    while len(out) < max_tokens and out[-1] != eos:
+    stops = set(eos if isinstance(eos, (list, tuple, set)) else ([] if eos is None else [eos]))
+    while len(out) < max_tokens and out[-1] not in stops:
         step = model(input_ids=nxt, past_key_values=past, use_cache=True)
         past = step.past_key_values
         nxt = pick(step.logits[:, -1, :])
@@ -75,7 +92,7 @@ def generate_batch_seq2seq(tokenizer, model, prompts_list: Sequence[str], max_to
         raise _lib.SdagB200Error("sdag_b200 runs on CUDA devices only (no CPU fallback)")
     enc = tokenizer(prompts_list, return_tensors="pt", padding=True, truncation=True)
     rows = [r.to(device) for r in _split_rows(enc)]
-    eos = tokenizer.eos_token_id
+    eos = _eos_ids(tokenizer, model)
     sdag.prepare_model(model)
     runner = get_runner(model) if sdag.USE_FUSED_PREFILL else None
     if runner is None:
@@ -83,7 +100,7 @@ def generate_batch_seq2seq(tokenizer, model, prompts_list: Sequence[str], max_to
     else:
         lengths = torch.tensor([int(r.numel()) for r in rows], dtype=torch.int64, device=device)
         L = int(lengths.max())
-        pad = eos if eos is not None else 0
+        pad = tokenizer.eos_token_id if tokenizer.eos_token_id is not None else 0
         ids = torch.full((len(rows), L), pad, dtype=torch.int64, device=device)
         for b, r in enumerate(rows):
             ids[b, : r.numel()] = r

@@ -4,10 +4,11 @@ SDAG.py:175-176).
 Hugging Face's decoder layer runs ~25 small torch kernels around each attention call (RMSNorm in fp32 with six
 passes, RoPE via slice / neg / cat, SiLU then mul, residual adds) — about a third of a Llama-3-8B prefill step on a
 B200.  ``FusedPrefill`` keeps the HF module's weights (the q/k/v and gate/up projections are re-pointed at views of
-fused weight matrices, no copy is kept) and drives: one cuBLAS GEMM for qkv, ``llm_rope_qkv`` (RoPE + KV-cache
-write), the SDAG attention kernel, o_proj, ``llm_rmsnorm`` (fused residual add), one GEMM for gate+up,
-``llm_swiglu``, down_proj.  Only the last position of each prompt goes through the final norm and the LM head
-(the reference computes all L rows and uses one, SDAG.py:181).  The returned KV cache is a HF ``DynamicCache``,
+fused weight matrices, no copy is kept) and drives, per layer: ``llm_gemm_rope`` (q/k/v projection with RoPE and the
+KV-cache write in its epilogue), the SDAG attention kernel, ``llm_gemm_residual`` (o_proj + residual add),
+``llm_rmsnorm``, ``llm_gemm`` with the SwiGLU epilogue (gate + up), ``llm_gemm_residual`` (down_proj + residual add),
+``llm_rmsnorm`` — no library GEMM in the prefill.  Only the last position of each prompt goes through the final norm
+and the LM head (the reference computes all L rows and uses one, SDAG.py:181).  The returned KV cache is a HF ``DynamicCache``,
 so decoding continues through the normal HF path (with the ``sdag_b200`` decode attention).
 """
 from __future__ import annotations
@@ -21,15 +22,56 @@ import torch.nn.functional as F
 from . import _lib
 
 
-def _linear(x, w, bias):
-    """F.linear, or llm_gemm for large token counts when PAIR_GEMM_ALL is set (experiment)."""
-    if PAIR_GEMM_ALL and x.shape[0] >= PAIR_GEMM_MIN_ROWS and w.shape[0] % 8 == 0 and x.stride(1) == 1 and x.stride(0) % 8 == 0:
+class _GemmTimer:
+    """bench.py: CUDA-event timing of one prefill GEMM launch on its stream, collected into ``_gemm_events`` as
+    ``(start, end, name, rows, N, K)`` — inactive (no events recorded) unless the list is set."""
+
+    def __init__(self, name: str, rows: int, N: int, K: int):
+        self.meta = (name, rows, N, K)
+        self.ev = None
+
+    def __enter__(self):
+        if _gemm_events is not None:
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            _gemm_events.append(self.ev + self.meta)
+        return False
+
+
+def _gemm_ok(x, w) -> bool:
+    """Shapes / strides llm_gemm takes: 16-byte rows everywhere (K, N and the row strides multiples of 8 elements)."""
+    return (x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.is_contiguous() and w.shape[0] % 8 == 0
+            and w.shape[1] % 8 == 0 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0)
+
+
+def _linear(x, w, bias, residual=None, prefill: bool = True, name: str = "linear"):
+    """``F.linear(x, w, bias)`` (+ ``residual``, added with the bf16 roundings of ``residual + linear(x)``) for bf16
+    ``x [rows, K]``.  The prefill runs every projection on this library's CTA-pair tcgen05 GEMM (``llm_gemm`` /
+    ``llm_gemm_residual``); the few-row GEMMs of a decode step with more than two prompts stay on cuBLAS, where a
+    256-row tile would be almost empty (``prefill=False``)."""
+    if prefill and USE_PAIR_GEMM and _gemm_ok(x, w) and (residual is None or (residual.stride(1) == 1 and residual.stride(0) % 8 == 0)):
         lib = _lib.load()
-        out = torch.empty((x.shape[0], w.shape[0]), dtype=torch.bfloat16, device=x.device)
-        _lib.check(lib.llm_gemm(x.data_ptr(), x.stride(0), w.data_ptr(), _lib.ptr(bias), out.data_ptr(), w.shape[0], x.shape[0],
-                                w.shape[0], w.shape[1], 0, _lib.stream_ptr(x.device)), "llm_gemm")
+        N, K = w.shape
+        out = torch.empty((x.shape[0], N), dtype=torch.bfloat16, device=x.device)
+        _lib.count_launches(1)
+        with _GemmTimer(name, x.shape[0], N, K):
+            if residual is None:
+                _lib.check(lib.llm_gemm(x.data_ptr(), x.stride(0), w.data_ptr(), _lib.ptr(bias), out.data_ptr(), N, x.shape[0], N, K,
+                                        0, _lib.stream_ptr(x.device)), "llm_gemm")
+            else:
+                _lib.check(lib.llm_gemm_residual(x.data_ptr(), x.stride(0), w.data_ptr(), _lib.ptr(bias), residual.data_ptr(),
+                                                 residual.stride(0), out.data_ptr(), N, x.shape[0], N, K,
+                                                 _lib.stream_ptr(x.device)), "llm_gemm_residual")
         return out
-    return F.linear(x, w, bias)
+    if prefill and USE_PAIR_GEMM:
+        _lib.note_fallback("llama_runner._linear", "operand layout not accepted by llm_gemm: cuBLAS")
+    y = F.linear(x, w, bias)
+    return y if residual is None else y + residual
 
 
 def _rmsnorm(x, residual, weight, eps):
@@ -74,27 +116,62 @@ class FusedPrefill:
         torch.cuda.empty_cache()
 
     @staticmethod
-    def try_build(model) -> Optional["FusedPrefill"]:
+    def unsupported_reason(model) -> Optional[str]:
+        """None when the fused engine covers this model, else why not (architecture / dtype / device)."""
+        cfg = model.config
+        inner = getattr(model, "model", None)
         try:
-            cfg = model.config
-            inner = model.model
             p0 = next(model.parameters())
-            ok = (p0.dtype == torch.bfloat16 and p0.is_cuda and getattr(cfg, "hidden_act", "") == "silu"
-                  and hasattr(inner, "rotary_emb") and hasattr(inner, "embed_tokens") and hasattr(model, "lm_head")
-                  and cfg.hidden_size % 8 == 0 and cfg.intermediate_size % 8 == 0)
-            D = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
-            ok = ok and D in (64, 128)
-            for layer in inner.layers:
-                at, mlp = layer.self_attn, layer.mlp
-                for name in ("q_proj", "k_proj", "v_proj", "o_proj"):
-                    ok = ok and isinstance(getattr(at, name, None), torch.nn.Linear)
-                for name in ("gate_proj", "up_proj", "down_proj"):
-                    ok = ok and isinstance(getattr(mlp, name, None), torch.nn.Linear) and getattr(mlp, name).bias is None
-                ok = ok and hasattr(layer.input_layernorm, "variance_epsilon") and hasattr(layer.post_attention_layernorm, "variance_epsilon")
-                ok = ok and not hasattr(at, "q_norm")  # per-head q/k norms (Qwen3, Gemma) are not handled
-            return FusedPrefill(model) if ok else None
-        except Exception:
+        except StopIteration:
+            return "model has no parameters"
+        if p0.dtype != torch.bfloat16:
+            return f"weights are {p0.dtype}, the engine computes in bf16"
+        if not p0.is_cuda:
+            return "weights are not on a CUDA device"
+        if getattr(cfg, "hidden_act", "") != "silu":
+            return f"hidden_act={getattr(cfg, 'hidden_act', None)!r} (SwiGLU MLP expected)"
+        if inner is None or not (hasattr(inner, "rotary_emb") and hasattr(inner, "embed_tokens") and hasattr(model, "lm_head")):
+            return "not a Llama-shaped decoder (rotary_emb / embed_tokens / lm_head)"
+        if cfg.hidden_size % 8 or cfg.intermediate_size % 8:
+            return "hidden / intermediate size not a multiple of 8"
+        D = getattr(cfg, "head_dim", None) or cfg.hidden_size // cfg.num_attention_heads
+        if D not in (64, 128):
+            return f"head_dim={D} (64 or 128 supported)"
+        for layer in inner.layers:
+            at, mlp = layer.self_attn, layer.mlp
+            for name in ("q_proj", "k_proj", "v_proj", "o_proj"):
+                if not isinstance(getattr(at, name, None), torch.nn.Linear):
+                    return f"self_attn.{name} is not nn.Linear"
+            for name in ("gate_proj", "up_proj", "down_proj"):
+                lin = getattr(mlp, name, None)
+                if not isinstance(lin, torch.nn.Linear) or lin.bias is not None:
+                    return f"mlp.{name} is not a bias-free nn.Linear"
+            if not (hasattr(layer.input_layernorm, "variance_epsilon") and hasattr(layer.post_attention_layernorm, "variance_epsilon")):
+                return "layer norms are not RMSNorm"
+            if hasattr(at, "q_norm"):
+                return "per-head q/k norms (Qwen3, Gemma) are not handled"
+        return None
+
+    @staticmethod
+    def try_build(model) -> Optional["FusedPrefill"]:
+        """The engine for ``model``, or None (Hugging Face forward + attention hook) when the architecture is not covered;
+        the reason is recorded through ``_lib.note_fallback`` (an error under SDAG_STRICT=1).  Errors while building the
+        engine for a covered model are not swallowed."""
+        reason = FusedPrefill.unsupported_reason(model)
+        if reason is not None:
+            _lib.note_fallback("FusedPrefill.try_build", reason)
             return None
+        return FusedPrefill(model)
+
+    @property
+    def path(self) -> str:
+        """Which kernels the prefill of this engine launches (bench.py prints it next to the numbers)."""
+        if USE_PAIR_GEMM:
+            qkv = "llm_gemm_rope (q/k/v + RoPE + KV write)" if FUSED_ROPE_GEMM else "llm_gemm + llm_rope_qkv"
+            lin = f"{qkv}, llm_gemm_residual (o, down), llm_gemm SwiGLU (gate/up), llm_gemm (lm_head)"
+        else:
+            lin = "cuBLAS via torch (SDAG_PAIR_GEMM=off)"
+        return f"FusedPrefill: {lin}; sdag_prefill_kernel; llm_rmsnorm"
 
     def rope_tables(self, n_pos: int, device):
         """bf16 cos / sin tables ``[n_pos, D]`` indexed by absolute position (HF rotary module, rounded like HF does)."""
@@ -137,8 +214,7 @@ class FusedPrefill:
         last_rows = torch.arange(B, device=dev) * L + ((lengths - 1) if lengths is not None else (L - 1))
         n_layers = len(self.layers)
         per_tile = 256 // D
-        fused_qkv = (FUSED_ROPE_GEMM and T >= PAIR_GEMM_MIN_ROWS and H % per_tile == 0 and Hkv % per_tile == 0
-                     and self.hidden % 8 == 0)
+        fused_qkv = (FUSED_ROPE_GEMM and USE_PAIR_GEMM and H % per_tile == 0 and Hkv % per_tile == 0 and self.hidden % 8 == 0)
         for i, ly in enumerate(self.layers):
             q = torch.empty((B, L, H, D), dtype=torch.bfloat16, device=dev)
             if kv is not None:
@@ -147,13 +223,15 @@ class FusedPrefill:
             else:
                 kbuf = k = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
                 vbuf = v = torch.empty((B, Hkv, L, D), dtype=torch.bfloat16, device=dev)
-            _lib.count_launches(1)
             if fused_qkv:  # q/k/v projection on the CTA-pair GEMM with RoPE + cache write in its epilogue
-                _lib.check(lib.llm_gemm_rope(normed.data_ptr(), normed.stride(0), ly["wqkv"].data_ptr(), _lib.ptr(ly["bqkv"]),
-                                             cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kbuf.data_ptr(), vbuf.data_ptr(), B, L, H,
-                                             Hkv, D, self.hidden, kbuf.stride(0), kbuf.stride(1), 0, stream), "llm_gemm_rope")
+                _lib.count_launches(1)
+                with _GemmTimer("qkv+rope", T, (H + 2 * Hkv) * D, self.hidden):
+                    _lib.check(lib.llm_gemm_rope(normed.data_ptr(), normed.stride(0), ly["wqkv"].data_ptr(), _lib.ptr(ly["bqkv"]),
+                                                 cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kbuf.data_ptr(), vbuf.data_ptr(), B, L,
+                                                 H, Hkv, D, self.hidden, kbuf.stride(0), kbuf.stride(1), 0, stream), "llm_gemm_rope")
             else:
-                qkv = _linear(normed, ly["wqkv"], ly["bqkv"])
+                qkv = _linear(normed, ly["wqkv"], ly["bqkv"], name="qkv")
+                _lib.count_launches(1)
                 _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kbuf.data_ptr(),
                                             vbuf.data_ptr(), B, L, H, Hkv, D, kbuf.stride(0), kbuf.stride(1), 0, 0, 0, stream),
                            "llm_rope_qkv")
@@ -167,39 +245,41 @@ class FusedPrefill:
             if last:  # only the last position of each prompt is read after the final layer
                 attn, resid = attn[last_rows], resid[last_rows]
             normed, resid = self._mlp_block(attn, resid, i)
-        logits = model.lm_head(normed)
+        logits = _linear(normed, model.lm_head.weight, model.lm_head.bias, name="lm_head")
         return logits, cache
 
-    def _mlp_block(self, attn_rows, resid, i):
-        """o_proj + residual + post-norm + SwiGLU MLP + residual + the next layer's (or the final) norm."""
+    def _mlp_block(self, attn_rows, resid, i, prefill: bool = True):
+        """o_proj + residual + post-norm + SwiGLU MLP + residual + the next layer's (or the final) norm.  In the prefill
+        both residual adds happen in the epilogues of the o / down GEMMs (``llm_gemm_residual``), so each RMSNorm reads one
+        tensor and writes one."""
         lib = _lib.load()
         ly = self.layers[i]
         inner = self.model.model
-        o = _linear(attn_rows, ly["wo"], ly["bo"])
-        resid, normed = _rmsnorm(o, resid, ly["w_post"], ly["eps_post"])
+        if prefill and USE_PAIR_GEMM:
+            resid = _linear(attn_rows, ly["wo"], ly["bo"], residual=resid, name="o+residual")
+            _, normed = _rmsnorm(resid, None, ly["w_post"], ly["eps_post"])
+        else:
+            o = _linear(attn_rows, ly["wo"], ly["bo"], prefill=prefill)
+            resid, normed = _rmsnorm(o, resid, ly["w_post"], ly["eps_post"])
         rows = normed.shape[0]
         act = torch.empty((rows, self.inter), dtype=torch.bfloat16, device=normed.device)
         _lib.count_launches(1)
-        if rows >= PAIR_GEMM_MIN_ROWS and self.inter % 8 == 0:
+        if (prefill or rows >= PAIR_GEMM_MIN_ROWS) and USE_PAIR_GEMM and self.inter % 8 == 0:
             # gate/up GEMM on CTA pairs with the SwiGLU in its epilogue: the [rows, 2*inter] intermediate is never written
-            ev = None
-            if _gemm_events is not None:  # bench.py: CUDA-event timing of the gate/up launches, on their stream
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                ev[0].record()
-            _lib.check(lib.llm_gemm(normed.data_ptr(), normed.stride(0), ly["wgu"].data_ptr(), 0, act.data_ptr(), self.inter,
-                                    rows, 2 * self.inter, self.hidden, 1, _lib.stream_ptr(normed.device)), "llm_gemm")
-            if ev is not None:
-                ev[1].record()
-                _gemm_events.append(ev + (rows,))
+            with _GemmTimer("gate_up+swiglu", rows, 2 * self.inter, self.hidden):
+                _lib.check(lib.llm_gemm(normed.data_ptr(), normed.stride(0), ly["wgu"].data_ptr(), 0, act.data_ptr(), self.inter,
+                                        rows, 2 * self.inter, self.hidden, 1, _lib.stream_ptr(normed.device)), "llm_gemm")
         else:
             gu = F.linear(normed, ly["wgu"])
             _lib.check(lib.llm_swiglu(gu.data_ptr(), act.data_ptr(), rows, self.inter, _lib.stream_ptr(gu.device)), "llm_swiglu")
-        d = _linear(act, ly["wdown"], None)
-        if i + 1 < len(self.layers):
-            nxt = self.layers[i + 1]
-            resid, normed = _rmsnorm(d, resid, nxt["w_in"], nxt["eps_in"])
+        nw, ne = ((self.layers[i + 1]["w_in"], self.layers[i + 1]["eps_in"]) if i + 1 < len(self.layers)
+                  else (inner.norm.weight, inner.norm.variance_epsilon))
+        if prefill and USE_PAIR_GEMM:
+            resid = _linear(act, ly["wdown"], None, residual=resid, name="down+residual")
+            _, normed = _rmsnorm(resid, None, nw, ne)
         else:
-            resid, normed = _rmsnorm(d, resid, inner.norm.weight, inner.norm.variance_epsilon)
+            d = _linear(act, ly["wdown"], None, prefill=prefill)
+            resid, normed = _rmsnorm(d, resid, nw, ne)
         return normed, resid
 
     # ------------------------------------------------------------------------------------------------
@@ -237,6 +317,9 @@ class FusedPrefill:
         c["top_p"] = torch.ones((1,), dtype=torch.float32, device=dev)
         q = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=dev)
         attn_out = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=dev)
+        # split-KV scratch owned by this context: the captured graph bakes its address in, so it must live exactly as
+        # long as the graph (the shared per-device scratch of sdag.py is replaced when a larger one is needed)
+        c["dec_ws"] = dec_ws = torch.empty(sdag.decode_workspace_bytes(B, H, D, S_cap), dtype=torch.uint8, device=dev)
         kc, vc, cos, sin = c["kc"], c["vc"], c["cos"], c["sin"]
         sample = temperature > 0
 
@@ -250,8 +333,9 @@ class FusedPrefill:
                 _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kc[i].data_ptr(),
                                             vc[i].data_ptr(), B, 1, H, Hkv, D, kc[i].stride(0), kc[i].stride(1), 0,
                                             c["pos"].data_ptr(), 1, _lib.stream_ptr(dev)), "llm_rope_qkv")
-                sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out)
-                normed, resid = self._mlp_block(attn_out.view(B, H * D), resid, i)
+                sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out,
+                                           workspace=dec_ws)
+                normed, resid = self._mlp_block(attn_out.view(B, H * D), resid, i, prefill=False)
             lg = model.lm_head(normed)
             if sample:
                 nxt = sample_tokens(lg, c["temp"], c["top_p"] if nucleus else None)
@@ -309,7 +393,8 @@ class FusedPrefill:
                         pf_stream.wait_stream(main)
                         _lib.count_launches(1)
                         _lib.check(lib.llm_prefetch_l2(ly["wo"].data_ptr(), ly["wo"].numel() * 2, pf_stream.cuda_stream), "llm_prefetch_l2")
-                    sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out)
+                    sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out,
+                                           workspace=dec_ws)
                     gemv(attn_out, ly["wo"], ly["bo"], None, resid, res_a, H * D, hid, 0)
                     gemv(res_a, ly["wgu"], None, ly["w_post"], None, gu_b, hid, 2 * inter, 1, ly["eps_post"], pair=1)  # -> act [B, inter]
                     gemv(gu_b, ly["wdown"], None, None, res_a, res_b, inter, hid, 0)
@@ -342,9 +427,10 @@ class FusedPrefill:
                 with torch.cuda.graph(graph):
                     step()
                 c["graph"] = graph
-            except Exception:
+            except Exception as exc:  # eager replay of the same step: correct, but every launch pays host latency
                 c["graph"] = None
                 torch.cuda.synchronize(dev)
+                _lib.note_fallback("FusedPrefill._decode_context", "CUDA-graph capture of the decode step failed", exc)
         ctxs[key] = c
         return c
 
@@ -382,6 +468,9 @@ class FusedPrefill:
             c["pos"].copy_(lengths)
             c["len"].copy_(lengths + 1)
         c["slot"].fill_(1)
+        eos_t = None  # one id or several (generation_config.eos_token_id may be a list)
+        if eos_token_id is not None and not (isinstance(eos_token_id, (list, tuple)) and len(eos_token_id) == 0):
+            eos_t = torch.as_tensor(eos_token_id, dtype=torch.int64, device=dev).reshape(-1)
         done = 0
         while done < max_new_tokens:
             n = min(poll_every, max_new_tokens - done)
@@ -392,14 +481,14 @@ class FusedPrefill:
                     c["step"]()
             done += n
             first = 0 if eos_from_first else 1  # the SDAG loop never stops on the prefill token
-            if eos_token_id is not None and bool((c["gen"][:, first : done + 1] == eos_token_id).any(dim=1).all()):
+            if eos_t is not None and bool(torch.isin(c["gen"][:, first : done + 1], eos_t).any(dim=1).all()):
                 break
         return c["gen"][:, : done + 1].clone()
 
 
-_gemm_events = None  # set to a list to collect (start, end, rows) around each prefill gate/up llm_gemm launch
-PAIR_GEMM_ALL = os.environ.get("SDAG_PAIR_GEMM", "") == "all"
-PAIR_GEMM_MIN_ROWS = 512  # prefill gate/up projections with at least this many token rows run on llm_gemm (fused SwiGLU)
+_gemm_events = None  # set to a list to collect (start, end, name, rows, N, K) around every prefill GEMM launch (_GemmTimer)
+USE_PAIR_GEMM = os.environ.get("SDAG_PAIR_GEMM", "") != "off"  # "off": cuBLAS for every projection (A/B measurements only)
+PAIR_GEMM_MIN_ROWS = 512  # decode steps of >= this many prompts would use llm_gemm for gate/up (never reached in practice)
 PREFETCH_O_PROJ = os.environ.get("SDAG_L2_PREFETCH", "") == "1"  # decode step: o_proj weights prefetched into L2 during attention (measured 3 % slower: off)
 FUSED_ROPE_GEMM = os.environ.get("SDAG_NO_FUSED_ROPE_GEMM", "") != "1"  # prefill q/k/v GEMM with the RoPE + cache-write epilogue
 FUSED_ROPE_GEMV = os.environ.get("SDAG_NO_FUSED_ROPE", "") != "1"  # decode q/k/v GEMV with the RoPE + cache-write epilogue

@@ -48,14 +48,13 @@ class Retriever(ABC):
 
 
 def _n_epochs(n_rows: int, cand_cap: int) -> int:
-    """Number of (GEMM + tighten) epochs ip_search runs: first cap/2 rows, same again, then doubling."""
+    """Number of (GEMM + tighten) epochs ip_search runs: the first cap/2 rows are dumped, then the swept prefix grows x4
+    per epoch below 64 k rows and x2 above (ip_search.cu, IP_FAST_GROWTH_ROWS)."""
     span = max(256, cand_cap // 2 // 256 * 256)
-    done, first, n = 0, True, 0
+    done, n = 0, 0
     while done < n_rows:
-        done += span
-        if not first:
-            span *= 2
-        first = False
+        done = min(n_rows, done + span)
+        span = 3 * done if done < 65536 else done
         n += 1
     return n
 
@@ -66,6 +65,8 @@ class FlatIPIndex:
 
     ``corpus_dtype="bf16"`` stores bf16 rows only; search is then exact over ``float32(bf16(corpus))``.
     """
+
+    MAX_ROWS = 0x7FFFFF00  # rows per shard (int32 row numbers inside ip_search); k <= cand_cap / 32; d % 64 == 0, d <= 8192
 
     def __init__(self, d: int, device="cuda", corpus_dtype: str = "fp32", id_offset: int = 0,
                  cand_cap: int = DEFAULT_CAND_CAP):
@@ -128,18 +129,54 @@ class FlatIPIndex:
             self._max_norm = torch.maximum(self._max_norm, nr.reshape(1).float())
         self.ntotal = n
 
+    def reserve(self, n_rows: int) -> None:
+        """Size the storage for ``n_rows`` rows up front (empty index only): later ``add`` calls then never re-allocate."""
+        if self.ntotal != 0 or n_rows <= 0:
+            return
+        if self.corpus_dtype == "fp32":
+            self._f32 = torch.empty((n_rows, self.d), dtype=torch.float32, device=self.device)
+        self._bf16 = torch.empty((n_rows, self.d), dtype=torch.bfloat16, device=self.device)
+
     def add(self, x) -> None:
-        """Append rows (numpy float32 ``[n, d]`` like faiss, or a torch tensor on any device)."""
+        """Append rows (numpy float32 ``[n, d]`` like faiss, or a torch tensor on any device).  Storage grows
+        geometrically, so a sequence of appends costs O(total rows) copies; only the new rows are cast / measured."""
+        lib = _lib.load()
         t = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)) if not torch.is_tensor(x) else x
         if t.dim() != 2 or t.shape[1] != self.d:
             raise ValueError(f"expected [n, {self.d}] rows")
-        t = t.to(self.device, dtype=torch.float32 if self.corpus_dtype == "fp32" else torch.bfloat16)
-        if self.ntotal == 0:
+        n = t.shape[0]
+        if n == 0:
+            return
+        if self.ntotal + n > self.MAX_ROWS:
+            raise _lib.SdagB200Error(f"an index shard holds at most {self.MAX_ROWS} rows (int32 row numbers in the candidate lists); "
+                                     "partition larger corpora with ShardedFlatIPIndex")
+        fp32 = self.corpus_dtype == "fp32"
+        t = t.to(self.device, dtype=torch.float32 if fp32 else torch.bfloat16)
+        if self.ntotal == 0 and (self._bf16 is None or self._bf16.shape[0] < n):
             self._adopt(t)
             return
-        old = self._f32 if self.corpus_dtype == "fp32" else self._bf16
-        self._max_norm.zero_()
-        self._adopt(torch.cat([old[: self.ntotal], t.to(old.dtype)], dim=0))
+        store = self._f32 if fp32 else self._bf16
+        need = self.ntotal + n
+        if store.shape[0] < need:  # amortised growth: double (at least), copy the live rows once
+            cap = max(need, 2 * store.shape[0])
+            if fp32:
+                grown = torch.empty((cap, self.d), dtype=torch.float32, device=self.device)
+                grown[: self.ntotal] = self._f32[: self.ntotal]
+                self._f32 = grown
+            grown16 = torch.empty((cap, self.d), dtype=torch.bfloat16, device=self.device)
+            grown16[: self.ntotal] = self._bf16[: self.ntotal]
+            self._bf16 = grown16
+        lo = self.ntotal
+        if fp32:
+            self._f32[lo:need] = t
+            # bf16 shadow + row norms of the new rows only; the kernel folds their largest norm into max_norm (atomic max)
+            _lib.check(lib.ip_cast_rows_bf16(self._f32[lo:need].data_ptr(), self._bf16[lo:need].data_ptr(), self._max_norm.data_ptr(),
+                                             n, self.d, _lib.stream_ptr(self.device)), "ip_cast_rows_bf16")
+        else:
+            self._bf16[lo:need] = t
+            nr = torch.linalg.vector_norm(t.float(), dim=1).max() * 1.000001
+            self._max_norm = torch.maximum(self._max_norm, nr.reshape(1).float())
+        self.ntotal = need
 
     # -- search ---------------------------------------------------------------------------------------
     def search_device(self, xq: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -152,7 +189,9 @@ class FlatIPIndex:
         if k <= 0:
             raise ValueError("k must be positive")
         if k > self.cand_cap // 32:
-            raise _lib.SdagB200Error(f"k={k} exceeds the supported maximum {self.cand_cap // 32}")
+            raise _lib.SdagB200Error(f"k={k} exceeds the supported maximum {self.cand_cap // 32} (cand_cap / 32)")
+        if self.d % 64 or self.d > 8192:
+            raise _lib.SdagB200Error(f"d={self.d}: the tensor-core pass needs d % 64 == 0 and d <= 8192")
         xq = xq.to(self.device, dtype=torch.float32).contiguous()
         Q = xq.shape[0]
         scores = torch.empty((Q, k), dtype=torch.float32, device=self.device)
@@ -220,11 +259,25 @@ class ShardedFlatIPIndex:
         if self.world == 1:
             return s, i
         Q = s.shape[0]
-        gs = torch.empty((self.world * Q, k), dtype=s.dtype, device=s.device)
-        gi = torch.empty((self.world * Q, k), dtype=i.dtype, device=i.device)
-        dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)  # rank-major concatenation
-        dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
-        return self.merge_fn(gs.view(self.world, Q, k), gi.view(self.world, Q, k), k)
+        if self.merge_fn is not merge_topk_device:  # injected checker (CPU / gloo tests): plain two-tensor exchange
+            gs = torch.empty((self.world * Q, k), dtype=s.dtype, device=s.device)
+            gi = torch.empty((self.world * Q, k), dtype=i.dtype, device=i.device)
+            dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)  # rank-major concatenation
+            dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
+            return self.merge_fn(gs.view(self.world, Q, k), gi.view(self.world, Q, k), k)
+        # one exchange: 12-byte {score, id} records, one all-gather over NVLink, merge straight from the gathered records
+        lib = _lib.load()
+        st = _lib.stream_ptr(s.device)
+        rec = torch.empty((Q, k, 3), dtype=torch.int32, device=s.device)
+        _lib.count_launches(2)
+        _lib.check(lib.topk_pack(s.data_ptr(), i.data_ptr(), Q * k, rec.data_ptr(), st), "topk_pack")
+        gathered = torch.empty((self.world, Q, k, 3), dtype=torch.int32, device=s.device)
+        dist.all_gather_into_tensor(gathered, rec, group=self.group)
+        out_s = torch.empty((Q, k), dtype=torch.float32, device=s.device)
+        out_i = torch.empty((Q, k), dtype=torch.int64, device=s.device)
+        _lib.check(lib.topk_merge_packed(gathered.data_ptr(), self.world, Q, k, out_s.data_ptr(), out_i.data_ptr(),
+                                         _lib.stream_ptr(s.device)), "topk_merge_packed")
+        return out_s, out_i
 
     def search(self, x, k: int):
         xq = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self.local.device)
@@ -246,35 +299,73 @@ def merge_topk_device(scores: torch.Tensor, ids: torch.Tensor, k: int):
 
 
 # ------------------------------------------------------------------------------------------------------
-# faiss IndexFlatIP file format.  Layout restated from faiss' index_write.cpp (not
-# verifiable here — no faiss in the image): fourcc "IxFI", int32 d, int64 ntotal, 2 x int64 dummy,
-# uint8 is_trained, int32 metric_type (0 = inner product), uint64 n_floats, n_floats x float32.
+# faiss IndexFlatIP file format — what faiss.write_index produces for an IndexFlatIP and what the
+# reference hands to faiss.read_index (dense.py:36).  Restated from faiss' impl/index_write.cpp (write_index ->
+# write_index_header + WRITEXBVECTOR) and impl/io_macros.h; no faiss in this image, so the layout is pinned by the
+# hand-assembled fixture tests/golden/faiss_flat_ip_3x64.index (tests/golden/make_ixfi_fixture.py documents every byte).
+# All fields little-endian, no padding:
+#
+#   offset  size  field         value / source
+#   0       4     fourcc        "IxFI" (IndexFlat, METRIC_INNER_PRODUCT; "IxF2" = L2, "IxFl" = other metrics)   index_write.cpp
+#   4       4     d             int32 vector dimension                                                  write_index_header
+#   8       8     ntotal        int64 number of vectors                                                 write_index_header
+#   16      8     dummy         int64 1 << 20 (legacy field, ignored on read)                           write_index_header
+#   24      8     dummy         int64 1 << 20                                                           write_index_header
+#   32      1     is_trained    uint8 bool (1 for flat indexes)                                         write_index_header
+#   33      4     metric_type   int32: 0 = METRIC_INNER_PRODUCT, 1 = METRIC_L2                          write_index_header
+#   [37     4     metric_arg    float32, only when metric_type > 1]                                     write_index_header
+#   37      8     size          uint64 = ntotal * d: number of float32 values (the byte count / 4)      WRITEXBVECTOR
+#   45      4*size  xb / codes  the vectors, row-major float32                                          WRITEXBVECTOR
 # ------------------------------------------------------------------------------------------------------
+_IXFI_HEADER = struct.Struct("<iqqqBi")  # d, ntotal, dummy, dummy, is_trained, metric_type (after the 4-byte fourcc)
+
+
 def write_flat_ip_file(path: str, x: np.ndarray) -> None:
     x = np.ascontiguousarray(x, dtype=np.float32)
     n, d = x.shape
     with open(path, "wb") as f:
         f.write(b"IxFI")
-        f.write(struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, 0))
+        f.write(_IXFI_HEADER.pack(d, n, 1 << 20, 1 << 20, 1, 0))
         f.write(struct.pack("<Q", n * d))
         f.write(x.tobytes())
 
 
-def read_flat_ip_file(path: str, device="cuda", **kw) -> FlatIPIndex:
+def parse_flat_ip_file(path: str) -> np.ndarray:
+    """The ``[ntotal, d]`` float32 vectors of a faiss ``IndexFlatIP`` file (host side of ``read_flat_ip_file``; the array
+    is a read-only memory map).  ``ValueError`` for other index types / metrics and for truncated or inconsistent files."""
+    size_on_disk = os.path.getsize(path)
     with open(path, "rb") as f:
         fourcc = f.read(4)
         if fourcc != b"IxFI":
-            raise ValueError(f"{path}: not a faiss IndexFlatIP file (fourcc {fourcc!r}); only flat inner-product "
-                             "indexes are supported")
-        d, n, _, _, _trained, metric = struct.unpack("<iqqqBi", f.read(4 + 8 * 3 + 1 + 4))
+            kind = {b"IxF2": "an IndexFlatL2", b"IxFl": "an IndexFlat with another metric"}.get(fourcc, f"fourcc {fourcc!r}")
+            raise ValueError(f"{path}: not a faiss IndexFlatIP file ({kind}); only flat inner-product indexes are supported")
+        head = f.read(_IXFI_HEADER.size)
+        if len(head) != _IXFI_HEADER.size:
+            raise ValueError(f"{path}: truncated index header")
+        d, n, _, _, _trained, metric = _IXFI_HEADER.unpack(head)
         if metric != 0:
-            raise ValueError("metric_type is not inner product")
-        (count,) = struct.unpack("<Q", f.read(8))
-        if count != n * d:
-            raise ValueError("corrupt index file: vector size does not match header")
-        x = np.frombuffer(f.read(count * 4), dtype=np.float32).reshape(n, d)
-    idx = FlatIPIndex(d, device=device, **kw)
-    idx.add(x)
+            raise ValueError(f"{path}: metric_type {metric} is not METRIC_INNER_PRODUCT (0)")
+        raw = f.read(8)
+        if len(raw) != 8:
+            raise ValueError(f"{path}: truncated index header")
+        (count,) = struct.unpack("<Q", raw)
+        offset = f.tell()
+    if d <= 0 or n < 0 or count != n * d:
+        raise ValueError(f"{path}: corrupt index file: {count} stored values for ntotal={n}, d={d}")
+    if size_on_disk < offset + 4 * count:
+        raise ValueError(f"{path}: truncated index file: {size_on_disk - offset} vector bytes, {4 * count} expected")
+    if count == 0:
+        return np.zeros((0, d), dtype=np.float32)
+    return np.memmap(path, dtype="<f4", mode="r", offset=offset, shape=(n, d))
+
+
+def read_flat_ip_file(path: str, device="cuda", **kw) -> FlatIPIndex:
+    x = parse_flat_ip_file(path)
+    idx = FlatIPIndex(x.shape[1], device=device, **kw)
+    for r0 in range(0, x.shape[0], 1 << 20):  # 1M-row pieces: bounded pinned staging, storage sized once
+        if r0 == 0 and x.shape[0] > (1 << 20):
+            idx.reserve(x.shape[0])
+        idx.add(np.ascontiguousarray(x[r0 : r0 + (1 << 20)]))
     return idx
 
 

@@ -96,6 +96,24 @@ class BlockMap:
         self.max_L = max_L
         self.kind = kind  # "spans" | "mask"
         self.launch_qtiles = cap_qtiles  # grid extent in query tiles (>= the device-side count)
+        self._ok: Optional[bool] = None if kind == "spans" else True  # span maps: status words not read back yet
+
+    def is_ok(self) -> bool:
+        """True when every prompt's map was built (header status 0).  The span builder rejects layouts outside its
+        canonical form (``qa_start`` inside a document span, overlapping / unsorted spans, ``S`` past the first span) with a
+        nonzero status and an empty tile list; the attention kernel would then leave the output unwritten.  Read back
+        once per map (one small device-to-host copy), then cached."""
+        if self._ok is None:
+            stride = self.stride_bytes // 4
+            status = self.buf.view(-1)[2 : 2 + stride * self.n_prompts : stride]
+            self._ok = not bool((status != 0).any())
+        return self._ok
+
+    def ensure_ok(self) -> None:
+        if not self.is_ok():
+            raise _lib.SdagB200Error(
+                "block map has a nonzero status: the layout is not in the span builder's canonical form "
+                "(use build_blockmap_checked / build_blockmap_from_mask for such layouts)")
 
     def header(self, i: int = 0) -> dict:
         """Host copy of prompt i's header (synchronises; tests / benchmarks only)."""
@@ -242,6 +260,7 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
         raise ValueError("one block map per batch entry (or a single shared one) expected")
     if blockmap.max_L != L or S != L:
         raise ValueError(f"block map was built for L={blockmap.max_L}, got Lq={L}, Skv={S}")
+    blockmap.ensure_ok()  # a rejected layout must not reach the kernel (its output rows would stay uninitialised)
     q, k, v = (_unit_inner(t) for t in (q, k, v))
     out = (torch.zeros if ragged else torch.empty)((B, L, H, D), dtype=torch.bfloat16, device=q.device)
     ws_bytes = int(lib.sdag_prefill_workspace_bytes(B, Hkv, D))
@@ -338,12 +357,20 @@ def compute_doc_knn_for_docs(ranker, docs: List[str], k_neighbors: int, device="
 # ------------------------------------------------------------------------------------------------------
 # Hugging Face attention hook
 # ------------------------------------------------------------------------------------------------------
+def decode_workspace_bytes(B: int, H: int, D: int, S: int) -> int:
+    """Bytes of split-KV scratch one ``sdag_decode_attention`` call needs (``sdag_decode_workspace_bytes``)."""
+    return int(_lib.load().sdag_decode_workspace_bytes(B, H, D, S))
+
+
 def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scaling: Optional[float] = None,
-                          kv_len_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                          kv_len_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                          workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One decode step, dense over the cache: q ``[B,H,1,D]``, k/v ``[B,Hkv,S,D]`` bf16 -> ``[B,1,H,D]``.
     ``kv_len_dev`` (int32 device scalar, or one value per prompt for ragged batches) makes the valid cache length a
     device-side value (``S`` is then the bound the grid is sized for) so the call can sit inside a CUDA graph that is
-    replayed per token."""
+    replayed per token.  ``workspace`` (uint8, at least ``decode_workspace_bytes``) is the split-KV scratch; a caller
+    that captures the call into a CUDA graph MUST pass its own, kept alive with the graph — the shared per-device
+    scratch is replaced when a later call needs a larger one, and a captured pointer to it would dangle."""
     lib = _lib.load()
     B, H, _, D = q.shape
     Hkv, S = k.shape[1], k.shape[2]
@@ -354,14 +381,22 @@ def sdag_decode_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, sca
     if out is None:
         out = torch.empty((B, 1, H, D), dtype=torch.bfloat16, device=q.device)
     ws_bytes = int(lib.sdag_decode_workspace_bytes(B, H, D, S))
-    ws = _workspace(q.device, ws_bytes)
+    if workspace is not None:
+        if workspace.numel() * workspace.element_size() < ws_bytes or workspace.device != q.device:
+            raise _lib.SdagB200Error("decode workspace too small or on another device")
+        ws = workspace
+    else:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.SdagB200Error("sdag_decode_attention inside a CUDA graph needs a caller-owned workspace")
+        ws = _workspace(q.device, ws_bytes)
     scaling = float(D ** -0.5 if scaling is None else scaling)
     _lib.count_launches(2)  # split + merge
     _lib.check(
         lib.sdag_decode_fwd(q2.data_ptr(), q2.stride(0), q2.stride(1),
                             k.data_ptr(), k.stride(0), k.stride(1), k.stride(2),
                             v.data_ptr(), v.stride(0), v.stride(1), v.stride(2),
-                            out.data_ptr(), B, H, Hkv, S, D, scaling, ws.data_ptr(), ws.numel(), _lib.ptr(kv_len_dev),
+                            out.data_ptr(), B, H, Hkv, S, D, scaling, ws.data_ptr(), ws.numel() * ws.element_size(),
+                            _lib.ptr(kv_len_dev),
                             1 if (kv_len_dev is not None and kv_len_dev.numel() == B and B > 1) else 0,
                             _lib.stream_ptr(q.device)),
         "sdag_decode_fwd",
@@ -410,7 +445,9 @@ def prepare_model(model):
     if getattr(model.config, "_attn_implementation", None) != ATTN_NAME:
         try:
             model.set_attn_implementation(ATTN_NAME)
-        except Exception:
+        except (AttributeError, ValueError, TypeError) as exc:
+            # older transformers / non-PreTrainedModel wrappers: no setter, the config field is what the layers read
+            _lib.note_fallback("prepare_model", "set_attn_implementation unavailable, config field set directly", exc)
             model.config._attn_implementation = ATTN_NAME
     return model
 
@@ -601,9 +638,7 @@ def run_rag_with_doc_isolation_batch(model, tokenizer, queries: Sequence[str], m
     if any(len(l.spans) > _lib.MAX_DOCS or l.nbr_k > _lib.MAX_NBR_K for l in layouts):
         return one_by_one()
     bm = build_blockmap(layouts, device)
-    stride = bm.stride_bytes // 4
-    status = bm.buf.view(-1)[2 : 2 + stride * len(layouts) : stride]  # header word 2 of every prompt
-    if bool((status != 0).any()):
+    if not bm.is_ok():  # some layout is outside the span builder's canonical form: dense-mask path per query
         return one_by_one()
     eos = tokenizer.eos_token_id
     lengths = torch.tensor([l.L for l in layouts], dtype=torch.int64, device=device)
@@ -624,7 +659,17 @@ def prefill_batch(model, input_ids_host: torch.Tensor, layouts: Sequence[SdagLay
     from the token offsets there, runs the SDAG prefill (last-position logits only) and returns
     ``(first_tokens_host [B] int64, past_key_values)``.  Greedy or sampled exactly like ``_pick``."""
     ids = input_ids_host.to(device, non_blocking=True)
-    bm = build_blockmap(layouts, device)
-    logits, past = prefill_forward(model, ids, bm)
-    nxt = _pick(logits)
-    return nxt[:, 0].cpu(), past
+    layouts = list(layouts)
+    bm = build_blockmap(layouts, device) if all(len(l.spans) <= _lib.MAX_DOCS and l.nbr_k <= _lib.MAX_NBR_K for l in layouts) else None
+    if bm is not None and bm.is_ok():
+        logits, past = prefill_forward(model, ids, bm)
+        nxt = _pick(logits)
+        return nxt[:, 0].cpu(), past
+    # some layout is not canonical (the reference still builds a mask for it): one prompt at a time through the
+    # dense-mask block map, which represents any mask
+    toks, pasts = [], []
+    for b, lay in enumerate(layouts):
+        logits, past = prefill_forward(model, ids[b : b + 1], build_blockmap_checked(lay, device))
+        toks.append(_pick(logits)[:, 0])
+        pasts.append(past)
+    return torch.cat(toks).cpu(), pasts

@@ -643,8 +643,15 @@ def test_prefill_gemm_swiglu_epilogue_matches_mlp_roundings(M, I, K):
     assert lib.llm_gemm(x.data_ptr(), K, Wgu.data_ptr(), x.data_ptr(), out.data_ptr(), out.stride(0), M, 2 * I, K, 1, st) == 1001  # no bias here
 
 
+def L_count():
+    import sdag_b200._lib as L
+
+    return L.launch_count
+
+
 def test_fused_prefill_with_pair_gemm_matches_cublas_path(monkeypatch):
-    """The prefill engine with gate/up on llm_gemm (fused SwiGLU) vs the same engine on cuBLAS + llm_swiglu."""
+    """The prefill engine with every projection on llm_gemm (RoPE / residual / SwiGLU epilogues) vs the same engine on
+    cuBLAS + the stand-alone glue kernels."""
     import sdag_b200.llama_runner as lr
     import sdag_b200.sdag as sdag
 
@@ -654,10 +661,12 @@ def test_fused_prefill_with_pair_gemm_matches_cublas_path(monkeypatch):
     assert runner is not None
     ids = torch.randint(5, len(tok), (2, 384), device="cuda")
     bm = sdag.causal_blockmap(384, ids.device)
-    monkeypatch.setattr(lr, "PAIR_GEMM_MIN_ROWS", 1 << 30)
+    monkeypatch.setattr(lr, "USE_PAIR_GEMM", False)
     ref, _ = runner.prefill(ids, bm, want_cache=False)
-    monkeypatch.setattr(lr, "PAIR_GEMM_MIN_ROWS", 1)
+    monkeypatch.setattr(lr, "USE_PAIR_GEMM", True)
+    launches0 = L_count()
     got, _ = runner.prefill(ids, bm, want_cache=False)
+    assert "llm_gemm_residual" in runner.path and L_count() > launches0
     torch.testing.assert_close(got.float(), ref.float(), atol=5e-2, rtol=5e-2)
     assert (got.argmax(-1) == ref.argmax(-1)).all()
 

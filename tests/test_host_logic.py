@@ -120,6 +120,56 @@ def test_faiss_flat_file_round_trip(tmp_path):
         load_faiss_index_and_meta(str(tmp_path / "missing.index"), str(p))
 
 
+def test_faiss_flat_ip_reader_on_hand_assembled_fixture(golden_dir, tmp_path):
+    """tests/golden/faiss_flat_ip_3x64.index was assembled field by field from faiss' serializer (make_ixfi_fixture.py);
+    the header below is that layout spelled out in hex, independent of both the fixture script and the reader."""
+    import struct
+
+    from sdag_b200.retrieval import parse_flat_ip_file, write_flat_ip_file
+
+    path = os.path.join(golden_dir, "faiss_flat_ip_3x64.index")
+    raw = open(path, "rb").read()
+    header = bytes.fromhex(
+        "49784649"          # 0   fourcc "IxFI"  (IndexFlat, METRIC_INNER_PRODUCT)
+        "40000000"          # 4   d = 64                        int32
+        "0300000000000000"  # 8   ntotal = 3                    int64 (idx_t)
+        "0000100000000000"  # 16  dummy = 1 << 20               int64
+        "0000100000000000"  # 24  dummy = 1 << 20               int64
+        "01"                # 32  is_trained = true             1 byte
+        "00000000"          # 33  metric_type = 0 (inner product) int32
+        "c000000000000000"  # 37  size = ntotal * d = 192 float32 values   uint64 (WRITEXBVECTOR)
+    )
+    assert len(header) == 45 and raw[:45] == header and len(raw) == 45 + 4 * 192
+    r = np.arange(3, dtype=np.float32)[:, None]
+    c = np.arange(64, dtype=np.float32)[None, :]
+    want = ((r + 1) * np.float32(0.5) - c / np.float32(64)).astype(np.float32)
+    x = parse_flat_ip_file(path)
+    assert x.shape == (3, 64) and x.dtype == np.float32 and np.array_equal(np.asarray(x), want)
+    # this repo's writer produces the same bytes
+    mine = tmp_path / "mine.index"
+    write_flat_ip_file(str(mine), want)
+    assert mine.read_bytes() == raw
+    # the metadata file next to it: one {"id", "text"} object per line (dense.py:38-41)
+    meta = [json.loads(line) for line in open(os.path.join(golden_dir, "faiss_flat_ip_3x64.docs_meta.jsonl"), encoding="utf-8")]
+    assert [m["id"] for m in meta] == ["doc-0", "doc-1", "doc-2"] and all("text" in m for m in meta)
+    # other index types, metrics and damaged files are refused with a reason
+    for fourcc, word in ((b"IxF2", "IndexFlatL2"), (b"IwFl", "fourcc")):
+        bad = tmp_path / "bad.index"
+        bad.write_bytes(fourcc + raw[4:])
+        with pytest.raises(ValueError, match=word):
+            parse_flat_ip_file(str(bad))
+    bad = tmp_path / "metric.index"
+    bad.write_bytes(raw[:33] + struct.pack("<i", 1) + raw[37:])
+    with pytest.raises(ValueError, match="metric_type"):
+        parse_flat_ip_file(str(bad))
+    bad.write_bytes(raw[:-8])
+    with pytest.raises(ValueError, match="truncated"):
+        parse_flat_ip_file(str(bad))
+    bad.write_bytes(raw[:37] + struct.pack("<Q", 191) + raw[45:])
+    with pytest.raises(ValueError, match="corrupt"):
+        parse_flat_ip_file(str(bad))
+
+
 def test_product_path_fails_loudly_without_gpu():
     import torch
 

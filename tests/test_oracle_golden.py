@@ -33,6 +33,36 @@ def test_mask_oracle_matches_reference_bits(golden_dir):
             assert np.array_equal(bits, packed[e["name"]]), e["name"]
 
 
+def test_cpu_reference_mask_equals_reference_builder(golden_dir):
+    """The mask builder of the CPU reference arm (oracle/cpu_reference.py): both its restatement and — where
+    /root/reference exists — the imported reference function give the reference's bits on every strict golden layout."""
+    from oracle.cpu_reference import reference_mask_builder, reference_style_mask
+
+    builders = [reference_style_mask, reference_mask_builder()[0]]
+    checked = 0
+    for e in _mask_meta(golden_dir):
+        if e["L"] > 4096 or e["neighbors"] is not None:
+            continue
+        canonical = e["S"] >= 0 and all(a < b for a, b in e["spans"]) and e["qa_start"] >= 0
+        if not canonical:
+            continue
+        for build in builders:
+            m = build(e["L"], e["S"], [tuple(s) for s in e["spans"]], e["qa_start"]).numpy()
+            if build is reference_style_mask and hashlib.sha256(np.packbits(m, axis=1).tobytes()).hexdigest() != e["sha256"]:
+                # the restatement covers the layouts the prompt builder produces (disjoint ascending spans)
+                spans = e["spans"]
+                ordered = all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+                assert not ordered or not spans or spans[0][0] < e["S"] or spans[-1][1] > e["qa_start"], e["name"]
+                continue
+            assert hashlib.sha256(np.packbits(m, axis=1).tobytes()).hexdigest() == e["sha256"], e["name"]
+            checked += 1
+    assert checked >= 4
+    by = {e["name"]: e for e in _mask_meta(golden_dir)}
+    e = by["cfg2_k10x256"]  # the benchmark layout itself
+    m = reference_style_mask(e["L"], e["S"], [tuple(s) for s in e["spans"]], e["qa_start"]).numpy()
+    assert int(m.sum()) == 516148 and hashlib.sha256(np.packbits(m, axis=1).tobytes()).hexdigest() == e["sha256"]
+
+
 def test_mask_oracle_pair_counts_match_survey(golden_dir):
     by = {e["name"]: e for e in _mask_meta(golden_dir)}
     assert by["cfg1_k5x256"]["pairs"] == 259388

@@ -54,6 +54,43 @@ def test_flat_ip_search_matches_oracle(N, d, Q, k):
     assert int(idx.last_stats[0]) == 0  # no overflow fallback on well-spread data
 
 
+@pytest.mark.parametrize("k", [10, 11, 51])
+def test_flat_ip_search_cta_pair_kernel_d1024_with_tie_set(k):
+    """The configuration bench.py times, in small: d = 1024 (16 k-blocks through the 6-stage ring of
+    ip_gemm_filter_kernel_2cta), a 640-query batch (five query tiles: three CTA-pair tiles, one of them half empty) over
+    200 k rows, 1 % of the rows duplicated at known indices (SURVEY.md §8d tie stress set), against the independent fp32
+    oracle.  k = TOP_K, TOP_K + 1 and the config-5 size."""
+    from sdag_b200.retrieval import FlatIPIndex
+
+    N, d, Q = 200_000, 1024, 640
+    x = _unit_rows(N, d, 42)
+    rng = np.random.default_rng(1)
+    src = rng.choice(N, N // 100, replace=False)
+    dst = rng.choice(np.setdiff1d(np.arange(N), src), N // 100, replace=False)
+    x[torch.from_numpy(dst).cuda()] = x[torch.from_numpy(src).cuda()]
+    q = _unit_rows(Q, d, 7)
+    q[:64] = x[torch.from_numpy(src[:64]).cuda()]  # these queries' two best hits are an exactly tied pair
+    idx = FlatIPIndex.from_device(x)
+    s, i = idx.search_device(q, k)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    assert int(idx.last_stats[0]) == 0  # candidate lists did not overflow: the tensor-core path produced the result
+    xh, qh = x.cpu().numpy(), q.cpu().numpy()
+    oracle = FlatIPOracle(d)
+    oracle.add(xh)
+    D, I = oracle.search(qh, k)
+    np.testing.assert_allclose(s, D, rtol=1e-5, atol=1e-6)
+    assert (np.diff(s, axis=1) <= 0).all()
+    for r, c in zip(*np.nonzero(i != I)):  # documented exception: fp32 near-ties (<= 2e-6 relative) may swap
+        a, b = i[r, c], I[r, c]
+        ea, eb = float(qh[r].astype(np.float64) @ xh[a].astype(np.float64)), float(qh[r].astype(np.float64) @ xh[b].astype(np.float64))
+        assert a >= 0 and b >= 0 and abs(ea - eb) <= 2e-6 * max(1.0, abs(eb)), (r, c, a, b, ea, eb)
+    tied = 0
+    for r in range(64):  # exact ties: lower id first (faiss heap rule)
+        assert s[r, 0] == s[r, 1] and i[r, 0] < i[r, 1] and {int(i[r, 0]), int(i[r, 1])} == {int(src[r]), int(dst[r])}
+        tied += 1
+    assert tied == 64
+
+
 def test_flat_ip_search_unnormalised_rows_and_incremental_add():
     from sdag_b200.retrieval import FlatIPIndex
 
@@ -278,3 +315,25 @@ def test_selector_reuses_index_embeddings_by_row():
         calls_reuse = len([c for c in ranker.calls if any(t.startswith("passage: document") for t in c)])
         assert a == b
         assert calls_encode == 1 and calls_reuse == 0
+
+
+def test_load_faiss_index_and_meta_on_hand_assembled_fixture(golden_dir):
+    """The byte-documented IndexFlatIP fixture (tests/golden/make_ixfi_fixture.py) through the reference's loader name
+    (dense.py:15-41) and a search: ids / scores of the three stored vectors."""
+    from sdag_b200.retrieval import DenseRetriever, load_faiss_index_and_meta, materialize_dense_hits, search_index
+
+    index, meta = load_faiss_index_and_meta(os.path.join(golden_dir, "faiss_flat_ip_3x64.index"),
+                                            os.path.join(golden_dir, "faiss_flat_ip_3x64.docs_meta.jsonl"))
+    assert index.ntotal == 3 and index.d == 64 and len(meta) == 3
+    r = np.arange(3, dtype=np.float32)[:, None]
+    c = np.arange(64, dtype=np.float32)[None, :]
+    x = ((r + 1) * np.float32(0.5) - c / np.float32(64)).astype(np.float32)
+    q = np.stack([x[2], -x[0]]).astype(np.float32)
+    idx, sc = search_index(index, q, 4)
+    want = q.astype(np.float64) @ x.astype(np.float64).T
+    order = np.argsort(-want, axis=1, kind="stable")
+    assert np.array_equal(idx[:, :3], order) and (idx[:, 3] == -1).all()
+    np.testing.assert_allclose(sc[:, :3], np.take_along_axis(want, order, axis=1), rtol=1e-5)
+    texts, ids, _ = materialize_dense_hits(idx, sc, meta)
+    assert ids[0][0] == "doc-2" and ids[0][3] == "NA" and texts[0][3] == ""
+    assert isinstance(DenseRetriever(None, index, meta), DenseRetriever)
