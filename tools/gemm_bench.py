@@ -48,32 +48,40 @@ def main():
     st = _lib.stream_ptr(dev)
     torch.manual_seed(0)
     for name, N, K, epi in (("qkv", 6144, 4096, 0), ("o", 4096, 4096, 0), ("gate_up", 28672, 4096, 0),
-                            ("gate_up+swiglu", 28672, 4096, 1), ("down", 4096, 14336, 0)):
+                            ("gate_up+swiglu", 28672, 4096, 1), ("down", 4096, 14336, 0),
+                            ("o+residual", 4096, 4096, 2), ("down+residual", 4096, 14336, 2)):
         if args.only and name != args.only:
             continue
         x = torch.randn(M, K, device=dev, dtype=torch.bfloat16) * 0.5
         w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.02
-        n_out = N // 2 if epi else N
+        n_out = N // 2 if epi == 1 else N
         out = torch.empty(M, n_out, device=dev, dtype=torch.bfloat16)
+        res = torch.randn(M, n_out, device=dev, dtype=torch.bfloat16) if epi == 2 else None
 
         def ours():
-            _lib.check(lib.llm_gemm(x.data_ptr(), K, w.data_ptr(), 0, out.data_ptr(), n_out, M, N, K, epi, st), "llm_gemm")
+            if epi == 2:  # residual add in the epilogue (what the prefill runs for o / down)
+                _lib.check(lib.llm_gemm_residual(x.data_ptr(), K, w.data_ptr(), 0, res.data_ptr(), n_out, out.data_ptr(), n_out, M, N, K,
+                                                 st), "llm_gemm_residual")
+            else:
+                _lib.check(lib.llm_gemm(x.data_ptr(), K, w.data_ptr(), 0, out.data_ptr(), n_out, M, N, K, epi, st), "llm_gemm")
 
         act = torch.empty(M, N // 2, device=dev, dtype=torch.bfloat16)
 
         def cublas():
             y = torch.nn.functional.linear(x, w)
-            if epi:
+            if epi == 1:
                 _lib.check(lib.llm_swiglu(y.data_ptr(), act.data_ptr(), M, N // 2, st), "swiglu")
+            elif epi == 2:
+                y = y + res
             return y
 
         t_o, t_c = timed(ours), timed(cublas)
         ref = cublas()
-        ref = act if epi else ref
+        ref = act if epi == 1 else ref
         ours()
         err = (out.float() - ref.float()).abs().max().item()
         fl = 2.0 * M * N * K
-        print(f"{name:16s} M={M} N={N} K={K}: llm_gemm {t_o:.3f} ms ({fl / t_o / 1e9:.0f} TFLOP/s)  cuBLAS{'+swiglu' if epi else ''} "
+        print(f"{name:16s} M={M} N={N} K={K}: llm_gemm {t_o:.3f} ms ({fl / t_o / 1e9:.0f} TFLOP/s)  cuBLAS{'+swiglu' if epi == 1 else ('+add' if epi == 2 else '')} "
               f"{t_c:.3f} ms ({fl / t_c / 1e9:.0f} TFLOP/s)  max|diff| {err:.4f}", flush=True)
         if args.sustain:
             print(f"{'':16s} sustained: llm_gemm {sustained(ours, fl):.0f}  cuBLAS {sustained(cublas, fl):.0f} TFLOP/s", flush=True)
