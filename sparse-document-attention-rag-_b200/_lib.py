@@ -9,7 +9,9 @@ import logging
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdag_b200.so")
+# SDAG_B200_LIB: A/B measurements against another build of the same sources (e.g. an earlier round's); symbols that build
+# lacks are then skipped at load time instead of failing
+LIB_PATH = os.environ.get("SDAG_B200_LIB") or os.path.join(_HERE, "libsdag_b200.so")
 
 SDAG_TILE = 128
 BLOCKMAP_HEADER = 16
@@ -81,6 +83,8 @@ def load():
         )
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("SDAG_B200_LIB") and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if the ABI and the header drift apart
         fn.restype = res
         fn.argtypes = args

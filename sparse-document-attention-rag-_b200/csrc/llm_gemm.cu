@@ -77,15 +77,25 @@ __device__ __forceinline__ uint32_t pack_out(float a, float b) {
   return pack_bf16x2(a, b);
 }
 
-// Residual add of the plain epilogue, on this thread's own row: v <- bf16(bf16(v) + resid[col0 + i]) — the two roundings of
-// `residual + linear(x)` with a bf16 linear output (LlamaDecoderLayer, BertSelfOutput / BertOutput).  64 contiguous bytes per
-// thread; columns past n_out (ragged last tile, N % 8 == 0) are left alone.
-__device__ __forceinline__ void add_residual(float (&v)[32], const __nv_bfloat16* rrow, int col0, int n_out) {
+// The residual row segment a thread will add to its accumulator row is known before the accumulators are: pull its 128-byte
+// lines into L2 while the epilogue warp would otherwise only wait for the tile's last MMA.
+__device__ __forceinline__ void prefetch_residual(const __nv_bfloat16* rrow, int col0, int n_cols, int n_out) {
+  for (int c = 0; c < n_cols; c += 64)
+    if (col0 + c < n_out) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + col0 + c));
+}
+// 32 residual values (64 bytes) of this thread's row as four 16-byte loads, issued ahead of the accumulator chunk they meet
+__device__ __forceinline__ void load_residual(uint4 (&w)[4], const __nv_bfloat16* rrow, int col0, int n_out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = (col0 + 8 * i + 8 <= n_out) ? __ldg(reinterpret_cast<const uint4*>(rrow + col0 + 8 * i)) : make_uint4(0u, 0u, 0u, 0u);
+}
+// v <- bf16(bf16(v) + residual): the two roundings of `residual + linear(x)` with a bf16 linear output (LlamaDecoderLayer,
+// BertSelfOutput / BertOutput); columns past n_out (ragged last tile, N % 8 == 0) are left alone
+__device__ __forceinline__ void apply_residual(float (&v)[32], const uint4 (&w)[4], int col0, int n_out) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (col0 + 8 * i + 8 <= n_out) {
-      const uint4 w = __ldg(reinterpret_cast<const uint4*>(rrow + col0 + 8 * i));
-      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+      const uint32_t ww[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[j]));
@@ -235,6 +245,11 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const bool ok_even = m_even < p.M, ok_odd = m_even + 1 < p.M;
       __nv_bfloat16* row_even = p.out + (ok_even ? m_even : 0) * p.ldo;
       __nv_bfloat16* row_odd = p.out + (ok_odd ? m_even + 1 : 0) * p.ldo;
+      const __nv_bfloat16* rrow = nullptr;  // this thread's residual row (plain epilogue with a residual only)
+      if (EPI == LLM_GEMM_PLAIN && p.resid && m_even + (lane & 1) < p.M) {
+        rrow = p.resid + (m_even + (lane & 1)) * p.ldr;
+        prefetch_residual(rrow, un.nt * TNP, TNP, p.n_out);
+      }
       mbar_wait(&acc_full[a], (ui >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem + lane_addr + a * TNP;
@@ -345,8 +360,8 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
         }
       } else {
-        const long long m_own = m_even + (lane & 1);
-        const __nv_bfloat16* rrow = (p.resid && m_own < p.M) ? p.resid + m_own * p.ldr : nullptr;
+        uint4 rw[4];
+        if (rrow) load_residual(rw, rrow, un.nt * TNP, p.n_out);
 #pragma unroll 1
         for (int c = 0; c < TNP / 32; ++c) {
           uint32_t r[32];
@@ -371,7 +386,10 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               }
             }
           }
-          if (rrow) add_residual(v, rrow, col0, p.n_out);
+          if (rrow) {  // the chunk's residual values were requested one iteration ago; request the next chunk's now
+            apply_residual(v, rw, col0, p.n_out);
+            if (c + 1 < TNP / 32) load_residual(rw, rrow, col0 + 32, p.n_out);
+          }
           uint32_t o[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = pack_out<EPI>(v[2 * i], v[2 * i + 1]);
@@ -512,6 +530,11 @@ llm_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const bool ok_even = m_even < p.M, ok_odd = m_even + 1 < p.M;
       __nv_bfloat16* row_even = p.out + (ok_even ? m_even : 0) * p.ldo;
       __nv_bfloat16* row_odd = p.out + (ok_odd ? m_even + 1 : 0) * p.ldo;
+      const __nv_bfloat16* rrow = nullptr;
+      if (EPI == LLM_GEMM_PLAIN && p.resid && m_even + (lane & 1) < p.M) {
+        rrow = p.resid + (m_even + (lane & 1)) * p.ldr;
+        prefetch_residual(rrow, un.nt * 512 + j * TNP, TNP, p.n_out);
+      }
       mbar_wait(&acc_full, ui & 1);
       tc_fence_after();
       {
@@ -535,8 +558,8 @@ llm_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             store_chunk(row_even, row_odd, ok_even, ok_odd, col0, p.n_out, o, lane);
           }
         } else {
-          const long long m_own = m_even + (lane & 1);
-          const __nv_bfloat16* rrow = (p.resid && m_own < p.M) ? p.resid + m_own * p.ldr : nullptr;
+          uint4 rw[4];
+          if (rrow) load_residual(rw, rrow, un.nt * 512 + j * TNP, p.n_out);
 #pragma unroll 1
           for (int c = 0; c < TNP / 32; ++c) {
             uint32_t r[32];
@@ -548,7 +571,8 @@ llm_gemm_wide_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
               float v[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-              add_residual(v, rrow, col0, p.n_out);
+              apply_residual(v, rw, col0, p.n_out);
+              if (c + 1 < TNP / 32) load_residual(rw, rrow, col0 + 32, p.n_out);
 #pragma unroll
               for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
             } else {

@@ -49,12 +49,18 @@ def _gemm_ok(x, w) -> bool:
             and w.shape[1] % 8 == 0 and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0)
 
 
+def _on_cublas(name: str) -> bool:
+    """A/B knob: SDAG_CUBLAS_PROJ=o,down,... sends the named prefill projections back to cuBLAS (+ stand-alone glue)."""
+    return name.split("+")[0] in CUBLAS_PROJ
+
+
 def _linear(x, w, bias, residual=None, prefill: bool = True, name: str = "linear"):
     """``F.linear(x, w, bias)`` (+ ``residual``, added with the bf16 roundings of ``residual + linear(x)``) for bf16
     ``x [rows, K]``.  The prefill runs every projection on this library's CTA-pair tcgen05 GEMM (``llm_gemm`` /
     ``llm_gemm_residual``); the few-row GEMMs of a decode step with more than two prompts stay on cuBLAS, where a
     256-row tile would be almost empty (``prefill=False``)."""
-    if prefill and USE_PAIR_GEMM and _gemm_ok(x, w) and (residual is None or (residual.stride(1) == 1 and residual.stride(0) % 8 == 0)):
+    if (prefill and USE_PAIR_GEMM and not _on_cublas(name) and _gemm_ok(x, w)
+            and (residual is None or (residual.stride(1) == 1 and residual.stride(0) % 8 == 0))):
         lib = _lib.load()
         N, K = w.shape
         out = torch.empty((x.shape[0], N), dtype=torch.bfloat16, device=x.device)
@@ -68,9 +74,10 @@ def _linear(x, w, bias, residual=None, prefill: bool = True, name: str = "linear
                                                  residual.stride(0), out.data_ptr(), N, x.shape[0], N, K,
                                                  _lib.stream_ptr(x.device)), "llm_gemm_residual")
         return out
-    if prefill and USE_PAIR_GEMM:
+    if prefill and USE_PAIR_GEMM and not _on_cublas(name):
         _lib.note_fallback("llama_runner._linear", "operand layout not accepted by llm_gemm: cuBLAS")
-    y = F.linear(x, w, bias)
+    with _GemmTimer(name + " (cuBLAS)", x.shape[0], w.shape[0], w.shape[1]):
+        y = F.linear(x, w, bias)
     return y if residual is None else y + residual
 
 
@@ -214,7 +221,7 @@ class FusedPrefill:
         last_rows = torch.arange(B, device=dev) * L + ((lengths - 1) if lengths is not None else (L - 1))
         n_layers = len(self.layers)
         per_tile = 256 // D
-        fused_qkv = (FUSED_ROPE_GEMM and USE_PAIR_GEMM and H % per_tile == 0 and Hkv % per_tile == 0 and self.hidden % 8 == 0)
+        fused_qkv = (FUSED_ROPE_GEMM and USE_PAIR_GEMM and not _on_cublas("qkv") and H % per_tile == 0 and Hkv % per_tile == 0 and self.hidden % 8 == 0)
         for i, ly in enumerate(self.layers):
             q = torch.empty((B, L, H, D), dtype=torch.bfloat16, device=dev)
             if kv is not None:
@@ -255,16 +262,16 @@ class FusedPrefill:
         lib = _lib.load()
         ly = self.layers[i]
         inner = self.model.model
-        if prefill and USE_PAIR_GEMM:
+        if prefill and USE_PAIR_GEMM and not _on_cublas("o"):
             resid = _linear(attn_rows, ly["wo"], ly["bo"], residual=resid, name="o+residual")
             _, normed = _rmsnorm(resid, None, ly["w_post"], ly["eps_post"])
         else:
-            o = _linear(attn_rows, ly["wo"], ly["bo"], prefill=prefill)
+            o = _linear(attn_rows, ly["wo"], ly["bo"], prefill=prefill, name="o")
             resid, normed = _rmsnorm(o, resid, ly["w_post"], ly["eps_post"])
         rows = normed.shape[0]
         act = torch.empty((rows, self.inter), dtype=torch.bfloat16, device=normed.device)
         _lib.count_launches(1)
-        if (prefill or rows >= PAIR_GEMM_MIN_ROWS) and USE_PAIR_GEMM and self.inter % 8 == 0:
+        if (prefill or rows >= PAIR_GEMM_MIN_ROWS) and USE_PAIR_GEMM and not _on_cublas("gate_up") and self.inter % 8 == 0:
             # gate/up GEMM on CTA pairs with the SwiGLU in its epilogue: the [rows, 2*inter] intermediate is never written
             with _GemmTimer("gate_up+swiglu", rows, 2 * self.inter, self.hidden):
                 _lib.check(lib.llm_gemm(normed.data_ptr(), normed.stride(0), ly["wgu"].data_ptr(), 0, act.data_ptr(), self.inter,
@@ -274,11 +281,11 @@ class FusedPrefill:
             _lib.check(lib.llm_swiglu(gu.data_ptr(), act.data_ptr(), rows, self.inter, _lib.stream_ptr(gu.device)), "llm_swiglu")
         nw, ne = ((self.layers[i + 1]["w_in"], self.layers[i + 1]["eps_in"]) if i + 1 < len(self.layers)
                   else (inner.norm.weight, inner.norm.variance_epsilon))
-        if prefill and USE_PAIR_GEMM:
+        if prefill and USE_PAIR_GEMM and not _on_cublas("down"):
             resid = _linear(act, ly["wdown"], None, residual=resid, name="down+residual")
             _, normed = _rmsnorm(resid, None, nw, ne)
         else:
-            d = _linear(act, ly["wdown"], None, prefill=prefill)
+            d = _linear(act, ly["wdown"], None, prefill=prefill, name="down")
             resid, normed = _rmsnorm(d, resid, nw, ne)
         return normed, resid
 
@@ -487,6 +494,7 @@ class FusedPrefill:
 
 
 _gemm_events = None  # set to a list to collect (start, end, name, rows, N, K) around every prefill GEMM launch (_GemmTimer)
+CUBLAS_PROJ = {p for p in os.environ.get("SDAG_CUBLAS_PROJ", "").split(",") if p}  # A/B measurements only: e.g. "o,down"
 USE_PAIR_GEMM = os.environ.get("SDAG_PAIR_GEMM", "") != "off"  # "off": cuBLAS for every projection (A/B measurements only)
 PAIR_GEMM_MIN_ROWS = 512  # decode steps of >= this many prompts would use llm_gemm for gate/up (never reached in practice)
 PREFETCH_O_PROJ = os.environ.get("SDAG_L2_PREFETCH", "") == "1"  # decode step: o_proj weights prefetched into L2 during attention (measured 3 % slower: off)

@@ -135,6 +135,28 @@ def gen_attention():
     print("attention cases:", len(out) // 4)
 
 
+class Top2Gaps:
+    """Forward hook on the reference's model: the fp32 gap between the best and the second-best logit at the last position
+    of every forward call — i.e. of every greedy decision, per batch row.  Stored next to the golden token ids so that the
+    GPU tests can hold every prompt to the reference's tokens and excuse a deviation only where the reference's own
+    decision was a near-tie (bf16 attention moves logits by ~1e-2)."""
+
+    def __init__(self, model):
+        self.calls = []
+        self.handle = model.register_forward_hook(self._hook)
+
+    def _hook(self, module, args, output):
+        top = output.logits[:, -1].float().topk(2, dim=-1).values
+        self.calls.append([round(float(x), 6) for x in (top[:, 0] - top[:, 1])])
+
+    def take(self):
+        calls, self.calls = self.calls, []
+        return calls
+
+    def remove(self):
+        self.handle.remove()
+
+
 def gen_generation():
     ref_sdag.TEMPERATURE = 0  # greedy (SURVEY.md Appendix A8: module-level import-time copy)
     tok = synth.make_tokenizer()
@@ -158,9 +180,12 @@ def gen_generation():
             return orig_decode(ids, **kw)
 
         tok.decode = spy
+        gaps = Top2Gaps(model)
         ans = ref_sdag.run_rag_with_doc_isolation(
             model=model, tokenizer=tok, query=synth.SAMPLE_QUERY, malicious_docs=mal, retrieved_docs=retrieved,
             max_new_tokens=6, device="cpu", add_attack_in_rank=rank, ranker=ranker, doc_neighbors_k=nbr_k)
+        top2_gaps = [c[0] for c in gaps.take()]  # one forward call per generated token (prefill, then the loop)
+        gaps.remove()
         tok.decode = orig_decode
         nbrs = ref_sdag.compute_doc_knn_for_docs(ranker, ranked, nbr_k) if nbr_k > 0 else None
         ids = tok(chat, return_tensors="pt").input_ids
@@ -174,7 +199,7 @@ def gen_generation():
         records.append(dict(case=case, retrieved=retrieved, malicious=mal, rank=rank, doc_neighbors_k=nbr_k,
                             chat_sha256=hashlib.sha256(chat.encode()).hexdigest(), L=L, S=S,
                             spans=[list(s) for s in spans], qa_start=qa, ranked_docs=ranked, neighbors=nbrs,
-                            new_token_ids=seen["ids"], answer=ans,
+                            new_token_ids=seen["ids"], top2_gaps=top2_gaps[: len(seen["ids"])], answer=ans,
                             prefill_top_ids=top.indices.tolist(), prefill_top_logits=top.values.tolist(),
                             prefill_logits_absmax=float(logits.abs().max())))
     with open(os.path.join(HERE, "generation.json"), "w") as f:
@@ -305,7 +330,10 @@ def gen_carg():
 
     tok.decode = spy
     raw_prompts = ["Paris is", "The highest mountain above sea level is called", "Honey", "Octopuses have three hearts and"]
+    gaps = Top2Gaps(model)
     raw_out = ref_cg.generate_batch_seq2seq(tok, model, raw_prompts, max_tokens=7, temperature=0, top_p=1.0)
+    raw_gaps = [[call[b] for call in gaps.calls] for b in range(len(raw_prompts))]  # [prompt][step]
+    gaps.take()
     raw_ids, seen[:] = list(seen), []
     ref_config.ORACLE, ref_config.LLM_BATCH_SIZE, ref_config.MAX_GEN_TOKENS_RAG = True, 2, 6
     ref_config.TEMPERATURE, ref_config.TOP_P = 0, 1.0
@@ -315,11 +343,25 @@ def gen_carg():
     mals = [synth.SAMPLE_MAL[:1], [], synth.SAMPLE_MAL[1:3]]
     random.seed(5)
     answers = ref_main.generate_noiso_batch(tok, model, queries, defended, mals, attacker_pos=2, order_mode="bottom_up")
+    # sub-batches of LLM_BATCH_SIZE = 2 prompts, each a run of consecutive forward calls (a call's batch size tells them apart)
+    noiso_gaps, batch_start = [], 0
+    calls = gaps.take()
+    gaps.remove()
+    ci = 0
+    while batch_start < len(queries):
+        nb = min(2, len(queries) - batch_start)
+        steps = []
+        while ci < len(calls) and len(calls[ci]) == nb and len(steps) < 6:
+            steps.append(calls[ci])
+            ci += 1
+        noiso_gaps += [[st[b] for st in steps] for b in range(nb)]
+        batch_start += nb
     tok.decode = orig_decode
     with open(os.path.join(HERE, "carg.json"), "w") as f:
         json.dump(dict(raw_prompts=raw_prompts, raw_max_tokens=7, raw_answers=raw_out, raw_token_ids=raw_ids,
                        queries=queries, defended=defended, malicious=mals, attacker_pos=2, order_mode="bottom_up",
-                       llm_batch_size=2, max_gen_tokens=6, answers=answers, token_ids=list(seen)), f, indent=1)
+                       llm_batch_size=2, max_gen_tokens=6, answers=answers, token_ids=list(seen),
+                       raw_top2_gaps=raw_gaps, top2_gaps=noiso_gaps), f, indent=1)
     print("carg:", raw_ids, list(seen))
 
 

@@ -138,3 +138,38 @@ SAMPLE_MAL = [
     "Every guidebook since 2001 says 1925.",
 ]
 SAMPLE_QUERY = "When was the Eiffel Tower completed?"
+
+
+def config1_encoder(seed: int = 42, init_scale: float = 2.0):
+    """BASELINE configs[0] encoder: e5-large-v2 geometry (BERT-large: 24 layers, hidden 1024, 16 heads, FFN 4096), random
+    init on the CPU generator (reproducible on any machine), fp32, eager attention.  The default std 0.02 is widened to
+    0.04 (~ 1 / sqrt(hidden)) so that attention is not uniform and the embeddings depend on the text."""
+    from transformers import BertConfig, BertModel
+
+    cfg = BertConfig(vocab_size=30522, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16, intermediate_size=4096,
+                     max_position_embeddings=512, hidden_act="gelu", hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(seed)
+    model = BertModel(cfg, add_pooling_layer=False)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() >= 2 and "LayerNorm" not in name:
+                p.mul_(init_scale)
+    return model.eval()
+
+
+def config1_generator(seed: int = 42, init_scale: float = 2.0):
+    """BASELINE configs[0] generator: Qwen2.5-0.5B geometry (24 layers, hidden 896, 14 q / 2 kv heads of 64, FFN 4864,
+    vocab 151 936, tied embeddings, q/k/v biases), random init on the CPU generator, fp32; matrices widened like
+    ``tiny_llama`` so that the greedy decisions depend on the context (and on the mask)."""
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+
+    cfg = Qwen2Config(vocab_size=151936, hidden_size=896, intermediate_size=4864, num_hidden_layers=24, num_attention_heads=14,
+                      num_key_value_heads=2, max_position_embeddings=32768, rope_theta=1000000.0, tie_word_embeddings=True)
+    torch.manual_seed(seed)
+    model = Qwen2ForCausalLM(cfg)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2:
+                p.mul_(init_scale)
+    return model.eval()

@@ -79,6 +79,26 @@ def test_decode_attention_per_prompt_lengths():
         np.testing.assert_allclose(out[b, 0].float().cpu().numpy(), ref, atol=1e-2, rtol=1e-2, err_msg=f"prompt {b}")
 
 
+# Greedy parity rule: every prompt's tokens equal the reference's; a deviation is accepted only at a position where the
+# reference's OWN fp32 decision was a near-tie — the gap between its two best logits (stored with the goldens as
+# ``top2_gaps``) is at most GAP_EXCUSE.  bf16 attention moves these logits by up to ~0.1 (the prefill-logit test below
+# bounds the top-8 values by atol 0.15), so a gap beyond GAP_EXCUSE cannot be explained by rounding.  Tokens after an
+# excused flip follow a different continuation and are not compared.
+GAP_EXCUSE = 0.1
+
+
+def tokens_match_or_excused(mine, ref, gaps, what):
+    """True if equal; False if the first deviation is an excused near-tie; fails the test otherwise."""
+    for t, (a, b) in enumerate(zip(mine, ref)):
+        if a != b:
+            assert t < len(gaps) and gaps[t] <= GAP_EXCUSE, \
+                f"{what}: token {t} is {a}, reference {b}, and the reference's fp32 top-2 logit gap there is {gaps[t] if t < len(gaps) else None}"
+            print(f"[excused flip] {what}: token {t} {a} vs {b}, reference top-2 gap {gaps[t]:.4f}")
+            return False
+    assert len(mine) == len(ref), (what, mine, ref)
+    return True
+
+
 def _records(golden_dir):
     with open(os.path.join(golden_dir, "generation.json")) as f:
         return json.load(f)
@@ -139,12 +159,10 @@ def test_run_rag_with_doc_isolation_greedy_matches_reference_golden(golden_dir):
                                               add_attack_in_rank=r["rank"], ranker=ranker, doc_neighbors_k=r["doc_neighbors_k"])
         tok.decode = orig
         assert len(seen["ids"]) == 7  # one token from the prefill + max_new_tokens (Appendix A7)
-        assert seen["ids"][0] == r["new_token_ids"][0], r["case"]
-        if seen["ids"] == r["new_token_ids"]:
+        if tokens_match_or_excused(seen["ids"], r["new_token_ids"], r["top2_gaps"], r["case"]):
             assert ans == r["answer"]
             agree += 1
-    # a chaotic random-init model may flip a late token under bf16 attention; the bulk must agree exactly
-    assert agree >= len(recs) - 1, agree
+    assert agree >= 2, agree  # the goldens hold two prompts whose every decision has a gap > GAP_EXCUSE
 
 
 def test_generate_with_custom_mask_dense_path_equals_span_path(golden_dir):
@@ -399,16 +417,18 @@ def test_carg_batch_generation_matches_reference_golden(golden_dir):
         noiso_ids = list(seen)
     finally:
         tok.decode = orig
-    same_raw = [a == b for a, b in zip(raw_ids, gold["raw_token_ids"])]
-    assert sum(same_raw) >= len(same_raw) - 1, (raw_ids, gold["raw_token_ids"])
+    assert len(raw_ids) == len(gold["raw_token_ids"]) and len(noiso_ids) == len(gold["token_ids"])
+    same_raw = [tokens_match_or_excused(a, b, g, f"raw prompt {n}")
+                for n, (a, b, g) in enumerate(zip(raw_ids, gold["raw_token_ids"], gold["raw_top2_gaps"]))]
     for ok, mine, ref in zip(same_raw, out, gold["raw_answers"]):
         if ok:
             assert mine == ref
-    same_noiso = [a == b for a, b in zip(noiso_ids, gold["token_ids"])]
-    assert len(noiso_ids) == len(gold["token_ids"]) and sum(same_noiso) >= len(same_noiso) - 1, (noiso_ids, gold["token_ids"])
+    same_noiso = [tokens_match_or_excused(a, b, g, f"noiso prompt {n}")
+                  for n, (a, b, g) in enumerate(zip(noiso_ids, gold["token_ids"], gold["top2_gaps"]))]
     for ok, mine, ref in zip(same_noiso, answers, gold["answers"]):
         if ok:
             assert mine == ref
+    assert sum(same_raw) >= 2 and sum(same_noiso) >= 1
 
 
 def _bf16_model(tok):
@@ -448,10 +468,12 @@ def test_carg_ragged_fused_batch_equals_hf_generate_and_single_runs():
         single_ids = list(seen)
     finally:
         tok.decode = orig
-    eos = tok.eos_token_id
+    from sdag_b200.generation import _eos_ids
+
+    stops = set(_eos_ids(tok, model))  # what HF generate stops on: generation_config.eos_token_id, not the tokenizer's id
 
     def cut(ids):
-        return ids[: ids.index(eos) + 1] if eos in ids else ids
+        return next((ids[: i + 1] for i, t in enumerate(ids) if t in stops), ids)
 
     def first_diff(a, b):
         return next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
