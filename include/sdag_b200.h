@@ -31,6 +31,8 @@ extern "C" {
 
 #define SDAG_TILE 128             /* query rows and key columns per attention tile */
 #define SDAG_PREFILL_NO_UNIFORM_ROWS 1 /* sdag_prefill_fwd flag: no query row is without an allowed key */
+#define SDAG_PREFILL_FORCE_SINGLE 2    /* sdag_prefill_fwd flag: single-CTA kernel even where the CTA-pair kernel applies */
+#define SDAG_PREFILL_FORCE_PAIR 4      /* sdag_prefill_fwd flag: CTA-pair kernel (head_dim 128, H / Hkv even) or SDAG_ERR_UNSUPPORTED */
 #define SDAG_BLOCKMAP_HEADER 16   /* int32 words */
 #define SDAG_LAYOUT_HEADER 8      /* int32 words */
 #define SDAG_MAX_NBR_K 16

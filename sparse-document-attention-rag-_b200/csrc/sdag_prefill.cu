@@ -29,6 +29,9 @@ constexpr int BN = SDAG_TILE;
 constexpr int KV_FLAG_BITMASK = 1;
 constexpr int VSUM_CHUNKS = 32;
 constexpr float RESCALE_TAU = 8.0f;  // log2 units: P stays <= 2^8 with a stale max
+#ifndef SDAG_PREFILL_PAIR_DEFAULT
+#define SDAG_PREFILL_PAIR_DEFAULT 0  // which kernel eligible shapes take when neither a flag nor SDAG_ATTN_PAIR says
+#endif
 
 struct PrefillParams {
   __nv_bfloat16* out;
@@ -937,6 +940,500 @@ int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtenso
   return static_cast<int>(cudaGetLastError());
 }
 
+
+// ================================================================================================================
+// CTA-pair variant (head_dim 128, an even number of query heads per kv head).
+//
+// The single-CTA kernel above is bound by what a cta_group::1 SS-mode MMA costs: a 128 x 64 x 16 Q.K^T instruction takes 80
+// cycles against 32 cycles of math because the 128 x 16 slice of Q is re-read from shared memory every time
+// (probe/mma_rate_probe.cu), which holds dense tiles at ~0.55 of the tensor pipe.  Two query heads of one GQA group share
+// their K / V tiles, so a pair of CTAs on neighbouring SMs can run them as ONE tcgen05.mma.cta_group::2 of M = 256: CTA r
+// of the pair owns head h0 + r (its 128 query rows, its S / P / O rows in its own TMEM, its softmax and epilogue), loads
+// only HALF of every K tile (64 of the 128 kv rows: its half of the N dimension of S = Q.K^T) and HALF of every V tile (64
+// of the 128 d columns: its half of the N dimension of O += P.V), and the leader CTA issues every MMA for both.  Per SM
+// and per 128 x 128 tile the operand traffic from shared memory drops from 2 x (Q slices + K) + V to Q slices + K/2 + V/2
+// and the MMAs run at N = 128, the shape that reaches the full rate on pairs (probe/mma2_rate_probe.cu).
+//
+// One CTA per SM, 512 TMEM columns: S0 / S1 (two 128-column score tiles; P, as bf16 pairs, is written over the first 64
+// columns of the tile it came from), O0 / O1 (the output accumulator is double-buffered across work items, so an item's
+// first P.V never waits for the previous item's epilogue).  Shared memory: Q double-buffered (2 x 32 KiB), four stages of
+// K halves and V halves (16 KiB each), the epilogue's staging rows.  Work items (query tile, head pair, prompt) are dealt
+// round-robin to the clusters, longest first — both CTAs of a pair and every role derive the same sequence, nothing is
+// exchanged for scheduling.  Cross-CTA protocol (same as the retrieval / linear-layer pair kernels): every TMA load
+// completes on the LEADER's `full` barrier (the leader announces the bytes of both CTAs), tcgen05.commit multicasts to the
+// barriers of both CTAs, and the peer's softmax / epilogue warps signal the leader's `p_full` / `o_empty` barriers with
+// one remote arrive per warp.
+//   warps 0-3  softmax (one query row per thread): row maximum over the allowed columns of the 128-column tile, lazy
+//              rescaling, P = exp2(S * scale - m) written back as bf16
+//   warp 4     TMA producer (both CTAs): Q, then K half / V half per tile
+//   warp 5     MMA issuer (leader CTA only)
+//   warps 8-11 epilogue: O / l -> bf16 -> staged, coalesced stores
+// ================================================================================================================
+namespace pairk {
+
+constexpr int KV_STAGES = 4;
+constexpr int Q_BYTES = BM * 128 * 2;  // 128 query rows x 128 d
+constexpr int K_BYTES = 64 * 128 * 2;  // this CTA's 64 of the tile's 128 kv rows x 128 d
+constexpr int V_BYTES = 128 * 64 * 2;  // 128 kv rows x this CTA's 64 of the 128 d columns
+constexpr int OUT_STAGE = 4 * 32 * 80;
+constexpr int SMEM_TOTAL = 2 * Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + OUT_STAGE + 1024;
+constexpr int D = 128;
+
+struct PItem {
+  int q0, nrows, n_kv, h0, b, hkv;
+  int pack, R;  // query heads per CTA (1, or 2 for tiles of <= 64 rows), rows per head in the 128-row tile
+  const int4* kvt;
+  const int32_t* map;
+  bool valid;
+};
+
+// Work item i -> (query tile, head-pair slot, prompt); tiles are the slow index (longest kv lists first).  A slot covers
+// query heads h0 .. h0 + 2 * pack - 1 of one kv group: CTA r takes heads h0 + r * pack ... (+ pack - 1).
+__device__ __forceinline__ PItem fetch_pitem(const PrefillParams& p, long long i) {
+  PItem it;
+  const unsigned slots = static_cast<unsigned>(p.H >> 1);
+  const unsigned per_tile = slots * static_cast<unsigned>(p.B), iu = static_cast<unsigned>(i);
+  const int t = static_cast<int>(iu / per_tile);
+  const int rem = static_cast<int>(iu - static_cast<unsigned>(t) * per_tile);
+  it.b = rem / static_cast<int>(slots);
+  const int slot = rem - it.b * static_cast<int>(slots);
+  it.h0 = 2 * slot;
+  const int G = p.H / p.Hkv;
+  it.hkv = it.h0 / G;
+  it.map = p.blockmaps + static_cast<long long>(it.b) * p.bm_stride_ints;
+  it.valid = t < it.map[0] && it.map[2] == 0;
+  it.q0 = it.nrows = it.n_kv = 0;
+  it.kvt = nullptr;
+  it.pack = 1, it.R = BM;
+  if (it.valid) {
+    const int4 qt = reinterpret_cast<const int4*>(it.map + SDAG_BLOCKMAP_HEADER)[t];
+    it.q0 = qt.x, it.nrows = qt.y, it.n_kv = qt.w;
+    it.kvt = reinterpret_cast<const int4*>(it.map + SDAG_BLOCKMAP_HEADER) + it.map[5] + qt.z;
+    if (it.n_kv > 0 && it.nrows <= 64 && (G % 4) == 0) {
+      it.pack = 2, it.R = 64;
+      if (slot & 1) it.valid = false;  // heads h0 .. h0 + 3 are covered by the item of the even slot
+    }
+  }
+  return it;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ64,
+                         const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const PrefillParams p,
+                         const long long n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                // [2][Q_BYTES]
+  uint8_t* sK = sQ + 2 * Q_BYTES;                    // [KV_STAGES][K_BYTES]
+  uint8_t* sV = sK + KV_STAGES * K_BYTES;            // [KV_STAGES][V_BYTES]
+  uint8_t* sStage = sV + KV_STAGES * V_BYTES;
+  __shared__ uint64_t q_full[2], q_empty[2], k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
+  __shared__ uint64_t s_full[2], p_full[2], pv_done, o_full[2], o_empty[2], l_full[2], l_empty[2];
+  __shared__ float l_buf[2][BM];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const long long cid = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (tid == 0) {
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&q_full[x], 1);    // (leader's copy is live) the leader's producer announces the bytes of both CTAs
+      mbar_init(&q_empty[x], 1);   // multicast commit
+      mbar_init(&s_full[x], 1);    // multicast commit
+      mbar_init(&p_full[x], 8);    // (leader's copy) one arrival per softmax warp of both CTAs
+      mbar_init(&o_full[x], 1);    // multicast commit
+      mbar_init(&o_empty[x], 8);   // (leader's copy) one arrival per epilogue warp of both CTAs
+      mbar_init(&l_full[x], 128);
+      mbar_init(&l_empty[x], 128);
+    }
+    for (int x = 0; x < KV_STAGES; ++x) {
+      mbar_init(&k_full[x], 1);
+      mbar_init(&k_empty[x], 1);
+      mbar_init(&v_full[x], 1);
+      mbar_init(&v_empty[x], 1);
+    }
+    mbar_init(&pv_done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmQ64);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 5) {
+    tmem_alloc_2cta(&tmem_base_s, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit / peer TMA completion
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem_S = tmem;        // + buf * 128
+  const uint32_t tmem_O = tmem + 256;  // + ob * 128
+
+  if (warp >= 8) {
+    // ======================= epilogue warpgroup =======================
+    const int quarter = warp - 8;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t lead_oempty0 = mapa_shared(smem_u32(&o_empty[0]), 0);
+    uint32_t nq = 0;
+    for (long long i = cid; i < n_items; i += n_clusters) {
+      const PItem it = fetch_pitem(p, i);
+      if (!it.valid || it.n_kv == 0) continue;
+      const uint32_t ob = nq & 1;
+      const float* vm = p.vsum + (static_cast<long long>(p.B) * p.Hkv * VSUM_CHUNKS + static_cast<long long>(it.b) * p.Hkv + it.hkv) * D;
+      const int hb = it.h0 + static_cast<int>(rank) * it.pack;
+      const int rr = row & (it.R - 1);
+      const bool valid = rr < it.nrows;
+      constexpr int SROW = 64 + 16;
+      uint8_t* wbase = sStage + quarter * 32 * SROW;
+      uint8_t* srow = wbase + lane * SROW;
+      const int wr = lane >> 2, ch = lane & 3;
+      __nv_bfloat16* orow[4];
+      {
+        const int rshift = 7 - (it.pack >> 1);  // log2(R)
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int trow = quarter * 32 + g8 * 8 + wr;
+          const int orr = trow & (it.R - 1);
+          orow[g8] = orr < it.nrows ? p.out + it.b * p.so_b + static_cast<long long>(it.q0 + orr) * p.so_l +
+                                          (hb + (trow >> rshift)) * p.so_h + ch * 8
+                                    : nullptr;
+        }
+      }
+      mbar_wait(&l_full[ob], (nq >> 1) & 1);
+      const float l = l_buf[ob][row];
+      mbar_arrive(&l_empty[ob]);
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      mbar_wait(&o_full[ob], (nq >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[16];
+#pragma unroll 1
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[16];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          tmem_ld_32x32b_x16(tmem_O + ob * 128 + lane_addr + c * 32 + hh * 16, r);
+          tmem_ld_wait();
+          if (c == D / 32 - 1 && hh == 1) {
+            // every lane of this warp holds its last O values: O[ob] may be overwritten by the item after the next
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(lead_oempty0 + ob * 8);
+          }
+          if (l > 0.f) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2)
+              o[hh * 8 + (e >> 1)] = pack_bf16x2(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const float4 f = valid ? *reinterpret_cast<const float4*>(vm + c * 32 + hh * 16 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+              o[hh * 8 + (e >> 1)] = pack_bf16x2(f.x, f.y);
+              o[hh * 8 + (e >> 1) + 1] = pack_bf16x2(f.z, f.w);
+            }
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(srow);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+        __syncwarp();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (orow[g8]) {
+            const uint4 val = *reinterpret_cast<const uint4*>(wbase + (g8 * 8 + wr) * SROW + ch * 16);
+            *reinterpret_cast<uint4*>(orow[g8] + c * 32) = val;
+          }
+        }
+        __syncwarp();
+      }
+      ++nq;
+    }
+  } else if (warp == 4) {
+    // ======================= TMA producer (both CTAs) =======================
+    const uint32_t lead_qfull0 = mapa_shared(smem_u32(&q_full[0]), 0);
+    const uint32_t lead_kfull0 = mapa_shared(smem_u32(&k_full[0]), 0);
+    const uint32_t lead_vfull0 = mapa_shared(smem_u32(&v_full[0]), 0);
+    uint32_t nq = 0, nkv = 0;
+    for (long long i = cid; i < n_items; i += n_clusters) {
+      const PItem it = fetch_pitem(p, i);
+      if (!it.valid || it.n_kv == 0) continue;
+      const uint32_t qb = nq & 1;
+      const int hb = it.h0 + static_cast<int>(rank) * it.pack;
+      mbar_wait(&q_empty[qb], ((nq >> 1) & 1) ^ 1);
+      {
+        const CUtensorMap* tm = it.pack == 1 ? &tmQ : &tmQ64;
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(&q_full[qb], 2 * Q_BYTES);
+          for (int g = 0; g < it.pack; ++g)
+            for (int dh = 0; dh < 2; ++dh)
+              tma_load_4d_2sm(sQ + qb * Q_BYTES + dh * BM * 128 + g * it.R * 128, tm, lead_qfull0 + qb * 8, dh * 64, it.q0, hb + g, it.b);
+        }
+        __syncwarp();
+      }
+      int4 kt_next = it.kvt[0];
+      for (int j = 0; j < it.n_kv; ++j, ++nkv) {
+        const int4 kt = kt_next;
+        if (j + 1 < it.n_kv) kt_next = it.kvt[j + 1];
+        const uint32_t s = nkv % KV_STAGES;
+        const uint32_t par = ((nkv / KV_STAGES) & 1) ^ 1;
+        mbar_wait(&k_empty[s], par);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(&k_full[s], 2 * K_BYTES);
+          for (int dh = 0; dh < 2; ++dh)
+            tma_load_4d_2sm(sK + s * K_BYTES + dh * 64 * 128, &tmK, lead_kfull0 + s * 8, dh * 64, kt.x + static_cast<int>(rank) * 64, it.hkv, it.b);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[s], par);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(&v_full[s], 2 * V_BYTES);
+          tma_load_4d_2sm(sV + s * V_BYTES, &tmV, lead_vfull0 + s * 8, static_cast<int>(rank) * 64, kt.x, it.hkv, it.b);
+        }
+        __syncwarp();
+      }
+      ++nq;
+    }
+  } else if (warp == 5) {
+    // ======================= MMA issuer (leader CTA only) =======================
+    if (leader) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16_f32(256, 128, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(256, 128, 0, 1);  // B = V, MN-major
+      uint32_t nq = 0, gq = 0, gp = 0;
+      for (long long i = cid; i < n_items; i += n_clusters) {
+        const PItem it = fetch_pitem(p, i);
+        if (!it.valid || it.n_kv == 0) continue;
+        const uint32_t qb = nq & 1, ob = nq & 1;
+        mbar_wait(&q_full[qb], (nq >> 1) & 1);
+        const uint64_t descQ0 = umma_smem_desc_sw128(smem_u32(sQ + qb * Q_BYTES), 16, 1024);
+        int qj = 0, pj = 0;
+        bool first_pv = true;
+        int4 kt_p = it.kvt[0];
+
+        auto issue_qk = [&]() {
+          const uint32_t s = gq % KV_STAGES, buf = gq & 1;
+          mbar_wait_spin(&k_full[s], (gq / KV_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t dk = umma_smem_desc_sw128(smem_u32(sK + s * K_BYTES), 16, 1024);
+          const uint32_t tS = tmem_S + buf * 128;
+          const bool last_qk = qj == it.n_kv - 1;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t off = (ks >> 2) * (BM * 128) + (ks & 3) * 32;
+              const uint32_t offk = (ks >> 2) * (64 * 128) + (ks & 3) * 32;
+              umma_ss_2cta(tS, descQ0 + (off >> 4), dk + (offk >> 4), idesc_qk, ks > 0);
+            }
+            umma_commit_2cta(&k_empty[s], 3);
+            if (last_qk) umma_commit_2cta(&q_empty[qb], 3);
+            umma_commit_2cta(&s_full[buf], 3);
+          }
+          __syncwarp();
+          ++gq;
+          ++qj;
+        };
+        auto issue_pv = [&]() {
+          const int4 kt = kt_p;
+          if (pj + 1 < it.n_kv) kt_p = it.kvt[pj + 1];
+          const uint32_t s = gp % KV_STAGES, buf = gp & 1;
+          mbar_wait_spin(&p_full[buf], (gp >> 1) & 1);
+          mbar_wait_spin(&v_full[s], (gp / KV_STAGES) & 1);
+          if (first_pv && nq >= 2) mbar_wait(&o_empty[ob], ((nq >> 1) - 1) & 1);  // the epilogues of item nq - 2 have read O[ob]
+          tc_fence_after();
+          const int pv_steps = (min(kt.y, BN) + 15) >> 4;
+          const uint64_t dv = umma_smem_desc_sw128(smem_u32(sV + s * V_BYTES), 64 * 128, 1024);
+          const uint32_t tP = tmem_S + buf * 128;
+          const bool last_pv = pj == it.n_kv - 1;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < BN / 16; ++ks)
+              if (ks < pv_steps)
+                umma_ts_2cta(tmem_O + ob * 128, tP + ks * 8, dv + ((ks * 16 * 128) >> 4), idesc_pv, (!first_pv || ks > 0) ? 1u : 0u);
+            umma_commit_2cta(&v_empty[s], 3);
+            umma_commit_2cta(&pv_done, 3);
+            if (last_pv) umma_commit_2cta(&o_full[ob], 3);
+          }
+          __syncwarp();
+          first_pv = false;
+          ++gp;
+          ++pj;
+        };
+
+        issue_qk();
+        if (qj < it.n_kv) issue_qk();
+        while (pj < it.n_kv) {
+          issue_pv();
+          if (qj < it.n_kv) issue_qk();
+        }
+        ++nq;
+      }
+    }
+  } else if (warp < 4) {
+    // ======================= softmax warpgroup =======================
+    const int quarter = warp;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t lead_pfull0 = mapa_shared(smem_u32(&p_full[0]), 0);
+    uint32_t r[32];
+    uint32_t nq = 0, g = 0;
+    for (long long i = cid; i < n_items; i += n_clusters) {
+      const PItem it = fetch_pitem(p, i);
+      if (!it.valid || it.n_kv == 0) continue;
+      const uint32_t ob = nq & 1;
+      const int q0 = it.q0;
+      const int32_t* map = it.map;
+      float m = -INFINITY, l = 0.f;
+      const uint32_t g_item0 = g;
+      const int rr = row & (it.R - 1);
+      const int wrow0 = (quarter * 32) & (it.R - 1);
+      int4 kt_next = it.kvt[0];
+#pragma unroll 1
+      for (int j = 0; j < it.n_kv; ++j, ++g) {
+        const int4 kt = kt_next;
+        if (j + 1 < it.n_kv) kt_next = it.kvt[j + 1];
+        const bool bitmask = (kt.w & KV_FLAG_BITMASK) != 0;
+        uint4 bits = make_uint4(~0u, ~0u, ~0u, ~0u);  // allow bits of the tile's four 32-column chunks
+        if (bitmask) {
+          bits = make_uint4(0u, 0u, 0u, 0u);
+          if (q0 + rr < p.Lq)
+            bits = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(map + map[10]) +
+                                                   static_cast<long long>(q0 + rr) * map[7] + (kt.x >> 5));
+        }
+        const int ncols = min(BN, kt.y);
+        const int doff = kt.z;
+        const int lim = bitmask ? ncols - 1 : min(ncols - 1, rr + doff);           // this row: columns [0, lim] (< 0: none)
+        const int wlim_lo = min(ncols - 1, wrow0 + doff);                            // warp-uniform bounds of lim
+        const int wlim_hi = bitmask ? ncols - 1 : min(ncols - 1, wrow0 + 31 + doff);
+        const bool full = !bitmask && wlim_lo >= BN - 1;
+        const uint32_t buf = g & 1;
+        const uint32_t tS = tmem_S + buf * 128 + lane_addr;
+        mbar_wait_spin(&s_full[buf], (g >> 1) & 1);
+        tc_fence_after();
+        auto chunk_mask = [&](int c) -> uint32_t {  // allowed columns of chunk c for this row
+          const int rel = lim - 32 * c;
+          const uint32_t up_to = rel < 0 ? 0u : (rel >= 31 ? ~0u : ((2u << rel) - 1u));
+          return up_to & (c == 0 ? bits.x : (c == 1 ? bits.y : (c == 2 ? bits.z : bits.w)));
+        };
+        const int n_chunks = wlim_hi < 0 ? 0 : (wlim_hi >> 5) + 1;  // chunks some row of this warp can see (warp-uniform)
+
+        // pass 1: row maximum over the allowed columns
+        float mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          tmem_ld_32x32b_x32(tS + c * 32, r);
+          tmem_ld_wait();
+          if (!full) {
+            const uint32_t am = chunk_mask(c);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) r[e] = (am >> e) & 1u ? r[e] : 0xff800000u;
+          }
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            mxa = fmax3(mxa, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+            mxb = fmax3(mxb, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+          }
+        }
+        const float mx = fmaxf(mxa, mxb) * p.scale_log2;
+        const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf)
+        if (__any_sync(0xffffffffu, need)) {
+          const float alpha = need ? exp2f(m - mx) : 1.f;
+          if (need) m = mx;
+          l *= alpha;
+          if (g != g_item0) {
+            mbar_wait(&pv_done, (g - 1) & 1);  // O holds every earlier P.V of this item once the latest one has landed
+            tc_fence_after();
+            uint32_t t[32];
+#pragma unroll 1
+            for (int oc = 0; oc < D / 32; ++oc) {
+              tmem_ld_32x32b_x32(tmem_O + ob * 128 + lane_addr + oc * 32, t);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) * alpha);
+              tmem_st_32x32b_x32(tmem_O + ob * 128 + lane_addr + oc * 32, t);
+            }
+          }
+        }
+        // pass 2: P = exp2(S * scale - m) as bf16 pairs over the first 64 columns of the same tile (chunk c -> columns
+        // [16 c, 16 c + 16): always behind the columns still to be read)
+        const float neg_m = (m == -INFINITY) ? 0.f : -m;
+        const unsigned long long scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(neg_m, neg_m);
+        unsigned long long lsA = pack2(0.f, 0.f), lsB = lsA;
+        const int pv_chunks = (ncols + 31) >> 5;  // chunks the P.V steps read (16 columns per step)
+#pragma unroll 1
+        for (int c = 0; c < pv_chunks; ++c) {
+          uint32_t pk[16];
+          if (c < n_chunks) {
+            tmem_ld_32x32b_x32(tS + c * 32, r);
+            tmem_ld_wait();
+            if (!full) {
+              const uint32_t am = chunk_mask(c);
+#pragma unroll
+              for (int e = 0; e < 32; ++e) r[e] = (am >> e) & 1u ? r[e] : 0xff800000u;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              float x0, x1, x2, x3;
+              unpack2(fma2(pack2u(r[e], r[e + 1]), scale2, negm2), x0, x1);
+              unpack2(fma2(pack2u(r[e + 2], r[e + 3]), scale2, negm2), x2, x3);
+              const float p0 = exp2f(x0), p1 = exp2f(x1), p2 = exp2f(x2), p3 = exp2f(x3);
+              lsA = add2(lsA, pack2(p0, p1));
+              lsB = add2(lsB, pack2(p2, p3));
+              pk[e >> 1] = pack_bf16x2(p0, p1);
+              pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = 0u;
+          }
+          tmem_st_32x32b_x16(tS + c * 16, pk);
+        }
+        {
+          float a0, a1;
+          unpack2(add2(lsA, lsB), a0, a1);
+          l += a0 + a1;
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(lead_pfull0 + buf * 8);
+      }
+      // hand the row sums to the epilogue warpgroup and move on
+      if (nq >= 2) mbar_wait(&l_empty[ob], ((nq >> 1) - 1) & 1);
+      l_buf[ob][row] = l;
+      mbar_arrive(&l_full[ob]);
+      ++nq;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody may still address the peer's shared memory / TMEM when a CTA tears down
+  if (warp == 5) tmem_dealloc_2cta(tmem, 512);
+}
+
+int launch(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtensorMap& tk, const CUtensorMap& tv128, const PrefillParams& p,
+           int cap_qtiles, cudaStream_t st) {
+  static bool configured[SDAG_MAX_DEVICES] = {};
+  const int dev = device_slot();
+  if (dev < 0) return SDAG_ERR_UNSUPPORTED;
+  if (!configured[dev]) {
+    SDAG_CUDA_TRY(cudaFuncSetAttribute(sdag_prefill_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    configured[dev] = true;
+  }
+  const int n_sm = device_sm_count();
+  const long long n_items = static_cast<long long>(cap_qtiles) * (p.H / 2) * p.B;
+  if (n_items <= 0) return SDAG_ERR_INVALID;
+  const long long clusters = n_items < n_sm / 2 ? n_items : n_sm / 2;
+  sdag_prefill_pair_kernel<<<static_cast<unsigned>(2 * clusters), 384, SMEM_TOTAL, st>>>(tq, tq64, tk, tv128, p, n_items);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace pairk
+
 }  // namespace
 
 extern "C" {
@@ -982,6 +1479,20 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
   if (make_map_4d(&tk, k, D, Skv, Hkv, B, sk_l, sk_h, bs(sk_b, sk_l * Skv), 64)) return SDAG_ERR_DRIVER;  // 64-row halves
   if (make_map_4d(&tv, v, D, Skv, Hkv, B, sv_l, sv_h, bs(sv_b, sv_l * Skv), 64)) return SDAG_ERR_DRIVER;
 
+  // CTA-pair kernel: head_dim 128 and query heads in pairs per kv head; SDAG_PREFILL_FORCE_SINGLE / _FORCE_PAIR pick a
+  // kernel explicitly (tests, A/B), otherwise SDAG_ATTN_PAIR=0 / 1 (read once) or the default below decides
+  static int pair_env = -2;
+  if (pair_env == -2) {
+    const char* e = getenv("SDAG_ATTN_PAIR");
+    pair_env = e ? (atoi(e) ? 1 : 0) : -1;
+  }
+  const bool pair_ok = D == 128 && ((H / Hkv) % 2) == 0;
+  if ((flags & SDAG_PREFILL_FORCE_PAIR) && !pair_ok) return SDAG_ERR_UNSUPPORTED;
+  const bool use_pair = pair_ok && !(flags & SDAG_PREFILL_FORCE_SINGLE) &&
+                        ((flags & SDAG_PREFILL_FORCE_PAIR) || (pair_env >= 0 ? pair_env == 1 : SDAG_PREFILL_PAIR_DEFAULT != 0));
+  CUtensorMap tv128;
+  if (use_pair && make_map_4d(&tv128, v, D, Skv, Hkv, B, sv_l, sv_h, bs(sv_b, sv_l * Skv), 128)) return SDAG_ERR_DRIVER;
+
   PrefillParams p;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.so_b = so_b, p.so_l = so_l, p.so_h = so_h;
@@ -997,6 +1508,7 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
     // caller guarantees every query row has an allowed key (causal / bidirectional maps): no mean-of-V pass, only the
     // work-stealing counter has to be reset
     SDAG_CUDA_TRY(cudaMemsetAsync(p.next_item, 0, sizeof(int), st));
+    if (use_pair) return pairk::launch(tq, tq64, tk, tv128, p, cap_qtiles, st);
     if (D == 128) return launch_prefill<128>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
     return launch_prefill<64>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
   }
@@ -1006,6 +1518,7 @@ int sdag_prefill_fwd(const void* q, int64_t sq_b, int64_t sq_h, int64_t sq_l, co
     v_mean_kernel<128><<<dim3(Hkv, B), 128, 0, st>>>(static_cast<float*>(workspace), B, Hkv, Skv, blockmaps_dev, p.bm_stride_ints,
                                                      p.out, p.so_b, p.so_l, p.so_h, H, Lq);
     SDAG_CUDA_TRY(cudaGetLastError());
+    if (use_pair) return pairk::launch(tq, tq64, tk, tv128, p, cap_qtiles, st);
     return launch_prefill<128>(tq, tq64, tq32, tk, tv, p, cap_qtiles, st);
   }
   v_colsum_kernel<64><<<vgrid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(v), sv_b, sv_h, sv_l, Skv,

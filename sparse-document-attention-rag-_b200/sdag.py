@@ -245,8 +245,11 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 
 
 def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, blockmap: BlockMap,
-                           scaling: Optional[float] = None, ragged: bool = False) -> torch.Tensor:
+                           scaling: Optional[float] = None, ragged: bool = False, kernel: Optional[str] = None) -> torch.Tensor:
     """q ``[B,H,L,D]`` (any strides with unit innermost), k/v ``[B,Hkv,S,D]`` bf16 -> out ``[B,L,H,D]`` bf16.
+
+    ``kernel``: None = the library's choice; ``"pair"`` / ``"single"`` force the CTA-pair kernel (head_dim 128 and an even
+    number of query heads per kv head, else an error) or the single-CTA kernel (tests, A/B measurements).
 
     ``ragged``: the block maps were built for prompts shorter than L (right-padded batch).  Rows past a prompt's end
     are not covered by any tile; they are returned as zeros so that everything downstream of them — in particular the
@@ -279,7 +282,9 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
             out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
             B, H, Hkv, L, S, D, scaling,
             blockmap.buf.data_ptr(), blockmap.stride_bytes if blockmap.n_prompts > 1 else 0, blockmap.launch_qtiles,
-            ws.data_ptr(), ws.numel(), 1 if getattr(blockmap, "no_uniform_rows", False) else 0, _lib.stream_ptr(q.device)),
+            ws.data_ptr(), ws.numel(),
+            (1 if getattr(blockmap, "no_uniform_rows", False) else 0) | {None: 0, "single": 2, "pair": 4}[kernel],
+            _lib.stream_ptr(q.device)),
         "sdag_prefill_fwd",
     )
     if ev is not None:
