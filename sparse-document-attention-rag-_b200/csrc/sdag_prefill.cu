@@ -963,11 +963,11 @@ int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtenso
 // completes on the LEADER's `full` barrier (the leader announces the bytes of both CTAs), tcgen05.commit multicasts to the
 // barriers of both CTAs, and the peer's softmax / epilogue warps signal the leader's `p_full` / `o_empty` barriers with
 // one remote arrive per warp.
-//   warps 0-3  softmax (one query row per thread): row maximum over the allowed columns of the 128-column tile, lazy
-//              rescaling, P = exp2(S * scale - m) written back as bf16
-//   warp 4     TMA producer (both CTAs): Q, then K half / V half per tile
-//   warp 5     MMA issuer (leader CTA only)
-//   warps 8-11 epilogue: O / l -> bf16 -> staged, coalesced stores
+//   warps 0-7   softmax, two threads per query row (columns [0,64) and [64,128) of the 128-column score tile): maximum over
+//               the allowed columns, exchanged between the two threads, lazy rescaling, P = exp2(S * scale - m) as bf16
+//   warp 8      TMA producer (both CTAs): Q, then K half / V half per tile
+//   warp 9      MMA issuer (leader CTA only)
+//   warps 12-15 epilogue: O / l -> bf16 -> staged, coalesced stores
 // ================================================================================================================
 namespace pairk {
 
@@ -978,6 +978,7 @@ constexpr int V_BYTES = 128 * 64 * 2;  // 128 kv rows x this CTA's 64 of the 128
 constexpr int OUT_STAGE = 4 * 32 * 80;
 constexpr int SMEM_TOTAL = 2 * Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + OUT_STAGE + 1024;
 constexpr int D = 128;
+constexpr int THREADS = 512;  // warps 0-7 softmax (two per row: columns [0,64) / [64,128)), 8 producer, 9 issuer, 12-15 epilogue
 
 struct PItem {
   int q0, nrows, n_kv, h0, b, hkv;
@@ -1017,7 +1018,7 @@ __device__ __forceinline__ PItem fetch_pitem(const PrefillParams& p, long long i
   return it;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmQ64,
                          const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const PrefillParams p,
                          const long long n_items) {
@@ -1029,7 +1030,8 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sStage = sV + KV_STAGES * V_BYTES;
   __shared__ uint64_t q_full[2], q_empty[2], k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
   __shared__ uint64_t s_full[2], p_full[2], pv_done, o_full[2], o_empty[2], l_full[2], l_empty[2];
-  __shared__ float l_buf[2][BM];
+  __shared__ float l_buf[2][2][BM];   // [O buffer][column half][row]: partial row sums handed to the epilogue
+  __shared__ float mx_buf[2][2][BM];  // [tile parity][column half][row]: the two threads of a row exchange their maxima
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1042,10 +1044,10 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_init(&q_full[x], 1);    // (leader's copy is live) the leader's producer announces the bytes of both CTAs
       mbar_init(&q_empty[x], 1);   // multicast commit
       mbar_init(&s_full[x], 1);    // multicast commit
-      mbar_init(&p_full[x], 8);    // (leader's copy) one arrival per softmax warp of both CTAs
+      mbar_init(&p_full[x], 16);   // (leader's copy) one arrival per softmax warp (eight per CTA) of both CTAs
       mbar_init(&o_full[x], 1);    // multicast commit
       mbar_init(&o_empty[x], 8);   // (leader's copy) one arrival per epilogue warp of both CTAs
-      mbar_init(&l_full[x], 128);
+      mbar_init(&l_full[x], 256);  // both softmax threads of every row
       mbar_init(&l_empty[x], 128);
     }
     for (int x = 0; x < KV_STAGES; ++x) {
@@ -1061,7 +1063,7 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc_2cta(&tmem_base_s, 512);
     tmem_relinquish_2cta();
   }
@@ -1073,9 +1075,9 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t tmem_S = tmem;        // + buf * 128
   const uint32_t tmem_O = tmem + 256;  // + ob * 128
 
-  if (warp >= 8) {
+  if (warp >= 12) {
     // ======================= epilogue warpgroup =======================
-    const int quarter = warp - 8;
+    const int quarter = warp - 12;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t lead_oempty0 = mapa_shared(smem_u32(&o_empty[0]), 0);
@@ -1105,7 +1107,7 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       }
       mbar_wait(&l_full[ob], (nq >> 1) & 1);
-      const float l = l_buf[ob][row];
+      const float l = l_buf[ob][0][row] + l_buf[ob][1][row];
       mbar_arrive(&l_empty[ob]);
       const float inv = l > 0.f ? 1.f / l : 0.f;
       mbar_wait(&o_full[ob], (nq >> 1) & 1);
@@ -1154,7 +1156,7 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       ++nq;
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ======================= TMA producer (both CTAs) =======================
     const uint32_t lead_qfull0 = mapa_shared(smem_u32(&q_full[0]), 0);
     const uint32_t lead_kfull0 = mapa_shared(smem_u32(&k_full[0]), 0);
@@ -1198,7 +1200,7 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       ++nq;
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ======================= MMA issuer (leader CTA only) =======================
     if (leader) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16_f32(256, 128, 0, 0);
@@ -1272,13 +1274,15 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         ++nq;
       }
     }
-  } else if (warp < 4) {
-    // ======================= softmax warpgroup =======================
-    const int quarter = warp;
+  } else if (warp < 8) {
+    // ======================= softmax: two warpgroups, one per 64-column half of every score tile =======================
+    // (a lone warp per scheduler cannot hide its own MUFU / TMEM latencies: 762 instructions per 128-column tile took
+    // ~2100 cycles; two threads per row — each 64 columns — put two warps on every scheduler)
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t lead_pfull0 = mapa_shared(smem_u32(&p_full[0]), 0);
-    uint32_t r[32];
     uint32_t nq = 0, g = 0;
     for (long long i = cid; i < n_items; i += n_clusters) {
       const PItem it = fetch_pitem(p, i);
@@ -1319,26 +1323,37 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           return up_to & (c == 0 ? bits.x : (c == 1 ? bits.y : (c == 2 ? bits.z : bits.w)));
         };
         const int n_chunks = wlim_hi < 0 ? 0 : (wlim_hi >> 5) + 1;  // chunks some row of this warp can see (warp-uniform)
+        const int c0 = 2 * half;                                     // this thread's chunks: c0, c0 + 1
 
-        // pass 1: row maximum over the allowed columns
+        // This thread's 64 columns go to registers with ONE wait; columns that are not allowed become -inf.
+        uint32_t r[64];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+          if (c0 + cc < n_chunks) tmem_ld_32x32b_x32(tS + (c0 + cc) * 32, r + 32 * cc);
+        tmem_ld_wait();
         float mxa = -INFINITY, mxb = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < n_chunks; ++c) {
-          tmem_ld_32x32b_x32(tS + c * 32, r);
-          tmem_ld_wait();
-          if (!full) {
-            const uint32_t am = chunk_mask(c);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) r[e] = (am >> e) & 1u ? r[e] : 0xff800000u;
-          }
+        for (int cc = 0; cc < 2; ++cc) {
+          if (c0 + cc < n_chunks) {
+            if (!full) {
+              const uint32_t am = chunk_mask(c0 + cc);
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            mxa = fmax3(mxa, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-            mxb = fmax3(mxb, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+              for (int e = 0; e < 32; ++e) r[32 * cc + e] = (am >> e) & 1u ? r[32 * cc + e] : 0xff800000u;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              mxa = fmax3(mxa, __uint_as_float(r[32 * cc + e]), __uint_as_float(r[32 * cc + e + 1]));
+              mxb = fmax3(mxb, __uint_as_float(r[32 * cc + e + 2]), __uint_as_float(r[32 * cc + e + 3]));
+            }
           }
         }
-        const float mx = fmaxf(mxa, mxb) * p.scale_log2;
-        const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf)
+        // row maximum = max over both halves: exchange through shared memory (buffer by tile parity, one barrier per tile;
+        // it also orders this tile's P writes, which land on the other half's score columns, after everybody's loads)
+        const float mine = fmaxf(mxa, mxb);
+        mx_buf[g & 1][half][row] = mine;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mx = fmaxf(mine, mx_buf[g & 1][half ^ 1][row]) * p.scale_log2;
+        const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf); identical in both threads of a row
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? exp2f(m - mx) : 1.f;
           if (need) m = mx;
@@ -1348,48 +1363,43 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             tc_fence_after();
             uint32_t t[32];
 #pragma unroll 1
-            for (int oc = 0; oc < D / 32; ++oc) {
-              tmem_ld_32x32b_x32(tmem_O + ob * 128 + lane_addr + oc * 32, t);
+            for (int oc = 0; oc < 2; ++oc) {  // this thread's half of the row's O columns
+              const uint32_t to = tmem_O + ob * 128 + lane_addr + half * 64 + oc * 32;
+              tmem_ld_32x32b_x32(to, t);
               tmem_ld_wait();
 #pragma unroll
               for (int e = 0; e < 32; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) * alpha);
-              tmem_st_32x32b_x32(tmem_O + ob * 128 + lane_addr + oc * 32, t);
+              tmem_st_32x32b_x32(to, t);
             }
           }
         }
-        // pass 2: P = exp2(S * scale - m) as bf16 pairs over the first 64 columns of the same tile (chunk c -> columns
-        // [16 c, 16 c + 16): always behind the columns still to be read)
         const float neg_m = (m == -INFINITY) ? 0.f : -m;
         const unsigned long long scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(neg_m, neg_m);
         unsigned long long lsA = pack2(0.f, 0.f), lsB = lsA;
         const int pv_chunks = (ncols + 31) >> 5;  // chunks the P.V steps read (16 columns per step)
-#pragma unroll 1
-        for (int c = 0; c < pv_chunks; ++c) {
-          uint32_t pk[16];
-          if (c < n_chunks) {
-            tmem_ld_32x32b_x32(tS + c * 32, r);
-            tmem_ld_wait();
-            if (!full) {
-              const uint32_t am = chunk_mask(c);
 #pragma unroll
-              for (int e = 0; e < 32; ++e) r[e] = (am >> e) & 1u ? r[e] : 0xff800000u;
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = c0 + cc;
+          if (c < pv_chunks) {
+            uint32_t pk[16];
+            if (c < n_chunks) {
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                float x0, x1, x2, x3;
+                unpack2(fma2(pack2u(r[32 * cc + e], r[32 * cc + e + 1]), scale2, negm2), x0, x1);
+                unpack2(fma2(pack2u(r[32 * cc + e + 2], r[32 * cc + e + 3]), scale2, negm2), x2, x3);
+                const float p0 = exp2f(x0), p1 = exp2f(x1), p2 = exp2f(x2), p3 = exp2f(x3);
+                lsA = add2(lsA, pack2(p0, p1));
+                lsB = add2(lsB, pack2(p2, p3));
+                pk[e >> 1] = pack_bf16x2(p0, p1);
+                pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) pk[e] = 0u;
             }
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              float x0, x1, x2, x3;
-              unpack2(fma2(pack2u(r[e], r[e + 1]), scale2, negm2), x0, x1);
-              unpack2(fma2(pack2u(r[e + 2], r[e + 3]), scale2, negm2), x2, x3);
-              const float p0 = exp2f(x0), p1 = exp2f(x1), p2 = exp2f(x2), p3 = exp2f(x3);
-              lsA = add2(lsA, pack2(p0, p1));
-              lsB = add2(lsB, pack2(p2, p3));
-              pk[e >> 1] = pack_bf16x2(p0, p1);
-              pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) pk[e] = 0u;
+            tmem_st_32x32b_x16(tS + c * 16, pk);
           }
-          tmem_st_32x32b_x16(tS + c * 16, pk);
         }
         {
           float a0, a1;
@@ -1401,9 +1411,9 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_pfull0 + buf * 8);
       }
-      // hand the row sums to the epilogue warpgroup and move on
+      // hand the partial row sums to the epilogue warpgroup and move on
       if (nq >= 2) mbar_wait(&l_empty[ob], ((nq >> 1) - 1) & 1);
-      l_buf[ob][row] = l;
+      l_buf[ob][half][row] = l;
       mbar_arrive(&l_full[ob]);
       ++nq;
     }
@@ -1412,7 +1422,7 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // nobody may still address the peer's shared memory / TMEM when a CTA tears down
-  if (warp == 5) tmem_dealloc_2cta(tmem, 512);
+  if (warp == 9) tmem_dealloc_2cta(tmem, 512);
 }
 
 int launch(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtensorMap& tk, const CUtensorMap& tv128, const PrefillParams& p,
@@ -1428,7 +1438,7 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtensorMap& tk
   const long long n_items = static_cast<long long>(cap_qtiles) * (p.H / 2) * p.B;
   if (n_items <= 0) return SDAG_ERR_INVALID;
   const long long clusters = n_items < n_sm / 2 ? n_items : n_sm / 2;
-  sdag_prefill_pair_kernel<<<static_cast<unsigned>(2 * clusters), 384, SMEM_TOTAL, st>>>(tq, tq64, tk, tv128, p, n_items);
+  sdag_prefill_pair_kernel<<<static_cast<unsigned>(2 * clusters), THREADS, SMEM_TOTAL, st>>>(tq, tq64, tk, tv128, p, n_items);
   return static_cast<int>(cudaGetLastError());
 }
 
