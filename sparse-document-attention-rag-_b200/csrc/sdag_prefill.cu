@@ -963,13 +963,35 @@ int launch_prefill(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtenso
 // completes on the LEADER's `full` barrier (the leader announces the bytes of both CTAs), tcgen05.commit multicasts to the
 // barriers of both CTAs, and the peer's softmax / epilogue warps signal the leader's `p_full` / `o_empty` barriers with
 // one remote arrive per warp.
-//   warps 0-7   softmax, two threads per query row (columns [0,64) and [64,128) of the 128-column score tile): maximum over
-//               the allowed columns, exchanged between the two threads, lazy rescaling, P = exp2(S * scale - m) as bf16
-//   warp 8      TMA producer (both CTAs): Q, then K half / V half per tile
-//   warp 9      MMA issuer (leader CTA only)
-//   warps 12-15 epilogue: O / l -> bf16 -> staged, coalesced stores
+//   warps 0-15  softmax, four threads per query row (one 32-column chunk of the 128-column score tile each): maximum over
+//               the allowed columns, exchanged between the four threads, lazy rescaling, P = exp2(S * scale - m) as bf16
+//               (half of the exponentials on the exp unit, half as a cubic on the FMA pipe)
+//   warp 16     TMA producer (both CTAs): Q, then K half / V half per tile
+//   warp 17     MMA issuer (leader CTA only)
+//   warps 20-23 epilogue: O / l -> bf16 -> staged, coalesced stores
 // ================================================================================================================
 namespace pairk {
+
+// 2^x for two values on the FMA pipe (no MUFU): x = n + f with n = rint(x), f in [-0.5, 0.5]; 2^f by the cubic
+// 1 + f (ln2 + f (ln2^2/2 + f ln2^3/6)) (relative error <= 4e-4, a fifth of a bf16 half-ulp — P is stored as bf16), 2^n by
+// adding n to the exponent field.  Inputs are clamped to >= -125 so the exponent field never underflows; masked columns
+// (x = -inf) therefore come out as 2^-125 ~ 2e-38 instead of exactly 0, which is below anything a row sum can see.  The
+// exp unit does 16 results per clock per SM: for a 128 x 128 score tile per SM that is 1024 cycles — as long as the tile's
+// tensor-core work on a CTA pair — so half of every row's exponentials are computed here, on otherwise idle FMA slots.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& o0, float& o1) {
+  const unsigned long long x2 = pack2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+  const unsigned long long t2 = add2(x2, pack2(12582912.f, 12582912.f));  // 1.5 * 2^23: the low mantissa bits now hold rint(x)
+  const unsigned long long n2 = add2(t2, pack2(-12582912.f, -12582912.f));
+  const unsigned long long f2 = fma2(n2, pack2(-1.f, -1.f), x2);
+  unsigned long long q2 = fma2(f2, pack2(0.0555041087f, 0.0555041087f), pack2(0.2402265070f, 0.2402265070f));
+  q2 = fma2(q2, f2, pack2(0.6931471806f, 0.6931471806f));
+  q2 = fma2(q2, f2, pack2(1.f, 1.f));
+  float t0, t1, q0, q1;
+  unpack2(t2, t0, t1);
+  unpack2(q2, q0, q1);
+  o0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  o1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
 
 constexpr int KV_STAGES = 4;
 constexpr int Q_BYTES = BM * 128 * 2;  // 128 query rows x 128 d
@@ -978,7 +1000,8 @@ constexpr int V_BYTES = 128 * 64 * 2;  // 128 kv rows x this CTA's 64 of the 128
 constexpr int OUT_STAGE = 4 * 32 * 80;
 constexpr int SMEM_TOTAL = 2 * Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + OUT_STAGE + 1024;
 constexpr int D = 128;
-constexpr int THREADS = 512;  // warps 0-7 softmax (two per row: columns [0,64) / [64,128)), 8 producer, 9 issuer, 12-15 epilogue
+constexpr int SPLIT = 4;          // softmax threads per query row: each takes one 32-column chunk of the 128-column score tile
+constexpr int THREADS = 768;      // warps 0-15 softmax (warp = part * 4 + row quarter), 16 producer, 17 issuer, 20-23 epilogue
 
 struct PItem {
   int q0, nrows, n_kv, h0, b, hkv;
@@ -1030,8 +1053,8 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint8_t* sStage = sV + KV_STAGES * V_BYTES;
   __shared__ uint64_t q_full[2], q_empty[2], k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
   __shared__ uint64_t s_full[2], p_full[2], pv_done, o_full[2], o_empty[2], l_full[2], l_empty[2];
-  __shared__ float l_buf[2][2][BM];   // [O buffer][column half][row]: partial row sums handed to the epilogue
-  __shared__ float mx_buf[2][2][BM];  // [tile parity][column half][row]: the two threads of a row exchange their maxima
+  __shared__ float l_buf[2][SPLIT][BM];   // [O buffer][column part][row]: partial row sums handed to the epilogue
+  __shared__ float mx_buf[2][SPLIT][BM];  // [tile parity][column part][row]: the threads of a row exchange their maxima
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1044,10 +1067,10 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       mbar_init(&q_full[x], 1);    // (leader's copy is live) the leader's producer announces the bytes of both CTAs
       mbar_init(&q_empty[x], 1);   // multicast commit
       mbar_init(&s_full[x], 1);    // multicast commit
-      mbar_init(&p_full[x], 16);   // (leader's copy) one arrival per softmax warp (eight per CTA) of both CTAs
+      mbar_init(&p_full[x], 8 * SPLIT);  // (leader's copy) one arrival per softmax warp of both CTAs
       mbar_init(&o_full[x], 1);    // multicast commit
       mbar_init(&o_empty[x], 8);   // (leader's copy) one arrival per epilogue warp of both CTAs
-      mbar_init(&l_full[x], 256);  // both softmax threads of every row
+      mbar_init(&l_full[x], 128 * SPLIT);  // every softmax thread of every row
       mbar_init(&l_empty[x], 128);
     }
     for (int x = 0; x < KV_STAGES; ++x) {
@@ -1063,7 +1086,7 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 9) {
+  if (warp == 17) {
     tmem_alloc_2cta(&tmem_base_s, 512);
     tmem_relinquish_2cta();
   }
@@ -1075,9 +1098,12 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const uint32_t tmem_S = tmem;        // + buf * 128
   const uint32_t tmem_O = tmem + 256;  // + ob * 128
 
-  if (warp >= 12) {
+  // Registers: the CTA's pool is what it was launched with, 768 x 80; setmaxnreg re-deals it 16 x 32 x 88 (softmax) +
+  // 4 x 32 x 56 (producer, issuer, two idle warps) + 4 x 32 x 72 (epilogue) = 61 440 exactly — an `inc` beyond the pool blocks forever.
+  if (warp >= 20) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     // ======================= epilogue warpgroup =======================
-    const int quarter = warp - 12;
+    const int quarter = warp - 20;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t lead_oempty0 = mapa_shared(smem_u32(&o_empty[0]), 0);
@@ -1107,7 +1133,9 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
       }
       mbar_wait(&l_full[ob], (nq >> 1) & 1);
-      const float l = l_buf[ob][0][row] + l_buf[ob][1][row];
+      float l = 0.f;
+#pragma unroll
+      for (int sp = 0; sp < SPLIT; ++sp) l += l_buf[ob][sp][row];
       mbar_arrive(&l_empty[ob]);
       const float inv = l > 0.f ? 1.f / l : 0.f;
       mbar_wait(&o_full[ob], (nq >> 1) & 1);
@@ -1156,7 +1184,9 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       ++nq;
     }
-  } else if (warp == 8) {
+  } else if (warp >= 16) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // warps 16-19 (two of them idle) hand registers to the softmax warps
+   if (warp == 16) {
     // ======================= TMA producer (both CTAs) =======================
     const uint32_t lead_qfull0 = mapa_shared(smem_u32(&q_full[0]), 0);
     const uint32_t lead_kfull0 = mapa_shared(smem_u32(&k_full[0]), 0);
@@ -1200,17 +1230,21 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       ++nq;
     }
-  } else if (warp == 9) {
+   } else if (warp == 17) {
     // ======================= MMA issuer (leader CTA only) =======================
     if (leader) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16_f32(256, 128, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(256, 128, 0, 1);  // B = V, MN-major
       uint32_t nq = 0, gq = 0, gp = 0;
+      Tracer tr;
+      TRACE_INIT(tr, 1, lane == 0);
       for (long long i = cid; i < n_items; i += n_clusters) {
         const PItem it = fetch_pitem(p, i);
         if (!it.valid || it.n_kv == 0) continue;
         const uint32_t qb = nq & 1, ob = nq & 1;
+        TRACE(tr, 30);
         mbar_wait(&q_full[qb], (nq >> 1) & 1);
+        TRACE(tr, 31);
         const uint64_t descQ0 = umma_smem_desc_sw128(smem_u32(sQ + qb * Q_BYTES), 16, 1024);
         int qj = 0, pj = 0;
         bool first_pv = true;
@@ -1218,7 +1252,9 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
         auto issue_qk = [&]() {
           const uint32_t s = gq % KV_STAGES, buf = gq & 1;
+          TRACE(tr, 10);
           mbar_wait_spin(&k_full[s], (gq / KV_STAGES) & 1);
+          TRACE(tr, 12);
           tc_fence_after();
           const uint64_t dk = umma_smem_desc_sw128(smem_u32(sK + s * K_BYTES), 16, 1024);
           const uint32_t tS = tmem_S + buf * 128;
@@ -1242,9 +1278,12 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           const int4 kt = kt_p;
           if (pj + 1 < it.n_kv) kt_p = it.kvt[pj + 1];
           const uint32_t s = gp % KV_STAGES, buf = gp & 1;
+          TRACE(tr, 20);
           mbar_wait_spin(&p_full[buf], (gp >> 1) & 1);
+          TRACE(tr, 21);
           mbar_wait_spin(&v_full[s], (gp / KV_STAGES) & 1);
           if (first_pv && nq >= 2) mbar_wait(&o_empty[ob], ((nq >> 1) - 1) & 1);  // the epilogues of item nq - 2 have read O[ob]
+          TRACE(tr, 22);
           tc_fence_after();
           const int pv_steps = (min(kt.y, BN) + 15) >> 4;
           const uint64_t dv = umma_smem_desc_sw128(smem_u32(sV + s * V_BYTES), 64 * 128, 1024);
@@ -1274,16 +1313,20 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         ++nq;
       }
     }
-  } else if (warp < 8) {
-    // ======================= softmax: two warpgroups, one per 64-column half of every score tile =======================
-    // (a lone warp per scheduler cannot hide its own MUFU / TMEM latencies: 762 instructions per 128-column tile took
-    // ~2100 cycles; two threads per row — each 64 columns — put two warps on every scheduler)
+   }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    // ======================= softmax: SPLIT threads per query row, one 32-column chunk of every score tile each ==========
+    // (the instruction stream of one row is a chain of dependent ALU / MUFU / TMEM operations: a lone warp per scheduler ran
+    // its 762 instructions per tile at an IPC of 0.3, two warps at 0.5; four warps per scheduler hide each other's latencies)
     const int quarter = warp & 3;
-    const int half = warp >> 2;
+    const int part = warp >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const uint32_t lead_pfull0 = mapa_shared(smem_u32(&p_full[0]), 0);
     uint32_t nq = 0, g = 0;
+    Tracer tr;
+    TRACE_INIT(tr, 0, tid == 0);
     for (long long i = cid; i < n_items; i += n_clusters) {
       const PItem it = fetch_pitem(p, i);
       if (!it.valid || it.n_kv == 0) continue;
@@ -1315,7 +1358,9 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         const bool full = !bitmask && wlim_lo >= BN - 1;
         const uint32_t buf = g & 1;
         const uint32_t tS = tmem_S + buf * 128 + lane_addr;
+        TRACE(tr, 1);
         mbar_wait_spin(&s_full[buf], (g >> 1) & 1);
+        TRACE(tr, 2);
         tc_fence_after();
         auto chunk_mask = [&](int c) -> uint32_t {  // allowed columns of chunk c for this row
           const int rel = lim - 32 * c;
@@ -1323,37 +1368,38 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           return up_to & (c == 0 ? bits.x : (c == 1 ? bits.y : (c == 2 ? bits.z : bits.w)));
         };
         const int n_chunks = wlim_hi < 0 ? 0 : (wlim_hi >> 5) + 1;  // chunks some row of this warp can see (warp-uniform)
-        const int c0 = 2 * half;                                     // this thread's chunks: c0, c0 + 1
+        const int c = part;  // this thread's chunk: columns [32 c, 32 c + 32)
+        const bool live = c < n_chunks;  // warp-uniform: some row of this warp sees a column of the chunk
 
-        // This thread's 64 columns go to registers with ONE wait; columns that are not allowed become -inf.
-        uint32_t r[64];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
-          if (c0 + cc < n_chunks) tmem_ld_32x32b_x32(tS + (c0 + cc) * 32, r + 32 * cc);
+        uint32_t r[32];
+        if (live) tmem_ld_32x32b_x32(tS + c * 32, r);
         tmem_ld_wait();
+        TRACE(tr, 3);
         float mxa = -INFINITY, mxb = -INFINITY;
+        if (live) {
+          if (!full) {
+            const uint32_t am = chunk_mask(c);
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          if (c0 + cc < n_chunks) {
-            if (!full) {
-              const uint32_t am = chunk_mask(c0 + cc);
+            for (int e = 0; e < 32; ++e) r[e] = (am >> e) & 1u ? r[e] : 0xff800000u;
+          }
 #pragma unroll
-              for (int e = 0; e < 32; ++e) r[32 * cc + e] = (am >> e) & 1u ? r[32 * cc + e] : 0xff800000u;
-            }
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              mxa = fmax3(mxa, __uint_as_float(r[32 * cc + e]), __uint_as_float(r[32 * cc + e + 1]));
-              mxb = fmax3(mxb, __uint_as_float(r[32 * cc + e + 2]), __uint_as_float(r[32 * cc + e + 3]));
-            }
+          for (int e = 0; e < 32; e += 4) {
+            mxa = fmax3(mxa, __uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+            mxb = fmax3(mxb, __uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
           }
         }
-        // row maximum = max over both halves: exchange through shared memory (buffer by tile parity, one barrier per tile;
-        // it also orders this tile's P writes, which land on the other half's score columns, after everybody's loads)
-        const float mine = fmaxf(mxa, mxb);
-        mx_buf[g & 1][half][row] = mine;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float mx = fmaxf(mine, mx_buf[g & 1][half ^ 1][row]) * p.scale_log2;
-        const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf); identical in both threads of a row
+        // row maximum = max over the SPLIT chunks: exchange through shared memory (buffer by tile parity, one barrier per
+        // tile among the warps of this row quarter; it also orders this tile's P writes, which land on other threads' score
+        // columns, after everybody's loads)
+        mx_buf[g & 1][part][row] = fmaxf(mxa, mxb);
+        TRACE(tr, 5);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(32 * SPLIT) : "memory");
+        TRACE(tr, 6);
+        float mx = mx_buf[g & 1][0][row];
+#pragma unroll
+        for (int sp = 1; sp < SPLIT; ++sp) mx = fmaxf(mx, mx_buf[g & 1][sp][row]);
+        mx *= p.scale_log2;
+        const bool need = mx > m + RESCALE_TAU;  // also the first finite maximum (m == -inf); identical in all threads of a row
         if (__any_sync(0xffffffffu, need)) {
           const float alpha = need ? exp2f(m - mx) : 1.f;
           if (need) m = mx;
@@ -1361,59 +1407,55 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           if (g != g_item0) {
             mbar_wait(&pv_done, (g - 1) & 1);  // O holds every earlier P.V of this item once the latest one has landed
             tc_fence_after();
-            uint32_t t[32];
-#pragma unroll 1
-            for (int oc = 0; oc < 2; ++oc) {  // this thread's half of the row's O columns
-              const uint32_t to = tmem_O + ob * 128 + lane_addr + half * 64 + oc * 32;
-              tmem_ld_32x32b_x32(to, t);
-              tmem_ld_wait();
+            uint32_t t[32];  // this thread's share of the row's O columns
+            const uint32_t to = tmem_O + ob * 128 + lane_addr + part * 32;
+            tmem_ld_32x32b_x32(to, t);
+            tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 32; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) * alpha);
-              tmem_st_32x32b_x32(to, t);
-            }
+            for (int e = 0; e < 32; ++e) t[e] = __float_as_uint(__uint_as_float(t[e]) * alpha);
+            tmem_st_32x32b_x32(to, t);
           }
         }
         const float neg_m = (m == -INFINITY) ? 0.f : -m;
         const unsigned long long scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(neg_m, neg_m);
         unsigned long long lsA = pack2(0.f, 0.f), lsB = lsA;
         const int pv_chunks = (ncols + 31) >> 5;  // chunks the P.V steps read (16 columns per step)
+        if (c < pv_chunks) {
+          uint32_t pk[16];
+          if (live) {
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = c0 + cc;
-          if (c < pv_chunks) {
-            uint32_t pk[16];
-            if (c < n_chunks) {
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                float x0, x1, x2, x3;
-                unpack2(fma2(pack2u(r[32 * cc + e], r[32 * cc + e + 1]), scale2, negm2), x0, x1);
-                unpack2(fma2(pack2u(r[32 * cc + e + 2], r[32 * cc + e + 3]), scale2, negm2), x2, x3);
-                const float p0 = exp2f(x0), p1 = exp2f(x1), p2 = exp2f(x2), p3 = exp2f(x3);
-                lsA = add2(lsA, pack2(p0, p1));
-                lsB = add2(lsB, pack2(p2, p3));
-                pk[e >> 1] = pack_bf16x2(p0, p1);
-                pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) pk[e] = 0u;
+            for (int e = 0; e < 32; e += 4) {
+              float x0, x1, x2, x3, p2, p3;
+              unpack2(fma2(pack2u(r[e], r[e + 1]), scale2, negm2), x0, x1);
+              unpack2(fma2(pack2u(r[e + 2], r[e + 3]), scale2, negm2), x2, x3);
+              const float p0 = exp2f(x0), p1 = exp2f(x1);  // exp unit
+              exp2_poly2(x2, x3, p2, p3);                  // FMA pipe
+              lsA = add2(lsA, pack2(p0, p1));
+              lsB = add2(lsB, pack2(p2, p3));
+              pk[e >> 1] = pack_bf16x2(p0, p1);
+              pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
             }
-            tmem_st_32x32b_x16(tS + c * 16, pk);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] = 0u;
           }
+          tmem_st_32x32b_x16(tS + c * 16, pk);
         }
         {
           float a0, a1;
           unpack2(add2(lsA, lsB), a0, a1);
           l += a0 + a1;
         }
+        TRACE(tr, 7);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(lead_pfull0 + buf * 8);
+        TRACE(tr, 4);
       }
       // hand the partial row sums to the epilogue warpgroup and move on
       if (nq >= 2) mbar_wait(&l_empty[ob], ((nq >> 1) - 1) & 1);
-      l_buf[ob][half][row] = l;
+      l_buf[ob][part][row] = (m == -INFINITY) ? 0.f : l;  // a row without any allowed key: the epilogue writes mean(V)
       mbar_arrive(&l_full[ob]);
       ++nq;
     }
@@ -1422,7 +1464,7 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // nobody may still address the peer's shared memory / TMEM when a CTA tears down
-  if (warp == 9) tmem_dealloc_2cta(tmem, 512);
+  if (warp == 17) tmem_dealloc_2cta(tmem, 512);
 }
 
 int launch(const CUtensorMap& tq, const CUtensorMap& tq64, const CUtensorMap& tk, const CUtensorMap& tv128, const PrefillParams& p,
