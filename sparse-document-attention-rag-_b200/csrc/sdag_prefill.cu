@@ -29,6 +29,9 @@ constexpr int BN = SDAG_TILE;
 constexpr int KV_FLAG_BITMASK = 1;
 constexpr int VSUM_CHUNKS = 32;
 constexpr float RESCALE_TAU = 8.0f;  // log2 units: P stays <= 2^8 with a stale max
+#ifndef SDAG_PAIR_POLY
+#define SDAG_PAIR_POLY 1  // pair kernel: half of the exponentials as a cubic on the FMA pipe (0: all on the exp unit)
+#endif
 #ifndef SDAG_PREFILL_PAIR_DEFAULT
 #define SDAG_PREFILL_PAIR_DEFAULT 0  // which kernel eligible shapes take when neither a flag nor SDAG_ATTN_PAIR says
 #endif
@@ -1429,7 +1432,11 @@ sdag_prefill_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
               unpack2(fma2(pack2u(r[e], r[e + 1]), scale2, negm2), x0, x1);
               unpack2(fma2(pack2u(r[e + 2], r[e + 3]), scale2, negm2), x2, x3);
               const float p0 = exp2f(x0), p1 = exp2f(x1);  // exp unit
+#if SDAG_PAIR_POLY
               exp2_poly2(x2, x3, p2, p3);                  // FMA pipe
+#else
+              p2 = exp2f(x2), p3 = exp2f(x3);
+#endif
               lsA = add2(lsA, pack2(p0, p1));
               lsB = add2(lsB, pack2(p2, p3));
               pk[e >> 1] = pack_bf16x2(p0, p1);
