@@ -151,6 +151,16 @@ int topk_merge(const float* scores, const int64_t* ids, int G, int Q, int k, flo
  * (rank-major [G,Q,k,3]) topk_merge_packed merges them into the global top-k with topk_merge's order rule (score
  * descending, then id ascending, padding ids -1 last).  Replaces faiss' single-index heap over the whole corpus,
  * dense.py:83, when the corpus rows are partitioned over GPUs. */
+/* The same exchange as ONE kernel over peer memory (NVLink / NVSwitch), no collective library call: every rank stores
+ * its packed records straight into the receive area of every rank, raises a per-(source rank, block) flag there (release,
+ * system scope), waits for the G flags of its own blocks and merges.  Every rank owns one buffer of
+ * topk_exchange_buffer_bytes(G, Q_cap, k) bytes, ZERO-FILLED ONCE and mapped into all ranks (CUDA peer access / IPC /
+ * symmetric memory); peer_buffers_dev is a device array of the G base addresses as THIS process sees them (entry [rank] = its
+ * own buffer).  epoch >= 1 must increase by one per call, identically on every rank; all ranks must make the call (a rank
+ * that never does lets the others trap after ~2 s instead of hanging).  Q <= Q_cap. */
+size_t topk_exchange_buffer_bytes(int G, int Q_cap, int k);
+int topk_exchange_merge(const float* scores, const int64_t* ids, int Q, int Q_cap, int k, int rank, int G,
+                        const uint64_t* peer_buffers_dev, uint32_t epoch, float* out_scores, int64_t* out_ids, void* stream);
 int topk_pack(const float* scores, const int64_t* ids, int64_t n, void* records, void* stream);
 int topk_merge_packed(const void* records, int G, int Q, int k, float* out_scores, int64_t* out_ids, void* stream);
 

@@ -47,6 +47,8 @@ SIGNATURES = {
     "ip_search_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "ip_search": (_i32, [_vp, _i32, _vp, _vp, _i64, _i32, _i64, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "topk_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "topk_exchange_buffer_bytes": (_sz, [_i32, _i32, _i32]),
+    "topk_exchange_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, C.c_uint32, _vp, _vp, _vp]),
     "topk_pack": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "topk_merge_packed": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "centroid_select": (_i32, [_vp, _vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

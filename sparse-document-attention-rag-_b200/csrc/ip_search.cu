@@ -842,6 +842,119 @@ topk_merge_packed_kernel(const int32_t* __restrict__ rec, int G, int Q, int k, f
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The exchange step of the sharded search as ONE kernel over peer memory (NVLink / NVSwitch), replacing
+// topk_pack -> ncclAllGather -> topk_merge_packed: every rank stores its packed local top-k records straight into the
+// receive buffers of ALL ranks (remote stores through the peer mappings of a symmetric allocation), raises one flag per
+// (source rank, block) in the receiver's flag array with release semantics at system scope, waits for the G flags of its
+// own block and merges them.  Block b of every rank only ever waits for block b of the other ranks, and those raise
+// their flags before they wait for anything, so the kernel cannot deadlock whatever order the blocks are scheduled in;
+// flags carry the call's epoch (they are never reset), the receive area is double-buffered by epoch parity (a rank can
+// be at most one call ahead of a peer: it needs that peer's flag of call n + 1 to get past n + 1).
+// Layout of a rank's symmetric buffer: uint32 flags[G][n_blocks] | pad to 256 B | int32 recv[2][G][Q_cap][k][3].
+// ------------------------------------------------------------------------------------------------
+constexpr int XCHG_QB = 8;  // queries per block
+struct ExchangeParams {
+  const float* scores;
+  const long long* ids;
+  float* out_scores;
+  long long* out_ids;
+  unsigned long long* peers;  // device array of G base addresses (this rank's mapping of every rank's buffer)
+  long long recv_off;         // byte offset of recv[parity] inside a buffer
+  int Q, Q_cap, k, rank, G, n_blocks;
+  uint32_t epoch;
+};
+
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(128)
+topk_exchange_merge_kernel(const ExchangeParams p) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = b * XCHG_QB;
+  const int nq = min(XCHG_QB, p.Q - q0);
+  const int words = nq * p.k * 3;  // int32 words this block contributes per destination
+  // phase 1: my records of these queries -> slot [rank] of every rank's receive area (self included)
+  for (int peer = 0; peer < p.G; ++peer) {
+    int32_t* dst = reinterpret_cast<int32_t*>(p.peers[peer] + p.recv_off) +
+                   (static_cast<long long>(p.rank) * p.Q_cap + q0) * p.k * 3;
+    for (int i = tid; i < words; i += blockDim.x) {
+      const int rec = i / 3, w = i - rec * 3;
+      const long long src = static_cast<long long>(q0) * p.k + rec;
+      const long long id = p.ids[src];
+      dst[i] = w == 0 ? __float_as_int(p.scores[src]) : (w == 1 ? static_cast<int32_t>(id & 0xffffffffll) : static_cast<int32_t>(id >> 32));
+    }
+  }
+  __threadfence_system();  // every thread's remote stores are ordered before the flags below
+  __syncthreads();
+  // phase 2: tell every rank that slot [rank] of block b holds call `epoch`
+  if (tid < p.G) {
+    uint32_t* flags = reinterpret_cast<uint32_t*>(p.peers[tid]);
+    st_release_sys_u32(flags + static_cast<long long>(p.rank) * p.n_blocks + b, p.epoch);
+  }
+  // phase 3: wait for block b of every rank
+  if (tid < p.G) {
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(p.peers[p.rank]) + static_cast<long long>(tid) * p.n_blocks + b;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - p.epoch) < 0) {
+      if (clock64() - t0 > SDAG_SPIN_TRAP_CYCLES) __trap();  // a rank that never calls: fail instead of hanging the box
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  // phase 4: merge G x k records per query (a warp per query): order (score desc, id asc), padding ids (-1) last
+  const int n = p.G * p.k;
+  float* s_all = reinterpret_cast<float*>(dyn);
+  long long* id_all = reinterpret_cast<long long*>(dyn + ((4 * n * 4 + 15) & ~15));
+  float* s = s_all + warp * n;
+  long long* id = id_all + warp * n;
+  const int32_t* recv = reinterpret_cast<const int32_t*>(p.peers[p.rank] + p.recv_off);
+  for (int qq = warp; qq < nq; qq += 4) {
+    const int q = q0 + qq;
+    for (int i = lane; i < n; i += 32) {
+      const int g = i / p.k, j = i - g * p.k;
+      const int32_t* r = recv + ((static_cast<long long>(g) * p.Q_cap + q) * p.k + j) * 3;
+      // written by other GPUs: read past L1 (the same addresses held the records of two calls ago)
+      s[i] = __int_as_float(__ldcv(r));
+      id[i] = static_cast<long long>(static_cast<uint32_t>(__ldcv(r + 1))) | (static_cast<long long>(__ldcv(r + 2)) << 32);
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const float si = s[i];
+      const long long ii = id[i];
+      const bool pad_i = ii < 0;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        const float sj = s[j];
+        const long long ij = id[j];
+        const bool pad_j = ij < 0;
+        bool better;
+        if (pad_i != pad_j)
+          better = pad_i;
+        else if (sj != si)
+          better = sj > si;
+        else if (ij != ii)
+          better = ij < ii;
+        else
+          better = j < i;
+        rank += better;
+      }
+      if (rank < p.k) {
+        p.out_scores[static_cast<long long>(q) * p.k + rank] = pad_i ? -FLT_MAX : si;
+        p.out_ids[static_cast<long long>(q) * p.k + rank] = pad_i ? -1 : ii;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WorkspaceLayout {
@@ -1003,6 +1116,35 @@ int topk_merge_packed(const void* records, int G, int Q, int k, float* out_score
   if (smem > 48 * 1024) return SDAG_ERR_UNSUPPORTED;
   topk_merge_packed_kernel<<<Q, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const int32_t*>(records), G, Q, k, out_scores, reinterpret_cast<long long*>(out_ids));
+  return static_cast<int>(cudaGetLastError());
+}
+
+size_t topk_exchange_buffer_bytes(int G, int Q_cap, int k) {
+  if (G <= 0 || Q_cap <= 0 || k <= 0) return 0;
+  const size_t n_blocks = (static_cast<size_t>(Q_cap) + XCHG_QB - 1) / XCHG_QB;
+  return align_up(static_cast<size_t>(G) * n_blocks * 4, 256) + 2 * static_cast<size_t>(G) * Q_cap * k * 12;
+}
+
+int topk_exchange_merge(const float* scores, const int64_t* ids, int Q, int Q_cap, int k, int rank, int G,
+                        const uint64_t* peer_buffers_dev, uint32_t epoch, float* out_scores, int64_t* out_ids, void* stream) {
+  if (!scores || !ids || !peer_buffers_dev || !out_scores || !out_ids) return SDAG_ERR_INVALID;
+  if (Q <= 0 || Q > Q_cap || k <= 0 || G <= 0 || G > 128 || rank < 0 || rank >= G || epoch == 0) return SDAG_ERR_INVALID;
+  const size_t n = static_cast<size_t>(G) * k;
+  const size_t smem = ((4 * n * 4 + 15) & ~size_t(15)) + 4 * n * 8;
+  if (smem > 48 * 1024) return SDAG_ERR_UNSUPPORTED;
+  ExchangeParams p;
+  p.scores = scores;
+  p.ids = reinterpret_cast<const long long*>(ids);
+  p.out_scores = out_scores;
+  p.out_ids = reinterpret_cast<long long*>(out_ids);
+  p.peers = reinterpret_cast<unsigned long long*>(const_cast<uint64_t*>(peer_buffers_dev));
+  p.Q = Q, p.Q_cap = Q_cap, p.k = k, p.rank = rank, p.G = G;
+  p.n_blocks = (Q_cap + XCHG_QB - 1) / XCHG_QB;
+  p.recv_off = static_cast<long long>(align_up(static_cast<size_t>(G) * p.n_blocks * 4, 256)) +
+               static_cast<long long>(epoch & 1) * G * Q_cap * k * 12;
+  p.epoch = epoch;
+  const int blocks = (Q + XCHG_QB - 1) / XCHG_QB;
+  topk_exchange_merge_kernel<<<blocks, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
   return static_cast<int>(cudaGetLastError());
 }
 

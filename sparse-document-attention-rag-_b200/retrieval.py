@@ -236,11 +236,17 @@ class ShardedFlatIPIndex:
     shard for all queries, one ``all_gather`` moves the local ``[Q,k]`` results, every rank merges ``G*k -> k``
     with the same order rule.  Global id = shard row offset + local row."""
 
-    def __init__(self, local: FlatIPIndex, group=None, merge_fn=None):
+    def __init__(self, local: FlatIPIndex, group=None, merge_fn=None, exchange: Optional[str] = None):
+        """``exchange``: ``"p2p"`` = one kernel over peer memory (``topk_exchange_merge``: remote stores over NVLink into a
+        symmetric allocation, per-block flags, merge — no collective library call), ``"nccl"`` = ``topk_pack`` + one
+        ``all_gather_into_tensor`` + ``topk_merge_packed``; default: the environment variable ``SDAG_EXCHANGE``, else
+        ``"p2p"`` on CUDA (falling back to ``"nccl"``, with a ``note_fallback``, when symmetric memory cannot be set up)."""
         import torch.distributed as dist
 
         self.local = local
         self.group = group
+        self.exchange = exchange or os.environ.get("SDAG_EXCHANGE") or "p2p"
+        self._xchg = None
         # merge of the gathered [G,Q,k] lists; the CUDA kernel unless a test injects a checker for CPU (gloo) runs
         self.merge_fn = merge_fn or merge_topk_device
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -265,6 +271,10 @@ class ShardedFlatIPIndex:
             dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)  # rank-major concatenation
             dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
             return self.merge_fn(gs.view(self.world, Q, k), gi.view(self.world, Q, k), k)
+        if self.exchange == "p2p":
+            out = self._search_exchange_p2p(s, i, k)
+            if out is not None:
+                return out
         # one exchange: 12-byte {score, id} records, one all-gather over NVLink, merge straight from the gathered records
         lib = _lib.load()
         st = _lib.stream_ptr(s.device)
@@ -277,6 +287,42 @@ class ShardedFlatIPIndex:
         out_i = torch.empty((Q, k), dtype=torch.int64, device=s.device)
         _lib.check(lib.topk_merge_packed(gathered.data_ptr(), self.world, Q, k, out_s.data_ptr(), out_i.data_ptr(),
                                          _lib.stream_ptr(s.device)), "topk_merge_packed")
+        return out_s, out_i
+
+    def _search_exchange_p2p(self, s: torch.Tensor, i: torch.Tensor, k: int):
+        """Exchange + merge in one kernel over peer memory; None when the symmetric buffer cannot be set up (every rank
+        takes the same decision: the setup is a collective and fails or succeeds node-wide)."""
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        dev = s.device
+        if self._xchg is None or self._xchg["k"] < k:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                group = self.group if self.group is not None else dist.group.WORLD
+                nbytes = int(lib.topk_exchange_buffer_bytes(self.world, MAX_QUERY_BATCH, k))
+                buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=dev)
+                buf.zero_()
+                hdl = symm_mem.rendezvous(buf, group)
+                hdl.barrier()  # every rank's flags are zero before anybody raises one
+                self._xchg = dict(buf=buf, hdl=hdl, k=k, epoch=0, peers=int(hdl.buffer_ptrs_dev), rank=dist.get_rank(group))
+            except Exception as exc:  # no symmetric memory on this system / build: the NCCL path computes the same result
+                _lib.note_fallback("ShardedFlatIPIndex", "peer-memory exchange unavailable: NCCL all-gather + merge", exc)
+                self.exchange = "nccl"
+                return None
+        x = self._xchg
+        Q = s.shape[0]
+        out_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        s, i = s.contiguous(), i.contiguous()
+        for q0 in range(0, Q, MAX_QUERY_BATCH):
+            q1 = min(Q, q0 + MAX_QUERY_BATCH)
+            x["epoch"] += 1
+            _lib.count_launches(1)
+            _lib.check(lib.topk_exchange_merge(s[q0:q1].data_ptr(), i[q0:q1].data_ptr(), q1 - q0, MAX_QUERY_BATCH, k,
+                                               x["rank"], self.world, x["peers"], x["epoch"], out_s[q0:q1].data_ptr(),
+                                               out_i[q0:q1].data_ptr(), _lib.stream_ptr(dev)), "topk_exchange_merge")
         return out_s, out_i
 
     def search(self, x, k: int):

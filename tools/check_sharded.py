@@ -32,15 +32,30 @@ def main():
     rows = N // world
     lo = rank * rows
     hi = N if rank == world - 1 else lo + rows
-    sharded = ShardedFlatIPIndex(FlatIPIndex.from_device(x[lo:hi].contiguous(), id_offset=lo))
-    s_sh, i_sh = sharded.search_device(xq, k)
     s_full, i_full = FlatIPIndex.from_device(x).search_device(xq, k)
-    ok = bool(torch.equal(i_sh, i_full)) and bool(torch.allclose(s_sh, s_full, rtol=0, atol=1e-6))
-    flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print(f"sharded == single-index top-{k} on {world} GPUs: {'OK' if int(flag) else 'MISMATCH'} "
-              f"(N={N}, Q={Q}, {len(dup)} duplicated rows across shards)")
+    local = FlatIPIndex.from_device(x[lo:hi].contiguous(), id_offset=lo)
+    flag = torch.tensor([1], device=dev)
+    for mode in ("p2p", "nccl"):  # one kernel over peer memory (NVLink) / pack + ncclAllGather + merge
+        sharded = ShardedFlatIPIndex(local, exchange=mode)
+        ok = True
+        for rep in range(5):  # repeated calls: the peer-memory exchange alternates its receive areas by call parity
+            s_sh, i_sh = sharded.search_device(xq, k)
+            ok = ok and bool(torch.equal(i_sh, i_full)) and bool(torch.allclose(s_sh, s_full, rtol=0, atol=1e-6))
+        # exchange step alone: time 50 back-to-back searches of a tiny local index (the exchange dominates)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            sharded.search_device(xq, k)
+        e1.record()
+        torch.cuda.synchronize()
+        f = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        flag = torch.minimum(flag, f)
+        if rank == 0:
+            print(f"[{mode} -> ran as {sharded.exchange}] sharded == single-index top-{k} on {world} GPUs: {'OK' if int(f) else 'MISMATCH'} "
+                  f"(N={N}, Q={Q}, {len(dup)} duplicated rows across shards); {e0.elapsed_time(e1) / 50:.3f} ms per sharded search")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if int(flag) else 1)
