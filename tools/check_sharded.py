@@ -20,7 +20,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    N, d, Q, k = 400_000, 256, 512, 10
+    N, d, Q, k = 400_000, 256, int(os.environ.get('CHECK_Q', '512')), 10
     g = torch.Generator(device=dev).manual_seed(123)  # same corpus on every rank
     x = torch.randn(N, d, generator=g, device=dev)
     x /= x.norm(dim=1, keepdim=True)
@@ -50,12 +50,42 @@ def main():
             sharded.search_device(xq, k)
         e1.record()
         torch.cuda.synchronize()
+        # the exchange step alone, on the local results of the last search (Q x k records per rank)
+        s_loc, i_loc = local.search_device(xq, k)
+        import sdag_b200._lib as L_
+
+        def exchange_only():
+            if sharded.exchange == "p2p":
+                return sharded._search_exchange_p2p(s_loc, i_loc, k)
+            lib = L_.load()
+            rec = torch.empty((Q, k, 3), dtype=torch.int32, device=dev)
+            L_.check(lib.topk_pack(s_loc.data_ptr(), i_loc.data_ptr(), Q * k, rec.data_ptr(), L_.stream_ptr(dev)), "topk_pack")
+            gathered = torch.empty((world, Q, k, 3), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(gathered, rec)
+            o_s = torch.empty((Q, k), dtype=torch.float32, device=dev)
+            o_i = torch.empty((Q, k), dtype=torch.int64, device=dev)
+            L_.check(lib.topk_merge_packed(gathered.data_ptr(), world, Q, k, o_s.data_ptr(), o_i.data_ptr(), L_.stream_ptr(dev)), "merge")
+            return o_s, o_i
+
+        for _ in range(5):
+            exchange_only()
+        torch.cuda.synchronize()
+        dist.barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for _ in range(200):
+            exchange_only()
+        x1.record()
+        torch.cuda.synchronize()
+        xs, xi = exchange_only()
+        ok = ok and bool(torch.equal(xi, i_full))
+        exch_us = x0.elapsed_time(x1) / 200 * 1e3
         f = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(f, op=dist.ReduceOp.MIN)
         flag = torch.minimum(flag, f)
         if rank == 0:
             print(f"[{mode} -> ran as {sharded.exchange}] sharded == single-index top-{k} on {world} GPUs: {'OK' if int(f) else 'MISMATCH'} "
-                  f"(N={N}, Q={Q}, {len(dup)} duplicated rows across shards); {e0.elapsed_time(e1) / 50:.3f} ms per sharded search")
+                  f"(N={N}, Q={Q}, {len(dup)} duplicated rows across shards); {e0.elapsed_time(e1) / 50:.3f} ms per sharded search, exchange + merge alone {exch_us:.1f} us")
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if int(flag) else 1)
