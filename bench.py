@@ -523,7 +523,10 @@ def run_b200(args):
             "scaling": "strong", "dtype": "bf16 tensor-core pass + fp32 exact re-score",
             "config": {"workload": f"configs[2]: {N} x {d} fp32 synthetic corpus (unit Gaussian rows) + bf16 shadow, "
                                    f"{Q}-query batch, k={k}, rows sharded over {world} GPU(s)",
-                       "candidates_per_query": stats[1] / Q, "overflow_queries": stats[0]},
+                       "candidates_per_query": stats[1] / Q, "overflow_queries": stats[0],
+                       "exchange": ("none (one GPU)" if world == 1 else
+                                    {"p2p": "topk_exchange_merge: one kernel over peer memory (remote stores over NVLink + flags + merge)",
+                                     "nccl": "topk_pack + one ncclAllGather of 12-byte records + topk_merge_packed"}[index.exchange])},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "traffic": measured_traffic("ip_gemm_filter_2cta")[0],
                          "frac_of_burst_peak": ach / peak_burst,

@@ -129,11 +129,12 @@ def strict() -> bool:
     return os.environ.get("SDAG_STRICT", "") == "1"
 
 
-def note_fallback(where: str, reason: str, exc: BaseException = None) -> None:
+def note_fallback(where: str, reason: str, exc: BaseException = None, fatal_in_strict: bool = True) -> None:
+    """``fatal_in_strict=False``: an alternative of (nearly) equal cost, recorded but never an error."""
     key = f"{where}: {reason}"
     first = key not in fallbacks
     fallbacks[key] = fallbacks.get(key, 0) + 1
-    if strict():
+    if strict() and fatal_in_strict:
         raise SdagB200Error(f"SDAG_STRICT=1 and the fast path was left at {key}") from exc
     if first:
         _log.warning("sdag_b200 fallback at %s%s", key, f" ({exc!r})" if exc is not None else "")
