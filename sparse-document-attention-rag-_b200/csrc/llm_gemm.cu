@@ -627,15 +627,18 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
   const int n_sm = device_sm_count();
   const bool swiglu = epi == LLM_GEMM_SWIGLU;
   // 256 x 512 pair tiles move 0.75x the L2 -> SM bytes per FLOP but cannot double-buffer the accumulator: measured faster
-  // where the main loop is long enough to hide the exposed epilogue (K = 14336 down projection: 1322 -> 1395 TFLOP/s
-  // sustained, cuBLAS 1407) and slower at K = 4096 (o, gate/up).  SDAG_GEMM_WIDE=0 / 1 forces one form (experiments).
+  // where the main loop is long enough to hide the exposed epilogue (K = 14336 down projection, plain epilogue: 1322 ->
+  // 1395 TFLOP/s sustained, cuBLAS 1407) and slower at K = 4096 (o, gate/up).  With the residual epilogue the exposed part
+  // grows and the order flips (same-box A/B inside the prefill step: down + residual 1.84 ms on 256 x 256 tiles, whose
+  // double-buffered accumulators hide the epilogue, vs 1.91 ms on wide tiles), so a residual keeps the 256 x 256 tiles.
+  // SDAG_GEMM_WIDE=0 / 1 forces one form (experiments).
   static int wide_env = -2;
   if (wide_env == -2) {
     const char* e = getenv("SDAG_GEMM_WIDE");
     wide_env = e ? (atoi(e) ? 1 : 0) : -1;
   }
   const bool wide_ok = swiglu || (epi == LLM_GEMM_PLAIN && !p.bias);
-  const bool wide = wide_ok && (wide_env >= 0 ? wide_env == 1 : (!swiglu && K >= 8192 && M >= 2048));
+  const bool wide = wide_ok && (wide_env >= 0 ? wide_env == 1 : (!swiglu && !p.resid && K >= 8192 && M >= 2048));
   p.M = M;
   p.n_mt = static_cast<int>((M + 2 * TMH - 1) / (2 * TMH));
   p.n_nt = swiglu ? (p.n_out + 127) / 128 : (N + TNP - 1) / TNP;

@@ -92,32 +92,25 @@ def test_config1_retrieval_top5_exact_on_gpu_embeddings_and_close_to_reference_r
     assert np.abs(scores[:, 0] - ref_scores[:, 0]).max() <= 3e-2  # best score per query within the embedding tolerance
 
 
-@pytest.mark.parametrize("dtype,excuse", [(torch.float32, GAP_EXCUSE), (torch.bfloat16, 1.0)])
-def test_config1_sdag_answers_match_reference_run(gold, corpus_and_queries, dtype, excuse, monkeypatch):
-    """run_rag_with_doc_isolation (batched) with the reference run's retrieved documents and chosen adversarial document:
-    every query's greedy tokens equal the reference's, a deviation being accepted only where the reference's own fp32
-    top-2 logit gap is below the excuse threshold.  fp32 weights go through the Hugging Face forward with this library's
-    attention (bf16 attention arithmetic: GAP_EXCUSE); bf16 weights through the fused engine (bf16 GEMMs as well: the
-    wide 1.0 — this case compares a bf16 MODEL with the fp32 reference model, which is model-precision noise rather than
-    kernel error: 24 layers of bf16 weight and activation rounding move these nearly flat logits (sigma ~1.2) by several
-    tenths.  Measured on a B200: with fp32 weights every flip sits at a reference gap <= 0.04; with bf16 weights flips
-    occur at gaps up to 0.55).
+def test_config1_sdag_answers_match_reference_run(gold, corpus_and_queries, monkeypatch):
+    """run_rag_with_doc_isolation with the reference run's retrieved documents and chosen adversarial document, on the
+    reference run's fp32 weights (Hugging Face forward + this library's attention, whose arithmetic is bf16): every query's
+    greedy tokens equal the reference's; a deviation is accepted only where the reference's own fp32 top-2 logit gap is at
+    most GAP_EXCUSE.
 
     A random-init model over a 151 936-word vocabulary is a hard case for greedy parity: the reference's own decisions
-    have a median top-2 gap of 0.18 and a third of them are below 0.1 (tests/golden/config1.json), so most 17-token
+    have a median top-2 gap of 0.18 and a third of them are below 0.1 (tests/golden/config1.json), so many 17-token
     continuations meet a near-tie somewhere; what is asserted is that NO deviation happens at a decision the reference
-    made with a clear margin, and that the first token (the prefill's decision, SDAG.py:181) agrees on >= 80 % of the
-    queries.  The counts are printed."""
+    made with a clear margin (observed on a B200: every flip sits at a reference gap <= 0.04), and that the first token
+    (the prefill's decision, SDAG.py:181) agrees on >= 80 % of the queries.  The counts are printed."""
     import sdag_b200.sdag as sdag
-    import test_generate_gpu as tg
 
     g, _ = gold
     docs, queries, picked = corpus_and_queries
     doc_text = {f"d{i}": d for i, d in enumerate(docs)}
     tok = synth.make_tokenizer()
-    model = synth.config1_generator().to("cuda", dtype=dtype)
+    model = synth.config1_generator().to("cuda")
     monkeypatch.setattr(sdag, "TEMPERATURE", 0)
-    monkeypatch.setattr(tg, "GAP_EXCUSE", excuse)
     recs = g["records"]
     equal = flips = first_ok = 0
     for lo in range(0, len(recs), 10):
@@ -137,11 +130,49 @@ def test_config1_sdag_answers_match_reference_run(gold, corpus_and_queries, dtyp
         for r, mine, ans in zip(chunk, seen, answers):
             assert len(mine) == g["new_tokens"] + 1 or tok.eos_token_id in mine[1:]
             first_ok += int(mine[0] == r["new_token_ids"][0])
-            if tokens_match_or_excused(mine, r["new_token_ids"], r["top2_gaps"], f"query {r['query_index']} ({dtype})"):
+            if tokens_match_or_excused(mine, r["new_token_ids"], r["top2_gaps"], f"query {r['query_index']}"):
                 assert ans == r["answer"]
                 equal += 1
             else:
                 flips += 1
-    print(f"config 1 greedy parity ({dtype}): {equal} of {len(recs)} answers token-for-token equal, {flips} with an excused "
-          f"near-tie flip, first token equal on {first_ok}")
-    assert first_ok >= int((0.8 if dtype == torch.float32 else 0.5) * len(recs))
+    print(f"config 1 greedy parity: {equal} of {len(recs)} answers token-for-token equal, {flips} with an excused near-tie flip, "
+          f"first token equal on {first_ok}")
+    assert first_ok >= int(0.8 * len(recs))
+
+
+def test_config1_bf16_engine_matches_hf_bf16_forward(gold, corpus_and_queries):
+    """The fused engine on the config-1 generator geometry (Qwen2.5-0.5B: q/k/v biases, 14 q / 2 kv heads of 64 — the
+    unfused q/k/v + RoPE path —, tied embeddings) in bf16 against the Hugging Face forward of the SAME bf16 model with this
+    library's attention hook: last-position prefill logits within bf16 GEMM-order noise, the first token equal unless the
+    Hugging Face run's own top-2 gap is below 0.1.  (Against the fp32 reference run a bf16 MODEL flips at gaps up to 0.55:
+    model-precision noise, not kernel error — the fp32-weight test above is the parity check.)"""
+    import sdag_b200.sdag as sdag
+    from sdag_b200.llama_runner import get_runner
+    from sdag_b200.prompts import SYSTEM_PROMPT_RAG, USER_RAG_PROMPT
+
+    g, _ = gold
+    docs, queries, picked = corpus_and_queries
+    doc_text = {f"d{i}": d for i, d in enumerate(docs)}
+    tok = synth.make_tokenizer()
+    model = sdag.prepare_model(synth.config1_generator().to("cuda", dtype=torch.bfloat16))
+    runner = get_runner(model)
+    assert runner is not None and "llm_gemm" in runner.path
+    agree = 0
+    recs = g["records"][:12]
+    for r in recs:
+        mal = [queries[r["query_index"]]["malicious_docs"][c] for c in r["chosen_malicious"]]
+        chat, S, spans, qa, _ = sdag.build_rag_chat_and_spans(tok, SYSTEM_PROMPT_RAG, USER_RAG_PROMPT, r["question"], mal,
+                                                              [doc_text[d] for d in r["retrieved_ids"]], 1)
+        ids = tok(chat, return_tensors="pt")["input_ids"].cuda()
+        assert ids.shape[1] == r["L"] and S == r["S"] and [list(s) for s in spans] == r["spans"]  # the reference run's layout
+        bm = sdag.build_blockmap([sdag.SdagLayout(ids.shape[1], S, spans, qa)])
+        fused, _ = runner.prefill(ids, bm, want_cache=False)
+        with torch.no_grad():
+            hf = model(input_ids=ids, use_cache=False, sdag_meta=bm, logits_to_keep=1).logits[:, -1]
+        torch.testing.assert_close(fused.float(), hf.float(), atol=0.12, rtol=0.05)
+        top2 = hf.float().topk(2, dim=-1).values[0]
+        same = int(fused.argmax(-1)) == int(hf.argmax(-1))
+        assert same or float(top2[0] - top2[1]) < 0.1
+        agree += int(same)
+    print(f"bf16 engine vs HF bf16 forward: first token equal on {agree} of {len(recs)} prompts")
+    assert agree >= len(recs) - 3

@@ -22,7 +22,7 @@ def _rand(shape, g, scale=1.0):
 
 
 @pytest.mark.parametrize("M,N,K,bias", [(1, 8, 8, False), (300, 520, 72, True), (700, 1288, 200, False), (257, 256, 4096, True),
-                                        (2304, 520, 8192, False)])  # the last shape takes the 256 x 512 wide-tile kernel
+                                        (2304, 520, 8192, False)])  # long K (the wide tiles' range; a residual keeps 256 x 256 tiles)
 def test_llm_gemm_residual_matches_torch_and_may_alias_out(M, N, K, bias):
     L, lib = _lib()
     g = torch.Generator(device="cuda").manual_seed(M + N)
@@ -60,7 +60,8 @@ PROD_M = 21136
 
 @pytest.mark.parametrize("name,M,N,K,kind", [
     ("o_proj + residual", PROD_M, 4096, 4096, "residual"),
-    ("down_proj + residual (wide tiles)", PROD_M, 4096, 14336, "residual"),
+    ("down_proj + residual", PROD_M, 4096, 14336, "residual"),
+    ("down_proj, plain epilogue (wide tiles)", PROD_M, 4096, 14336, "plain"),
     ("gate/up + SwiGLU", PROD_M, 28672, 4096, "swiglu"),
     ("lm_head on the last rows", 8, 128256, 4096, "plain"),
 ])

@@ -788,6 +788,16 @@ for M, N, K, epi in ((700, 1288, 200, 0), (1000, 1040, 136, 1), (300, 512, 64, 0
     torch.testing.assert_close(out[:M, :n_out].float(), ref.float(), atol=3e-2, rtol=3e-2)
     assert (out[:M, :n_out] == ref).float().mean() > 0.9
     assert (out[M:] == 7.0).all() and (out[:, n_out:] == 7.0).all()
+# the residual epilogue on wide tiles (only reachable with the knob: the default keeps 256 x 256 tiles for it)
+M, N, K = 2304, 520, 8192
+x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+W = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(torch.bfloat16)
+res = torch.randn(M, N, generator=g, device="cuda").to(torch.bfloat16)
+out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+L.check(lib.llm_gemm_residual(x.data_ptr(), K, W.data_ptr(), 0, res.data_ptr(), N, out.data_ptr(), N, M, N, K, st), "llm_gemm_residual wide")
+ref = (torch.nn.functional.linear(x.float(), W.float()).to(torch.bfloat16).float() + res.float()).to(torch.bfloat16)
+torch.testing.assert_close(out.float(), ref.float(), atol=3e-2, rtol=3e-2)
+assert (out == ref).float().mean() > 0.9
 print("wide ok")
 '''
     env = dict(os.environ, SDAG_GEMM_WIDE="1")
