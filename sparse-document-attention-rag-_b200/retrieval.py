@@ -412,7 +412,7 @@ def read_flat_ip_file(path: str, device="cuda", **kw) -> FlatIPIndex:
     for r0 in range(0, x.shape[0], 1 << 20):  # 1M-row pieces: bounded pinned staging, storage sized once
         if r0 == 0 and x.shape[0] > (1 << 20):
             idx.reserve(x.shape[0])
-        idx.add(np.ascontiguousarray(x[r0 : r0 + (1 << 20)]))
+        idx.add(np.array(x[r0 : r0 + (1 << 20)], dtype=np.float32))  # a writable copy of the mapped piece
     return idx
 
 
