@@ -37,6 +37,7 @@ constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024;
 constexpr int SORT_MAX = 2048;
 constexpr int SCAN_SLICES = 32;
 constexpr long long IP_FAST_GROWTH_ROWS = 65536;  // the swept prefix grows x4 per epoch below this many rows, x2 above
+constexpr uint32_t ROW_EXACT = 0x80000000u;  // Cand.row bit: .score already is the exact fp32 score (rows are < 2^31)
 constexpr int SELECT_MAX_K = 32;  // tighten: k-th best by k max-extraction rounds up to this k, bitonic sort above
 // |bf16(x).bf16(q) - x.q| <= (2u + u^2) |x||q| with u = 2^-8, plus fp32 accumulation slack
 constexpr float ERR_COEF = 0.0078125f + 0.00048828125f;
@@ -49,6 +50,7 @@ struct Cand {
 struct SearchState {   // device arrays, all indexed by query
   float* thr;          // current emission threshold (bf16-score domain)
   int32_t* cnt;        // candidates appended (may exceed cap -> overflow)
+  int32_t* cnt_done;   // cnt as the last tighten left it (stable while the next epoch's filter appends behind it)
   int32_t* overflow;   // sticky flag
   float* qnorm;        // |q|
   Cand* cand;          // [Q][cap]
@@ -492,6 +494,7 @@ tighten_kernel(SearchState st, int k, int force_cnt, const float* __restrict__ m
   if (threadIdx.x == 0) {
     st.thr[q] = thr;
     st.cnt[q] = n_keep_s;
+    st.cnt_done[q] = n_keep_s;
   }
 }
 
@@ -556,6 +559,7 @@ tighten_warp_kernel(SearchState st, int Q, int k, const float* __restrict__ max_
     if (lane == 0) {
       st.thr[q] = thr;
       st.cnt[q] = keep;
+      st.cnt_done[q] = keep;
     }
     return;
   }
@@ -588,6 +592,7 @@ tighten_warp_kernel(SearchState st, int Q, int k, const float* __restrict__ max_
   if (lane == 0) {
     st.thr[q] = thr;
     st.cnt[q] = keep;
+    st.cnt_done[q] = keep;
   }
 }
 
@@ -691,6 +696,35 @@ exact_scan_kernel(SearchState st, int Q, const float* __restrict__ xq, const flo
   }
 }
 
+// Exact re-scoring ahead of time: the candidates that survived the tighten before the LAST epoch (about seven eighths of
+// the final list) get their exact fp32 score now, on a second stream, while the last epoch's GEMM — which leaves HBM ~95 %
+// idle — sweeps the rest of the corpus and appends behind cnt_done.  The exact score replaces the bf16 one in place and
+// the row is tagged ROW_EXACT; the last tighten may treat such a score like any other (|stored - exact| <= e holds for
+// both kinds, which is all its bound needs), and rescore_topk below only computes what is still untagged.  Re-scoring is
+// 4 KB of row per candidate, ~100 candidates per query: 275 us per 4096-query search when it ran after the sweep, whatever
+// the shard size (profiles/r02_topk_dram.md).
+__global__ void __launch_bounds__(256)
+rescore_partial_kernel(SearchState st, const float* __restrict__ xq, const float* __restrict__ corpus_f32,
+                       const __nv_bfloat16* __restrict__ corpus_bf16, int d) {
+  extern __shared__ __align__(16) uint8_t dyn[];
+  float* sq = reinterpret_cast<float*>(dyn);
+  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (st.overflow[q]) return;  // redone by exact_scan anyway
+  int n = st.cnt_done[q];
+  if (n > st.cap) n = st.cap;
+  if (n == 0) return;
+  for (int j = tid; j < d; j += blockDim.x) sq[j] = xq[static_cast<long long>(q) * d + j];
+  __syncthreads();
+  Cand* cq = st.cand + static_cast<long long>(q) * st.cap;
+  for (int i = warp; i < n; i += blockDim.x / 32) {
+    const Cand c = cq[i];
+    if (c.row < 0) continue;  // already exact
+    const float s = corpus_f32 ? warp_dot_f32(corpus_f32 + static_cast<long long>(c.row) * d, sq, d, lane)
+                               : warp_dot_bf16(corpus_bf16 + static_cast<long long>(c.row) * d, sq, d, lane);
+    if (lane == 0) cq[i] = Cand{s, static_cast<int32_t>(static_cast<uint32_t>(c.row) | ROW_EXACT)};
+  }
+}
+
 // Exact re-scoring of the candidates and the final ordered top-k.
 __global__ void __launch_bounds__(256)
 rescore_topk_kernel(SearchState st, const float* __restrict__ xq, const float* __restrict__ corpus_f32,
@@ -708,13 +742,16 @@ rescore_topk_kernel(SearchState st, const float* __restrict__ xq, const float* _
   __syncthreads();
   const Cand* cq = st.cand + static_cast<long long>(q) * st.cap;
   for (int i = warp; i < n; i += blockDim.x / 32) {
-    const int row = cq[i].row;
+    const Cand c = cq[i];
     unsigned long long key = 0;
-    if (row >= 0) {
-      const float s = corpus_f32 ? warp_dot_f32(corpus_f32 + static_cast<long long>(row) * d, sq, d, lane)
-                                 : warp_dot_bf16(corpus_bf16 + static_cast<long long>(row) * d, sq, d, lane);
+    if (c.row != -1) {  // -1: padding written by exact_scan
+      const uint32_t row = static_cast<uint32_t>(c.row) & ~ROW_EXACT;
+      float s = c.score;  // tagged: scored by rescore_partial_kernel while the last epoch was running
+      if (c.row >= 0)
+        s = corpus_f32 ? warp_dot_f32(corpus_f32 + static_cast<long long>(row) * d, sq, d, lane)
+                       : warp_dot_bf16(corpus_bf16 + static_cast<long long>(row) * d, sq, d, lane);
       // descending key order = score descending, then row ascending
-      key = (static_cast<unsigned long long>(orderable(s)) << 32) | (0xffffffffu - static_cast<uint32_t>(row));
+      key = (static_cast<unsigned long long>(orderable(s)) << 32) | (0xffffffffu - row);
     }
     if (lane == 0) keys[i] = key;
   }
@@ -741,6 +778,7 @@ __global__ void init_state_kernel(SearchState st, int Q, int32_t* stats) {
   if (q < Q) {
     st.thr[q] = -INFINITY;
     st.cnt[q] = 0;
+    st.cnt_done[q] = 0;
     st.overflow[q] = 0;
   }
   if (q < 4 && stats) stats[q] = 0;
@@ -958,7 +996,7 @@ topk_exchange_merge_kernel(const ExchangeParams p) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WorkspaceLayout {
-  size_t xq_bf16, qnorm, thr, cnt, overflow, cand, total;
+  size_t xq_bf16, qnorm, thr, cnt, cnt_done, overflow, cand, total;
   int q_pad;
 };
 inline WorkspaceLayout plan_workspace(int Q, int d, int cap) {
@@ -969,6 +1007,7 @@ inline WorkspaceLayout plan_workspace(int Q, int d, int cap) {
   w.qnorm = off, off = align_up(off + static_cast<size_t>(w.q_pad) * 4, 256);
   w.thr = off, off = align_up(off + static_cast<size_t>(Q) * 4, 256);
   w.cnt = off, off = align_up(off + static_cast<size_t>(Q) * 4, 256);
+  w.cnt_done = off, off = align_up(off + static_cast<size_t>(Q) * 4, 256);
   w.overflow = off, off = align_up(off + static_cast<size_t>(Q) * 4, 256);
   w.cand = off, off = align_up(off + static_cast<size_t>(Q) * cap * sizeof(Cand), 256);
   w.total = off;
@@ -1008,6 +1047,7 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
   SearchState state;
   state.thr = reinterpret_cast<float*>(ws + w.thr);
   state.cnt = reinterpret_cast<int32_t*>(ws + w.cnt);
+  state.cnt_done = reinterpret_cast<int32_t*>(ws + w.cnt_done);
   state.overflow = reinterpret_cast<int32_t*>(ws + w.overflow);
   state.qnorm = reinterpret_cast<float*>(ws + w.qnorm);
   state.cand = reinterpret_cast<Cand*>(ws + w.cand);
@@ -1064,8 +1104,27 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
     if (span < TN) span = TN;
     bool first = true;
     int epochs = 0;
+    // second stream for the early exact re-scoring (rescore_partial_kernel): forked before the last epoch's GEMM, joined
+    // before the tighten that follows it.  One per device, created on first use; calls are expected from one host thread.
+    static cudaStream_t aux[SDAG_MAX_DEVICES] = {};
+    static cudaEvent_t ev_fork[SDAG_MAX_DEVICES] = {}, ev_join[SDAG_MAX_DEVICES] = {};
+    if (!aux[dev]) {
+      SDAG_CUDA_TRY(cudaStreamCreateWithFlags(&aux[dev], cudaStreamNonBlocking));
+      SDAG_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+      SDAG_CUDA_TRY(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+    }
+    static int early_env = -1;
+    if (early_env < 0) {
+      const char* e = getenv("SDAG_IP_EARLY_RESCORE");  // 0: re-score everything after the sweep (A/B)
+      early_env = (e && !atoi(e)) ? 0 : 1;
+    }
     while (begin < N) {
       long long end = begin + span < N ? begin + span : N;
+      const bool fork = early_env && !first && end == N;  // last epoch, and a tighten has already run
+      if (fork) {
+        SDAG_CUDA_TRY(cudaEventRecord(ev_fork[dev], st));
+        SDAG_CUDA_TRY(cudaStreamWaitEvent(aux[dev], ev_fork[dev], 0));
+      }
       gp.row_begin = begin;
       gp.row_end = end;
       gp.n_ct = static_cast<int>((end - begin + TN - 1) / TN);
@@ -1079,6 +1138,12 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
       } else {
         const int grid = static_cast<int>(units < n_sm ? units : n_sm);
         ip_gemm_filter_kernel<<<grid, 192, GEMM_SMEM, st>>>(tmA, tmB, gp);
+      }
+      if (fork) {  // launched after the GEMM so that the GEMM's CTAs take their SMs first; the re-scoring blocks fit beside them
+        rescore_partial_kernel<<<Q, 256, static_cast<size_t>(d) * 4, aux[dev]>>>(
+            state, xq, corpus_f32, static_cast<const __nv_bfloat16*>(corpus_bf16), d);
+        SDAG_CUDA_TRY(cudaEventRecord(ev_join[dev], aux[dev]));
+        SDAG_CUDA_TRY(cudaStreamWaitEvent(st, ev_join[dev], 0));
       }
       if (first)  // every list holds the whole dumped span: block per query
         tighten_kernel<<<Q, 256, 0, st>>>(state, k, static_cast<int>(end - begin), max_norm_dev);
