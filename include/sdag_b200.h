@@ -139,9 +139,9 @@ size_t ip_search_workspace_bytes(int Q, int d, int k, int cand_cap);
  * id_offset added to row numbers (corpus sharding), max_norm = max corpus row norm (device scalar).
  * Outputs on device: scores float32 [Q,k], ids int64 [Q,k]; stats int32[4] =
  * {overflowed queries (re-run exactly inside), total candidates, epochs, reserved}.
- * The exact re-scoring of the candidates found before the last epoch runs on an internal second stream under the last
- * epoch's GEMM (forked from and joined back into `stream` with events, so the call stays stream-ordered and capturable);
- * the library keeps one such stream per device: make the calls of one device from one host thread. */
+ * With SDAG_IP_EARLY_RESCORE=1 (off by default: measured slower) the exact re-scoring of the candidates found before the
+ * last epoch runs on an internal second stream under the last epoch's GEMM (forked from and joined back into `stream` with
+ * events, so the call stays stream-ordered and capturable); the library keeps one such stream per device. */
 int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpus_bf16, int64_t N, int d,
               int64_t id_offset, const float* max_norm_dev, int k, float* out_scores, int64_t* out_ids,
               int32_t* stats_dev, void* workspace, size_t workspace_bytes, int cand_cap, void* stream);

@@ -704,24 +704,30 @@ exact_scan_kernel(SearchState st, int Q, const float* __restrict__ xq, const flo
 // 4 KB of row per candidate, ~100 candidates per query: 275 us per 4096-query search when it ran after the sweep, whatever
 // the shard size (profiles/r02_topk_dram.md).
 __global__ void __launch_bounds__(256)
-rescore_partial_kernel(SearchState st, const float* __restrict__ xq, const float* __restrict__ corpus_f32,
+rescore_partial_kernel(SearchState st, int Q, const float* __restrict__ xq, const float* __restrict__ corpus_f32,
                        const __nv_bfloat16* __restrict__ corpus_bf16, int d) {
+  // A small persistent grid (two blocks per SM, 4 KB of shared memory each) walks the queries: it must never hold the
+  // thread slots or the shared memory the GEMM's CTAs (193 KB, one per SM) need — a first version with a block per query
+  // flooded the SMs ahead of the GEMM and cost more than it saved.
   extern __shared__ __align__(16) uint8_t dyn[];
   float* sq = reinterpret_cast<float*>(dyn);
-  const int q = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (st.overflow[q]) return;  // redone by exact_scan anyway
-  int n = st.cnt_done[q];
-  if (n > st.cap) n = st.cap;
-  if (n == 0) return;
-  for (int j = tid; j < d; j += blockDim.x) sq[j] = xq[static_cast<long long>(q) * d + j];
-  __syncthreads();
-  Cand* cq = st.cand + static_cast<long long>(q) * st.cap;
-  for (int i = warp; i < n; i += blockDim.x / 32) {
-    const Cand c = cq[i];
-    if (c.row < 0) continue;  // already exact
-    const float s = corpus_f32 ? warp_dot_f32(corpus_f32 + static_cast<long long>(c.row) * d, sq, d, lane)
-                               : warp_dot_bf16(corpus_bf16 + static_cast<long long>(c.row) * d, sq, d, lane);
-    if (lane == 0) cq[i] = Cand{s, static_cast<int32_t>(static_cast<uint32_t>(c.row) | ROW_EXACT)};
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+    __syncthreads();  // sq of the previous query is no longer read
+    if (st.overflow[q]) continue;  // redone by exact_scan anyway (block-uniform)
+    int n = st.cnt_done[q];
+    if (n > st.cap) n = st.cap;
+    if (n == 0) continue;
+    for (int j = tid; j < d; j += blockDim.x) sq[j] = xq[static_cast<long long>(q) * d + j];
+    __syncthreads();
+    Cand* cq = st.cand + static_cast<long long>(q) * st.cap;
+    for (int i = warp; i < n; i += blockDim.x / 32) {
+      const Cand c = cq[i];
+      if (c.row < 0) continue;  // already exact
+      const float s = corpus_f32 ? warp_dot_f32(corpus_f32 + static_cast<long long>(c.row) * d, sq, d, lane)
+                                 : warp_dot_bf16(corpus_bf16 + static_cast<long long>(c.row) * d, sq, d, lane);
+      if (lane == 0) cq[i] = Cand{s, static_cast<int32_t>(static_cast<uint32_t>(c.row) | ROW_EXACT)};
+    }
   }
 }
 
@@ -1115,8 +1121,12 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
     }
     static int early_env = -1;
     if (early_env < 0) {
-      const char* e = getenv("SDAG_IP_EARLY_RESCORE");  // 0: re-score everything after the sweep (A/B)
-      early_env = (e && !atoi(e)) ? 0 : 1;
+      // Measured and left OFF (same box, 1.25 M-row shard, Q = 4096): 8.49-8.59 ms without, 8.68-8.72 ms with a block per
+      // query on the second stream (its 4096 blocks take the thread slots ahead of the GEMM's CTAs), 8.94-8.96 ms with two
+      // persistent blocks per SM (latency-bound: it outlasts the last epoch and the join waits); the chip runs at its power
+      // cap during the GEMM, so the HBM traffic moved under it is not free either.  SDAG_IP_EARLY_RESCORE=1 turns it on.
+      const char* e = getenv("SDAG_IP_EARLY_RESCORE");
+      early_env = (e && atoi(e)) ? 1 : 0;
     }
     while (begin < N) {
       long long end = begin + span < N ? begin + span : N;
@@ -1140,8 +1150,8 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
         ip_gemm_filter_kernel<<<grid, 192, GEMM_SMEM, st>>>(tmA, tmB, gp);
       }
       if (fork) {  // launched after the GEMM so that the GEMM's CTAs take their SMs first; the re-scoring blocks fit beside them
-        rescore_partial_kernel<<<Q, 256, static_cast<size_t>(d) * 4, aux[dev]>>>(
-            state, xq, corpus_f32, static_cast<const __nv_bfloat16*>(corpus_bf16), d);
+        rescore_partial_kernel<<<Q < 2 * n_sm ? Q : 2 * n_sm, 256, static_cast<size_t>(d) * 4, aux[dev]>>>(
+            state, Q, xq, corpus_f32, static_cast<const __nv_bfloat16*>(corpus_bf16), d);
         SDAG_CUDA_TRY(cudaEventRecord(ev_join[dev], aux[dev]));
         SDAG_CUDA_TRY(cudaStreamWaitEvent(st, ev_join[dev], 0));
       }

@@ -208,7 +208,7 @@ class FlatIPIndex:
             if self._ws is None or self._ws.numel() < need:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             part_stats = torch.zeros(4, dtype=torch.int32, device=self.device)
-            _lib.count_launches(2 + 2 * _n_epochs(self.ntotal, self.cand_cap) + 3)  # init+cast, (gemm+tighten)*, early rescore, scan+rescore
+            _lib.count_launches(2 + 2 * _n_epochs(self.ntotal, self.cand_cap) + 2)  # init+cast, (gemm+tighten)*, scan+rescore
             _lib.check(
                 lib.ip_search(
                     xq[q0:q1].data_ptr(), nq,
