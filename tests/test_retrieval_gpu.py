@@ -337,3 +337,36 @@ def test_load_faiss_index_and_meta_on_hand_assembled_fixture(golden_dir):
     texts, ids, _ = materialize_dense_hits(idx, sc, meta)
     assert ids[0][0] == "doc-2" and ids[0][3] == "NA" and texts[0][3] == ""
     assert isinstance(DenseRetriever(None, index, meta), DenseRetriever)
+
+
+def test_flat_ip_search_with_early_rescoring_knob_in_subprocess():
+    """SDAG_IP_EARLY_RESCORE=1 (read once per process; off by default because it measured slower): the candidates found
+    before the last epoch are re-scored on a second stream under the last epoch's GEMM and tagged in place — ids and scores
+    must still equal the oracle's, exact ties included."""
+    import subprocess
+    import sys
+
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, "tests")
+from oracle.flat_ip import FlatIPOracle
+from sdag_b200.retrieval import FlatIPIndex
+g = torch.Generator(device="cuda").manual_seed(5)
+x = torch.randn(300000, 256, generator=g, device="cuda"); x /= x.norm(dim=1, keepdim=True)
+x[150000:150100] = x[:100]
+q = torch.randn(300, 256, generator=g, device="cuda"); q /= q.norm(dim=1, keepdim=True)
+q[:50] = x[:50]
+idx = FlatIPIndex.from_device(x)
+for k in (10, 51):
+    s, i = idx.search_device(q, k)
+    o = FlatIPOracle(256); o.add(x.cpu().numpy())
+    D, I = o.search(q.cpu().numpy(), k)
+    assert np.array_equal(i.cpu().numpy(), I), k
+    np.testing.assert_allclose(s.cpu().numpy(), D, rtol=1e-5, atol=1e-6)
+    assert int(idx.last_stats[0]) == 0
+print("early rescore ok")
+'''
+    env = dict(os.environ, SDAG_IP_EARLY_RESCORE="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "early rescore ok" in r.stdout, r.stdout + r.stderr
