@@ -361,8 +361,14 @@ for k in (10, 51):
     s, i = idx.search_device(q, k)
     o = FlatIPOracle(256); o.add(x.cpu().numpy())
     D, I = o.search(q.cpu().numpy(), k)
-    assert np.array_equal(i.cpu().numpy(), I), k
     np.testing.assert_allclose(s.cpu().numpy(), D, rtol=1e-5, atol=1e-6)
+    got = i.cpu().numpy()
+    x64, q64 = x.double(), q.double()
+    for r, c in zip(*np.nonzero(got != I)):  # the documented exception class: fp32 near-ties (<= 2e-6) may swap
+        a, b = int(got[r, c]), int(I[r, c])
+        assert a >= 0 and b >= 0 and abs(float(q64[r] @ x64[a]) - float(q64[r] @ x64[b])) <= 2e-6, (k, r, c, a, b)
+    assert (got[:50, 0] == np.arange(50)).all()  # the exactly tied pairs: lower id first
+    print("k", k, "near-tie swaps", int((got != I).sum()))
     assert int(idx.last_stats[0]) == 0
 print("early rescore ok")
 '''
