@@ -244,6 +244,16 @@ int llm_gemv_rope(const void* x, const void* weight, const void* bias, const voi
                   int Hkv, int D, int64_t kv_stride_b, int64_t kv_stride_h, int pos0, const int32_t* pos0_dev,
                   int pos0_dev_stride, void* stream);
 
+/* The same decode-step linear layer (SDAG.py:191-211) for 1..32 prompts as a TMA weight stream on the tensor cores
+ * (tcgen05, prompts on the padded M side; csrc/llm_skinny.cu): out [B, N] rows ldo apart = xin [B, K] (rows ldx apart) .
+ * weight[N, K]^T (+ bias) (+ residual [B, N], rows ldr apart; out may alias it).  norm_weight != NULL: xin = RMSNorm(x) *
+ * norm_weight (eps), computed in the kernel (B * K small enough to stage: SDAG_ERR_UNSUPPORTED otherwise — normalise with
+ * llm_rmsnorm first).  pair_swiglu != 0: weight is the fused gate|up matrix [N = 2*I, K] and out [B, I] = silu(gate row j) *
+ * (up row j + I), no bias / residual.  K % 64 == 0, N % 8 == 0 (16 with pair_swiglu), ldx / ldr / ldo % 8 == 0, B <= 32. */
+int llm_skinny_linear(const void* x, int64_t ldx, const void* weight, const void* bias, const void* norm_weight, float eps,
+                      const void* residual, int64_t ldr, void* out, int64_t ldo, int B, int N, int K, int pair_swiglu,
+                      void* stream);
+
 /* Hint: pull `bytes` at `ptr` (16-byte aligned) into L2.  The generation engine (SDAG.py:191-211 decode loop) launches it
  * on a side stream for the next layer's o_proj weights while the decode attention kernels run. */
 int llm_prefetch_l2(const void* ptr, size_t bytes, void* stream);

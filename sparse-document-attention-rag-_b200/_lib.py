@@ -57,6 +57,7 @@ SIGNATURES = {
     "llm_rope_qkv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp, _i32, _vp]),
     "llm_swiglu": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "llm_gemv": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "llm_skinny_linear": (_i32, [_vp, _i64, _vp, _vp, _vp, _f32, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "llm_prefetch_l2": (_i32, [_vp, _sz, _vp]),
     "llm_gemm_rope": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp]),
     "llm_gemv_rope": (_i32, [_vp, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i64, _i64, _i32, _vp,

@@ -20,7 +20,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
     "-Xcompiler", "-fPIC",
 ] + os.environ.get("SDAG_EXTRA_NVCC_FLAGS", "").split()
-SOURCES = ["sdag_blockmap.cu", "sdag_prefill.cu", "sdag_decode.cu", "ip_search.cu", "selector.cu", "llm_glue.cu", "llm_gemm.cu", "encoder.cu", "abi.cu"]
+SOURCES = ["sdag_blockmap.cu", "sdag_prefill.cu", "sdag_decode.cu", "ip_search.cu", "selector.cu", "llm_glue.cu", "llm_gemm.cu", "llm_skinny.cu", "encoder.cu", "abi.cu"]
 
 
 def _digest(paths):

@@ -299,7 +299,7 @@ class FusedPrefill:
 
         lib = _lib.load()
         S_cap = max(2048, (need_cap + 2047) // 2048 * 2048)
-        key = (B, S_cap, temperature > 0, nucleus, use_graph, USE_FUSED_GEMV, str(dev))
+        key = (B, S_cap, temperature > 0, nucleus, use_graph, USE_FUSED_GEMV, tuple(sorted(DECODE_GEMV.items())), str(dev))
         ctxs = self.__dict__.setdefault("_ctx", {})
         ctx = ctxs.get(key)
         if ctx is not None:
@@ -421,6 +421,104 @@ class FusedPrefill:
                     main.wait_stream(pf_stream)
 
             step = step_fused
+        # 3 <= B <= 8: every linear layer named in DECODE_GEMV runs on llm_gemv's warp-MMA form (weights streamed once,
+        # RMSNorm prologue / SwiGLU / residual epilogues fused), the others on cuBLAS + the stand-alone glue kernels.
+        # The residual stream is (x + pending): a cuBLAS o / down output stays pending until the next RMSNorm adds it.
+        mixed = DECODE_GEMV if (USE_FUSED_GEMV and 3 <= B <= 8 and not fused_ok and hid % 32 == 0 and inter % 32 == 0
+                                and (H * D) % 32 == 0 and ((H + 2 * Hkv) * D) % 16 == 0 and hid % 16 == 0
+                                and head_w.dtype == torch.bfloat16) else {}
+        if mixed:
+            n_qkv = (H + 2 * Hkv) * D
+            qkv_b = torch.empty((B, n_qkv), dtype=torch.bfloat16, device=dev)
+            gu_b = torch.empty((B, inter), dtype=torch.bfloat16, device=dev)
+            res_a = torch.empty((B, hid), dtype=torch.bfloat16, device=dev)
+            res_b = torch.empty((B, hid), dtype=torch.bfloat16, device=dev)
+            logits_b = torch.empty((B, head_w.shape[0]), dtype=torch.bfloat16, device=dev)
+
+            def gemv_for(name):
+                """llm_gemv (warp-MMA form, weights through registers) or, for ``name=skinny``, llm_skinny_linear (TMA ring +
+                tcgen05, K split over a cluster for the narrow layers)."""
+                skinny = mixed.get(name) == "skinny"
+
+                def run(x, w, bias, norm_w, resid, out, K, N, pro, eps=0.0, pair=0):
+                    _lib.count_launches(1)
+                    if skinny:
+                        _lib.check(lib.llm_skinny_linear(x.data_ptr(), x.stride(0), w.data_ptr(), _lib.ptr(bias), _lib.ptr(norm_w), float(eps),
+                                                         _lib.ptr(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(),
+                                                         out.stride(0), B, N, K, pair, _lib.stream_ptr(dev)), "llm_skinny_linear")
+                    else:
+                        _lib.check(lib.llm_gemv(x.data_ptr(), w.data_ptr(), _lib.ptr(bias), _lib.ptr(norm_w), _lib.ptr(resid), out.data_ptr(),
+                                                B, K, N, pro, float(eps), pair, _lib.stream_ptr(dev)), "llm_gemv")
+                return run
+
+            g_qkv, g_o, g_gu, g_down, g_head = (gemv_for(n) for n in ("qkv", "o", "gate_up", "down", "head"))
+
+            def settle(x, pending, w, eps):
+                """(stream, normed): adds a pending cuBLAS output into the stream inside the RMSNorm launch."""
+                if pending is None:
+                    return x, _rmsnorm(x, None, w, eps)[1]
+                return _rmsnorm(pending, x, w, eps)
+
+            def step_mixed():
+                x, pending = inner.embed_tokens(c["tok"]).view(B, hid), None
+                for i, ly in enumerate(self.layers):
+                    if "qkv" in mixed and pending is None:
+                        g_qkv(x, ly["wqkv"], ly["bqkv"], ly["w_in"], None, qkv_b, hid, n_qkv, 1, ly["eps_in"])
+                        qkv = qkv_b
+                    else:
+                        x, normed = settle(x, pending, ly["w_in"], ly["eps_in"])
+                        pending = None
+                        if "qkv" in mixed:
+                            g_qkv(normed, ly["wqkv"], ly["bqkv"], None, None, qkv_b, hid, n_qkv, 0)
+                            qkv = qkv_b
+                        else:
+                            qkv = F.linear(normed, ly["wqkv"], ly["bqkv"])
+                    _lib.count_launches(1)
+                    _lib.check(lib.llm_rope_qkv(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), q.data_ptr(), kc[i].data_ptr(),
+                                                vc[i].data_ptr(), B, 1, H, Hkv, D, kc[i].stride(0), kc[i].stride(1), 0,
+                                                c["pos"].data_ptr(), 1, _lib.stream_ptr(dev)), "llm_rope_qkv")
+                    sdag.sdag_decode_attention(q.transpose(1, 2), kc[i], vc[i], ly["scaling"], kv_len_dev=c["len"], out=attn_out,
+                                               workspace=dec_ws)
+                    a = attn_out.view(B, H * D)
+                    if "o" in mixed:
+                        g_o(a, ly["wo"], ly["bo"], None, x, res_a, H * D, hid, 0)
+                        x = res_a
+                    else:
+                        pending = F.linear(a, ly["wo"], ly["bo"])
+                    if "gate_up" in mixed and pending is None:
+                        g_gu(x, ly["wgu"], None, ly["w_post"], None, gu_b, hid, 2 * inter, 1, ly["eps_post"], pair=1)
+                    else:
+                        x, normed = settle(x, pending, ly["w_post"], ly["eps_post"])
+                        pending = None
+                        if "gate_up" in mixed:
+                            g_gu(normed, ly["wgu"], None, None, None, gu_b, hid, 2 * inter, 0, pair=1)
+                        else:
+                            gu = F.linear(normed, ly["wgu"])
+                            _lib.count_launches(1)
+                            _lib.check(lib.llm_swiglu(gu.data_ptr(), gu_b.data_ptr(), B, inter, _lib.stream_ptr(dev)), "llm_swiglu")
+                    if "down" in mixed:
+                        g_down(gu_b, ly["wdown"], None, None, x, res_b, inter, hid, 0)
+                        x = res_b
+                    else:
+                        pending = F.linear(gu_b, ly["wdown"])
+                if "head" in mixed and pending is None:
+                    g_head(x, head_w, model.lm_head.bias, inner.norm.weight, None, logits_b, hid, head_w.shape[0], 1,
+                         inner.norm.variance_epsilon)
+                    lg = logits_b
+                else:
+                    x, normed = settle(x, pending, inner.norm.weight, inner.norm.variance_epsilon)
+                    lg = model.lm_head(normed)
+                if sample:
+                    nxt = sample_tokens(lg, c["temp"], c["top_p"] if nucleus else None)
+                else:
+                    nxt = torch.argmax(lg, dim=-1, keepdim=True)
+                c["gen"].scatter_(1, c["slot"], nxt)
+                c["tok"].copy_(nxt)
+                c["pos"].add_(1)
+                c["len"].add_(1)
+                c["slot"].add_(1)
+
+            step = step_mixed
         c["step"] = step
         c["graph"] = None
         if use_graph:
@@ -500,6 +598,8 @@ PAIR_GEMM_MIN_ROWS = 512  # decode steps of >= this many prompts would use llm_g
 PREFETCH_O_PROJ = os.environ.get("SDAG_L2_PREFETCH", "") == "1"  # decode step: o_proj weights prefetched into L2 during attention (measured 3 % slower: off)
 FUSED_ROPE_GEMM = os.environ.get("SDAG_NO_FUSED_ROPE_GEMM", "") != "1"  # prefill q/k/v GEMM with the RoPE + cache-write epilogue
 FUSED_ROPE_GEMV = os.environ.get("SDAG_NO_FUSED_ROPE", "") != "1"  # decode q/k/v GEMV with the RoPE + cache-write epilogue
+# decode steps of 3-8 prompts: the linear layers to run on llm_gemv's warp-MMA form instead of cuBLAS ("qkv,o,gate_up,down,head")
+DECODE_GEMV = {p.split("=")[0]: (p.split("=") + ["mma"])[1] for p in os.environ.get("SDAG_DECODE_GEMV", "").split(",") if p}
 USE_FUSED_GEMV = True  # decode-step linear layers on llm_gemv (B <= 4); False: cuBLAS + stand-alone glue kernels
 
 

@@ -128,3 +128,51 @@ def test_llm_gemm_rope_production_shape_on_sampled_rows():
     torch.testing.assert_close(k[b_idx, :, pos].float(), k_ref.float(), **TOL)
     torch.testing.assert_close(v[b_idx, :, pos].float(), v_ref.float(), **TOL)
     assert (v[b_idx, :, pos] == v_ref).float().mean() > 0.9
+
+
+@pytest.mark.parametrize("B,N,K,mode", [
+    (1, 4096, 4096, "residual"), (3, 4096, 14336, "residual"), (8, 6144, 4096, "norm+bias"), (4, 28672, 4096, "norm+swiglu"),
+    (2, 128256, 4096, "norm"), (8, 896 + 256, 896, "norm+bias"), (5, 9728, 896, "norm+swiglu"), (7, 896, 4864, "residual"),
+    (17, 1000, 192, "plain"), (32, 4096, 4096, "residual"), (8, 4096, 7168, "norm"),
+])
+def test_llm_skinny_linear_matches_torch(B, N, K, mode):
+    """The decode step's few-row linear layers as a TMA weight stream on tcgen05 (csrc/llm_skinny.cu): Llama-3-8B and
+    Qwen2.5-0.5B layer shapes, 1..32 prompts, every prologue / epilogue form, padded row strides; against an fp32 product of
+    the same bf16 operands with the Hugging Face roundings (LlamaRMSNorm, nn.Linear -> bf16, residual add, LlamaMLP)."""
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + N)
+    x = _rand((B, K + 8), g)[:, :K]  # ldx != K
+    W = _rand((N, K), g, K ** -0.5)
+    norm = "norm" in mode
+    pair = "swiglu" in mode
+    nw = (1.0 + 0.1 * torch.randn(K, generator=g, device="cuda")).to(torch.bfloat16) if norm else None
+    bias = _rand((N,), g) if "bias" in mode else None
+    res = _rand((B, N + 16), g)[:, :N] if mode == "residual" else None
+    n_out = N // 2 if pair else N
+    out = torch.full((B + 1, n_out + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+    st = L.stream_ptr(x.device)
+    rc = lib.llm_skinny_linear(x.data_ptr(), x.stride(0), W.data_ptr(), L.ptr(bias), L.ptr(nw), 1e-5, L.ptr(res),
+                               res.stride(0) if res is not None else 0, out.data_ptr(), out.stride(0), B, N, K, int(pair), st)
+    L.check(rc, "llm_skinny_linear")
+    xf = x.float()
+    if norm:
+        xf = (nw.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(torch.bfloat16).float()).to(torch.bfloat16).float()
+    lin = xf @ W.float().T
+    if bias is not None:
+        lin = lin + bias.float()
+    lin = lin.to(torch.bfloat16)
+    if pair:
+        ref = (torch.nn.functional.silu(lin[:, :n_out].float()).to(torch.bfloat16).float() * lin[:, n_out:].float()).to(torch.bfloat16)
+    elif res is not None:
+        ref = (lin.float() + res.float()).to(torch.bfloat16)
+    else:
+        ref = lin
+    got = out[:B, :n_out]
+    torch.testing.assert_close(got.float(), ref.float(), **TOL)
+    assert (got == ref).float().mean() > 0.9
+    assert (out[B:] == 7.0).all() and (out[:, n_out:] == 7.0).all()  # nothing written outside [B, n_out]
+    if res is not None:  # in place: out aliases the residual
+        inplace = res.clone()
+        L.check(lib.llm_skinny_linear(x.data_ptr(), x.stride(0), W.data_ptr(), 0, 0, 0.0, inplace.data_ptr(), inplace.stride(0),
+                                      inplace.data_ptr(), inplace.stride(0), B, N, K, 0, st), "in place")
+        assert torch.equal(inplace, got)

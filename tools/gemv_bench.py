@@ -33,8 +33,30 @@ for name, K, N, pro, pair in shapes:
     def cublas(i):
         F.linear(xin, Ws[i % copies], out=None)
 
+    out_sk = torch.empty(B, N // 2 if pair else N, device=dev, dtype=torch.bfloat16)
+
+    def skinny(i):
+        L.check(lib.llm_skinny_linear(x.data_ptr(), x.stride(0), Ws[i % copies].data_ptr(), 0, nw.data_ptr() if pro == 1 else 0, 1e-5,
+                                      res.data_ptr() if (pro != 1 and not pair) else 0, N, out_sk.data_ptr(), out_sk.stride(0), B, N, K,
+                                      pair, L.stream_ptr(dev)), "skinny")
+
     row = dict(layer=name, B=B, K=K, N=N, MB=round(K * N * 2 / 1e6, 1))
-    for label, fn in (("gemv", ours), ("cublas", cublas)):
+    # the skinny kernel against an fp32 product of the same bf16 operands (first weight copy)
+    skinny(0)
+    xf = x.float()
+    if pro == 1:
+        xf = (nw.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)).to(torch.bfloat16).float()).to(torch.bfloat16).float()
+    ref = xf @ Ws[0].float().T
+    if pair:
+        gte, up = ref[:, : N // 2].to(torch.bfloat16).float(), ref[:, N // 2:].to(torch.bfloat16).float()
+        ref = F.silu(gte).to(torch.bfloat16).float() * up
+    elif pro != 1:
+        ref = ref.to(torch.bfloat16).float() + res.float()
+    row["skinny_max_abs_err"] = round(float((out_sk.float() - ref).abs().max()), 5)
+    row["skinny_ref_max"] = round(float(ref.abs().max()), 3)
+    for label, fn in (("skinny", skinny), ("gemv", ours), ("cublas", cublas)):
+        if label == "gemv" and B > 8:
+            continue
         for i in range(copies):
             fn(i)
         torch.cuda.synchronize()

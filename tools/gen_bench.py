@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--new", type=int, default=64)
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--hf", action="store_true", help="also time the per-token HF loop")
+    ap.add_argument("--batch", type=int, default=1, help="prompts per call (3-8: the cuBLAS / SDAG_DECODE_GEMV step)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     model = sdag.prepare_model(bench.build_llama(args.layers, dev))
@@ -32,9 +33,10 @@ def main():
         lay, K = {"cfg2": ((48, 10, 256, 1, 24), 0), "cfg5": ((48, 50, 640, 1, 24), 2)}[name]
         L, S, spans, qa = layout(*lay)
         nb = knn_lists(len(spans), K) if K else None
-        ids = torch.randint(0, 128000, (1, L), generator=torch.Generator().manual_seed(1)).to(dev)
-        bm = sdag.build_blockmap([sdag.SdagLayout(L, S, spans, qa, nb)], dev)
-        res = dict(case=name, L=L, new_tokens=args.new, layers=args.layers)
+        Bn = args.batch
+        ids = torch.randint(0, 128000, (Bn, L), generator=torch.Generator().manual_seed(1)).to(dev)
+        bm = sdag.build_blockmap([sdag.SdagLayout(L, S, spans, qa, nb)] * Bn, dev)
+        res = dict(case=name, L=L, batch=Bn, new_tokens=args.new, layers=args.layers, decode_gemv=os.environ.get("SDAG_DECODE_GEMV", ""))
 
         def timed(n_new):
             torch.cuda.synchronize()
@@ -49,7 +51,7 @@ def main():
         res["generate_ms"] = min(timed(args.new) for _ in range(3))
         res["decode_ms_per_token"] = (res["generate_ms"] - res["prefill_ms"]) / args.new
         res["graph"] = next(iter(runner._ctx.values()))["graph"] is not None
-        kv_bytes = 2 * L * 8 * 128 * 2 * args.layers
+        kv_bytes = 2 * L * 8 * 128 * 2 * args.layers * Bn
         w_bytes = sum(p.numel() for p in model.parameters()) * 2 - model.model.embed_tokens.weight.numel() * 2
         res["decode_hbm_gbs"] = (kv_bytes + w_bytes) / res["decode_ms_per_token"] / 1e6
         if args.hf:
