@@ -138,8 +138,11 @@ __device__ __forceinline__ void store_chunk(__nv_bfloat16* row_even, __nv_bfloat
   }
 }
 
-template <int EPI, bool BIAS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+// EW: epilogue warps per CTA.  4 (one per TMEM lane quarter, a 256-column row each) keep up with a main loop of K >= 2048;
+// at K = 1024 (the encoder's hidden size) a tile's MMAs take ~8 k cycles and a 256-column GELU or residual row does not
+// fit under them (ncu: tensor pipe 38-52 % active), so those launches run 8 epilogue warps of 128 columns each.
+template <int EPI, bool BIAS, int EW = 4>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -156,7 +159,7 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);   // multicast commit of the leader
-      mbar_init(&acc_empty[a], 8);  // (leader's copy) one arrival per epilogue warp of both CTAs
+      mbar_init(&acc_empty[a], 2 * EW);  // (leader's copy) one arrival per epilogue warp of both CTAs
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmX);
@@ -233,7 +236,10 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
     }
   } else {
-    // ======================= epilogue (warps 2..5, both CTAs): TMEM -> bf16 rows =======================
+    // ======================= epilogue (warps 2.., both CTAs): TMEM -> bf16 rows =======================
+    static_assert(EW == 4 || (EW == 8 && (EPI == LLM_GEMM_PLAIN || EPI == LLM_GEMM_GELU)), "8 epilogue warps: plain / GELU rows only");
+    constexpr int CPW = (TNP / 32) / (EW / 4);  // 32-column chunks per warp
+    const int c_lo = ((warp - 2) >> 2) * CPW;   // warps 2-5 take the first column half of their rows, warps 6-9 the second
     const int quarter = warp & 3;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t ui = 0;
@@ -248,7 +254,7 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const __nv_bfloat16* rrow = nullptr;  // this thread's residual row (plain epilogue with a residual only)
       if (EPI == LLM_GEMM_PLAIN && p.resid && m_even + (lane & 1) < p.M) {
         rrow = p.resid + (m_even + (lane & 1)) * p.ldr;
-        prefetch_residual(rrow, un.nt * TNP, TNP, p.n_out);
+        prefetch_residual(rrow, un.nt * TNP + c_lo * 32, CPW * 32, p.n_out);
       }
       mbar_wait(&acc_full[a], (ui >> 1) & 1);
       tc_fence_after();
@@ -361,9 +367,9 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
       } else {
         uint4 rw[4];
-        if (rrow) load_residual(rw, rrow, un.nt * TNP, p.n_out);
+        if (rrow) load_residual(rw, rrow, un.nt * TNP + c_lo * 32, p.n_out);
 #pragma unroll 1
-        for (int c = 0; c < TNP / 32; ++c) {
+        for (int c = c_lo; c < c_lo + CPW; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(tacc + c * 32, r);
           tmem_ld_wait();
@@ -388,7 +394,7 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
           if (rrow) {  // the chunk's residual values were requested one iteration ago; request the next chunk's now
             apply_residual(v, rw, col0, p.n_out);
-            if (c + 1 < TNP / 32) load_residual(rw, rrow, col0 + 32, p.n_out);
+            if (c + 1 < c_lo + CPW) load_residual(rw, rrow, col0 + 32, p.n_out);
           }
           uint32_t o[16];
 #pragma unroll
@@ -618,6 +624,10 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_SWIGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+    SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+    SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+    SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_wide_kernel<LLM_GEMM_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
@@ -662,7 +672,22 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
   const long long units = static_cast<long long>(p.n_mt) * p.n_nt;
   const long long pairs = units < n_sm / 2 ? units : n_sm / 2;
   const unsigned grid = static_cast<unsigned>(2 * pairs);
-  if (wide && swiglu)
+  // short main loops (K <= 2048, the encoder) cannot hide a 256-column epilogue row: eight epilogue warps.  SDAG_GEMM_EW=4 / 8 forces one form.
+  static int ew_env = -1;
+  if (ew_env < 0) {
+    const char* e = getenv("SDAG_GEMM_EW");
+    ew_env = e ? atoi(e) : 0;
+  }
+  const bool ew8 = !wide && (epi == LLM_GEMM_PLAIN || epi == LLM_GEMM_GELU) && (ew_env ? ew_env == 8 : p.kblocks <= 32);
+  if (ew8 && epi == LLM_GEMM_GELU && p.bias)
+    llm_gemm_kernel<LLM_GEMM_GELU, true, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (ew8 && epi == LLM_GEMM_GELU)
+    llm_gemm_kernel<LLM_GEMM_GELU, false, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (ew8 && p.bias)
+    llm_gemm_kernel<LLM_GEMM_PLAIN, true, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (ew8)
+    llm_gemm_kernel<LLM_GEMM_PLAIN, false, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (wide && swiglu)
     llm_gemm_wide_kernel<LLM_GEMM_SWIGLU><<<grid, W_THREADS, W_SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (wide)
     llm_gemm_wide_kernel<LLM_GEMM_PLAIN><<<grid, W_THREADS, W_SMEM_BYTES, st>>>(tmX, tmW, p);

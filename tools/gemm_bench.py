@@ -41,37 +41,46 @@ def main():
     ap.add_argument("--tokens", type=int, default=21248)
     ap.add_argument("--only", default="", help="run one shape by name (qkv, o, gate_up, gate_up+swiglu, down)")
     ap.add_argument("--sustain", action="store_true", help="also report TFLOP/s of 1.5 s back-to-back runs")
+    ap.add_argument("--encoder", action="store_true", help="the e5-large-v2 encoder's projections (hidden 1024, FFN 4096) instead")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda:0")
     M = args.tokens
     st = _lib.stream_ptr(dev)
     torch.manual_seed(0)
-    for name, N, K, epi in (("qkv", 6144, 4096, 0), ("o", 4096, 4096, 0), ("gate_up", 28672, 4096, 0),
-                            ("gate_up+swiglu", 28672, 4096, 1), ("down", 4096, 14336, 0),
-                            ("o+residual", 4096, 4096, 2), ("down+residual", 4096, 14336, 2)):
+    llama = (("qkv", 6144, 4096, 0), ("o", 4096, 4096, 0), ("gate_up", 28672, 4096, 0), ("gate_up+swiglu", 28672, 4096, 1),
+             ("down", 4096, 14336, 0), ("o+residual", 4096, 4096, 2), ("down+residual", 4096, 14336, 2))
+    # epilogue 3: bias + erf-GELU (llm_gemm epilogue code 2), 4: bias + residual
+    e5 = (("enc qkv+bias", 3072, 1024, 5), ("enc o+bias+res", 1024, 1024, 4), ("enc ffn1+gelu", 4096, 1024, 3), ("enc ffn2+bias+res", 1024, 4096, 4))
+    for name, N, K, epi in (e5 if args.encoder else llama):
         if args.only and name != args.only:
             continue
         x = torch.randn(M, K, device=dev, dtype=torch.bfloat16) * 0.5
         w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.02
         n_out = N // 2 if epi == 1 else N
         out = torch.empty(M, n_out, device=dev, dtype=torch.bfloat16)
-        res = torch.randn(M, n_out, device=dev, dtype=torch.bfloat16) if epi == 2 else None
+        res = torch.randn(M, n_out, device=dev, dtype=torch.bfloat16) if epi in (2, 4) else None
+        bias = torch.randn(N, device=dev, dtype=torch.bfloat16) if epi >= 3 else None
 
         def ours():
-            if epi == 2:  # residual add in the epilogue (what the prefill runs for o / down)
-                _lib.check(lib.llm_gemm_residual(x.data_ptr(), K, w.data_ptr(), 0, res.data_ptr(), n_out, out.data_ptr(), n_out, M, N, K,
-                                                 st), "llm_gemm_residual")
+            if epi in (2, 4):  # residual add in the epilogue (what the prefill runs for o / down)
+                _lib.check(lib.llm_gemm_residual(x.data_ptr(), K, w.data_ptr(), _lib.ptr(bias), res.data_ptr(), n_out, out.data_ptr(), n_out,
+                                                 M, N, K, st), "llm_gemm_residual")
+            elif epi in (3, 5):
+                _lib.check(lib.llm_gemm(x.data_ptr(), K, w.data_ptr(), bias.data_ptr(), out.data_ptr(), n_out, M, N, K, 2 if epi == 3 else 0, st),
+                           "llm_gemm")
             else:
                 _lib.check(lib.llm_gemm(x.data_ptr(), K, w.data_ptr(), 0, out.data_ptr(), n_out, M, N, K, epi, st), "llm_gemm")
 
         act = torch.empty(M, N // 2, device=dev, dtype=torch.bfloat16)
 
         def cublas():
-            y = torch.nn.functional.linear(x, w)
+            y = torch.nn.functional.linear(x, w, bias)
+            if epi == 3:
+                y = torch.nn.functional.gelu(y)
             if epi == 1:
                 _lib.check(lib.llm_swiglu(y.data_ptr(), act.data_ptr(), M, N // 2, st), "swiglu")
-            elif epi == 2:
+            elif epi in (2, 4):
                 y = y + res
             return y
 
