@@ -139,11 +139,13 @@ class BertEncoderRunner:
         x = _layernorm(x, None, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps)
         bm = full_blockmap(lengths, L)
         scaling = float(D) ** -0.5
+        # one attention output buffer for all layers, zeroed once: rows past a sequence's end are never written
+        ctx_buf = torch.zeros((B, L, H, D), dtype=torch.bfloat16, device=dev)
         for ly in self.layers:
             qkv = _linear(x, ly["wqkv"], ly["bqkv"]).view(B, L, 3, H, D)
             # strided views straight into the fused projection: q [B,H,L,D], k / v [B,H,L,D] (no copies, TMA takes strides)
             q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
-            ctx = sdag.sdag_prefill_attention(q, k, v, bm, scaling, ragged=True).view(T, hid)
+            ctx = sdag.sdag_prefill_attention(q, k, v, bm, scaling, ragged=True, out=ctx_buf).view(T, hid)
             del qkv
             # dense + bias + residual in the GEMM epilogue; LayerNorm then reads one tensor
             x = _layernorm(_linear(ctx, ly["wo"], ly["bo"], residual=x), None, ly["ln1_w"], ly["ln1_b"], ly["eps1"])

@@ -245,7 +245,8 @@ def _workspace(device, nbytes: int) -> torch.Tensor:
 
 
 def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, blockmap: BlockMap,
-                           scaling: Optional[float] = None, ragged: bool = False, kernel: Optional[str] = None) -> torch.Tensor:
+                           scaling: Optional[float] = None, ragged: bool = False, kernel: Optional[str] = None,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q ``[B,H,L,D]`` (any strides with unit innermost), k/v ``[B,Hkv,S,D]`` bf16 -> out ``[B,L,H,D]`` bf16.
 
     ``kernel``: None = the library's choice; ``"pair"`` / ``"single"`` force the CTA-pair kernel (head_dim 128 and an even
@@ -253,7 +254,11 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
 
     ``ragged``: the block maps were built for prompts shorter than L (right-padded batch).  Rows past a prompt's end
     are not covered by any tile; they are returned as zeros so that everything downstream of them — in particular the
-    K / V rows the next layer derives from them, which sit inside the last kv tile of the prompt — stays finite."""
+    K / V rows the next layer derives from them, which sit inside the last kv tile of the prompt — stays finite.
+
+    ``out``: caller-owned contiguous ``[B,L,H,D]`` bf16 result buffer (a layer loop re-uses one instead of allocating — and,
+    when ``ragged``, zero-filling — per call; with ``ragged`` its rows past each prompt's end must already be zero: the
+    kernel never writes them)."""
     lib = _lib.load()
     if q.dtype != torch.bfloat16 or k.dtype != torch.bfloat16 or v.dtype != torch.bfloat16:
         raise TypeError("sdag_b200 attention computes in bf16 (fp32 softmax / accumulation)")
@@ -265,7 +270,10 @@ def sdag_prefill_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, bl
         raise ValueError(f"block map was built for L={blockmap.max_L}, got Lq={L}, Skv={S}")
     blockmap.ensure_ok()  # a rejected layout must not reach the kernel (its output rows would stay uninitialised)
     q, k, v = (_unit_inner(t) for t in (q, k, v))
-    out = (torch.zeros if ragged else torch.empty)((B, L, H, D), dtype=torch.bfloat16, device=q.device)
+    if out is None:
+        out = (torch.zeros if ragged else torch.empty)((B, L, H, D), dtype=torch.bfloat16, device=q.device)
+    elif out.shape != (B, L, H, D) or out.dtype != torch.bfloat16 or not out.is_contiguous() or out.device != q.device:
+        raise ValueError("out must be a contiguous bf16 [B, L, H, D] tensor on q's device")
     ws_bytes = int(lib.sdag_prefill_workspace_bytes(B, Hkv, D))
     ws = _workspace(q.device, ws_bytes)
     scaling = float(D ** -0.5 if scaling is None else scaling)
