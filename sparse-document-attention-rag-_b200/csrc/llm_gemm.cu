@@ -138,9 +138,10 @@ __device__ __forceinline__ void store_chunk(__nv_bfloat16* row_even, __nv_bfloat
   }
 }
 
-// EW: epilogue warps per CTA.  4 (one per TMEM lane quarter, a 256-column row each) keep up with a main loop of K >= 2048;
-// at K = 1024 (the encoder's hidden size) a tile's MMAs take ~8 k cycles and a 256-column GELU or residual row does not
-// fit under them (ncu: tensor pipe 38-52 % active), so those launches run 8 epilogue warps of 128 columns each.
+// EW: epilogue warps per CTA.  4 (one per TMEM lane quarter, a 256-column row each) is what the SwiGLU epilogue uses; at
+// K = 1024 (the encoder's hidden size) a tile's MMAs take ~8 k cycles and a 256-column GELU or residual row does not fit
+// under them (ncu: tensor pipe 38-52 % active), so the other epilogues run 8 warps of 128 columns (RoPE: of half the
+// tile's heads) each.
 template <int EPI, bool BIAS, int EW = 4>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p) {
@@ -237,7 +238,7 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else {
     // ======================= epilogue (warps 2.., both CTAs): TMEM -> bf16 rows =======================
-    static_assert(EW == 4 || (EW == 8 && (EPI == LLM_GEMM_PLAIN || EPI == LLM_GEMM_GELU)), "8 epilogue warps: plain / GELU rows only");
+    static_assert(EW == 4 || (EW == 8 && EPI != LLM_GEMM_SWIGLU), "8 epilogue warps: plain / GELU / RoPE rows only");
     constexpr int CPW = (TNP / 32) / (EW / 4);  // 32-column chunks per warp
     const int c_lo = ((warp - 2) >> 2) * CPW;   // warps 2-5 take the first column half of their rows, warps 6-9 the second
     const int quarter = warp & 3;
@@ -270,8 +271,10 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const __nv_bfloat16* cosr = p.cos + static_cast<long long>(p.pos0 + my_l) * D;
         const __nv_bfloat16* sinr = p.sin + static_cast<long long>(p.pos0 + my_l) * D;
         const bool my_ok = (lane & 1) ? ok_odd : ok_even;
+        const int hh_n = heads_per_tile / (EW / 4);  // heads per warp (a tile holds 2 or 4 whole heads)
+        const int hh_lo = ((warp - 2) >> 2) * hh_n;
 #pragma unroll 1
-        for (int hh = 0; hh < heads_per_tile; ++hh) {
+        for (int hh = hh_lo; hh < hh_lo + hh_n; ++hh) {
           const int head = un.nt * heads_per_tile + hh;
           if (head >= p.H + 2 * p.Hkv) break;
           __nv_bfloat16 *base_e, *base_o;
@@ -628,6 +631,8 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+    SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+    SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_wide_kernel<LLM_GEMM_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, W_SMEM_BYTES));
@@ -672,14 +677,20 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
   const long long units = static_cast<long long>(p.n_mt) * p.n_nt;
   const long long pairs = units < n_sm / 2 ? units : n_sm / 2;
   const unsigned grid = static_cast<unsigned>(2 * pairs);
-  // short main loops (K <= 2048, the encoder) cannot hide a 256-column epilogue row: eight epilogue warps.  SDAG_GEMM_EW=4 / 8 forces one form.
+  // Eight epilogue warps for the plain / residual / GELU / RoPE rows: decisive for short main loops (K = 1024, the encoder: a
+  // 256-column row does not fit under ~8 k cycles of MMAs), a consistent +0.3 % on the Llama prefill step (same-box ABAB:
+  // o + residual 1254 -> 1263, q/k/v + RoPE 1290 -> 1301 TFLOP/s).  SDAG_GEMM_EW=4 / 8 forces one form.
   static int ew_env = -1;
   if (ew_env < 0) {
     const char* e = getenv("SDAG_GEMM_EW");
     ew_env = e ? atoi(e) : 0;
   }
-  const bool ew8 = !wide && (epi == LLM_GEMM_PLAIN || epi == LLM_GEMM_GELU) && (ew_env ? ew_env == 8 : p.kblocks <= 32);
-  if (ew8 && epi == LLM_GEMM_GELU && p.bias)
+  const bool ew8 = !wide && !swiglu && (ew_env ? ew_env == 8 : true);
+  if (ew8 && epi == LLM_GEMM_ROPE_EPI && p.bias)
+    llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (ew8 && epi == LLM_GEMM_ROPE_EPI)
+    llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (ew8 && epi == LLM_GEMM_GELU && p.bias)
     llm_gemm_kernel<LLM_GEMM_GELU, true, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (ew8 && epi == LLM_GEMM_GELU)
     llm_gemm_kernel<LLM_GEMM_GELU, false, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
