@@ -304,7 +304,12 @@ class FusedPrefill:
         ctx = ctxs.get(key)
         if ctx is not None:
             return ctx
-        if len(ctxs) >= 2:  # keep HBM bounded: drop the oldest context
+        # keep HBM bounded: drop the oldest contexts once their KV caches exceed the budget.  (A fixed limit of two made a loop
+        # that alternates greedy SDAG and sampled CARG batches around a capacity-bucket boundary re-capture its graphs again
+        # and again: seconds per hundred queries.)
+        n_layers_ = len(self.layers)
+        new_bytes = 2 * n_layers_ * B * self.Hkv * S_cap * self.D * 2
+        while ctxs and sum(c_["kc"].numel() * 4 for c_ in ctxs.values()) + new_bytes > DECODE_CTX_BUDGET_BYTES:
             ctxs.pop(next(iter(ctxs)))
             torch.cuda.empty_cache()
         model, inner = self.model, self.model.model
@@ -555,6 +560,7 @@ class FusedPrefill:
         dev = input_ids.device
         nucleus = temperature > 0 and top_p is not None and top_p < 1.0
         c = self._decode_context(B, L + max_new_tokens + 1, temperature, dev, use_graph, nucleus)
+        self._last_ctx = c  # tools: the context this call used
         logits, _ = self.prefill(input_ids, blockmap, want_cache=False, kv=(c["kc"], c["vc"], c["cos"], c["sin"]),
                                  lengths=lengths)
         if temperature > 0:
@@ -600,6 +606,7 @@ FUSED_ROPE_GEMM = os.environ.get("SDAG_NO_FUSED_ROPE_GEMM", "") != "1"  # prefil
 FUSED_ROPE_GEMV = os.environ.get("SDAG_NO_FUSED_ROPE", "") != "1"  # decode q/k/v GEMV with the RoPE + cache-write epilogue
 # decode steps of 3-8 prompts: the linear layers to run on llm_gemv's warp-MMA form instead of cuBLAS ("qkv,o,gate_up,down,head")
 DECODE_GEMV = {p.split("=")[0]: (p.split("=") + ["mma"])[1] for p in os.environ.get("SDAG_DECODE_GEMV", "").split(",") if p}
+DECODE_CTX_BUDGET_BYTES = int(float(os.environ.get("SDAG_DECODE_CTX_GB", "24")) * 2 ** 30)  # KV caches of the cached decode contexts
 USE_FUSED_GEMV = True  # decode-step linear layers on llm_gemv (B <= 4); False: cuBLAS + stand-alone glue kernels
 
 

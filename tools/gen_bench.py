@@ -50,7 +50,7 @@ def main():
         res["prefill_ms"] = min(timed(0) for _ in range(3))
         res["generate_ms"] = min(timed(args.new) for _ in range(3))
         res["decode_ms_per_token"] = (res["generate_ms"] - res["prefill_ms"]) / args.new
-        res["graph"] = next(iter(runner._ctx.values()))["graph"] is not None
+        res["graph"] = runner._last_ctx["graph"] is not None
         kv_bytes = 2 * L * 8 * 128 * 2 * args.layers * Bn
         w_bytes = sum(p.numel() for p in model.parameters()) * 2 - model.model.embed_tokens.weight.numel() * 2
         res["decode_hbm_gbs"] = (kv_bytes + w_bytes) / res["decode_ms_per_token"] / 1e6

@@ -141,7 +141,7 @@ def config5(model, device, new_tokens: int = 128, peak_tflops: float = 1360.8, p
     gen_ms = min(_timed_ms(lambda: runner.generate(ids, bm, new_tokens, None), 3, warmup=0))
     decode_ms = (gen_ms - prefill_ms) / new_tokens
     attn_flops = 4.0 * D * hdr["pairs"] * H
-    ctx = list(runner._ctx.values())[-1]  # the context generate() just used (most recently created)
+    ctx = runner._last_ctx  # the context generate() just used
     kv_bytes = 2.0 * (Lp + new_tokens / 2) * Hkv * D * 2 * n_layers
     w_bytes = (sum(p.numel() for p in model.parameters()) - model.model.embed_tokens.weight.numel()) * 2.0
     return {
