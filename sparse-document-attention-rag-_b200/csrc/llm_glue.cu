@@ -710,7 +710,14 @@ extern "C" int llm_gemv(const void* x, const void* weight, const void* bias, con
 #ifdef SDAG_GEMV_FORCE_MMA
   if (mma_ok) return launch_gemv_mma(x, weight, bias, norm_weight, residual, out, B, K, N, prologue, eps, pair, st);
 #endif
-  if (B > 2 && mma_ok) return launch_gemv_mma(x, weight, bias, norm_weight, residual, out, B, K, N, prologue, eps, pair, st);
+  // the FMA form keeps up with the stream for one or two prompts; SDAG_GEMV_FMA_MAX_B (3 or 4) widens it for experiments
+  static int fma_max_b = -1;
+  if (fma_max_b < 0) {
+    const char* e = getenv("SDAG_GEMV_FMA_MAX_B");
+    fma_max_b = e ? atoi(e) : 2;
+    if (fma_max_b < 2 || fma_max_b > 4) fma_max_b = 2;
+  }
+  if (B > fma_max_b && mma_ok) return launch_gemv_mma(x, weight, bias, norm_weight, residual, out, B, K, N, prologue, eps, pair, st);
   if (B > 4 || static_cast<size_t>(B) * K * 2 > 200 * 1024) return SDAG_ERR_UNSUPPORTED;
   switch (B) {
     case 1: return launch_gemv<1>(x, weight, bias, norm_weight, residual, out, K, N, prologue, eps, pair, st);

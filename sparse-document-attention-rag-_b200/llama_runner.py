@@ -299,7 +299,7 @@ class FusedPrefill:
 
         lib = _lib.load()
         S_cap = max(2048, (need_cap + 2047) // 2048 * 2048)
-        key = (B, S_cap, temperature > 0, nucleus, use_graph, USE_FUSED_GEMV, tuple(sorted(DECODE_GEMV.items())), str(dev))
+        key = (B, S_cap, temperature > 0, nucleus, use_graph, USE_FUSED_GEMV, FUSED_GEMV_MAX_B, tuple(sorted(DECODE_GEMV.items())), str(dev))
         ctxs = self.__dict__.setdefault("_ctx", {})
         ctx = ctxs.get(key)
         if ctx is not None:
@@ -365,7 +365,7 @@ class FusedPrefill:
         # HBM stream (tools/gemv_bench.py) and cuBLAS is the faster path again.
         inter, hid = self.inter, self.hidden
         head_w = model.lm_head.weight
-        fused_ok = (USE_FUSED_GEMV and B <= 2 and hid % 8 == 0 and inter % 8 == 0 and (H * D) % 8 == 0
+        fused_ok = (USE_FUSED_GEMV and B <= FUSED_GEMV_MAX_B and hid % 8 == 0 and inter % 8 == 0 and (H * D) % 8 == 0
                     and all(n % 4 == 0 for n in ((H + 2 * Hkv) * D, hid, 2 * inter, head_w.shape[0]))
                     and model.lm_head.bias is None and head_w.dtype == torch.bfloat16 and B * inter * 2 <= 200 * 1024)
         if fused_ok:
@@ -607,6 +607,7 @@ FUSED_ROPE_GEMV = os.environ.get("SDAG_NO_FUSED_ROPE", "") != "1"  # decode q/k/
 # decode steps of 3-8 prompts: the linear layers to run on llm_gemv's warp-MMA form instead of cuBLAS ("qkv,o,gate_up,down,head")
 DECODE_GEMV = {p.split("=")[0]: (p.split("=") + ["mma"])[1] for p in os.environ.get("SDAG_DECODE_GEMV", "").split(",") if p}
 DECODE_CTX_BUDGET_BYTES = int(float(os.environ.get("SDAG_DECODE_CTX_GB", "24")) * 2 ** 30)  # KV caches of the cached decode contexts
+FUSED_GEMV_MAX_B = min(4, max(1, int(os.environ.get("SDAG_FUSED_GEMV_MAX_B", "2"))))  # largest batch on the fused llm_gemv step
 USE_FUSED_GEMV = True  # decode-step linear layers on llm_gemv (B <= 4); False: cuBLAS + stand-alone glue kernels
 
 
