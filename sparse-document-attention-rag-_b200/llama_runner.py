@@ -432,6 +432,8 @@ class FusedPrefill:
         mixed = DECODE_GEMV if (USE_FUSED_GEMV and 3 <= B <= 8 and not fused_ok and hid % 32 == 0 and inter % 32 == 0
                                 and (H * D) % 32 == 0 and ((H + 2 * Hkv) * D) % 16 == 0 and hid % 16 == 0
                                 and head_w.dtype == torch.bfloat16) else {}
+        if "head" in mixed and head_w.shape[0] % (8 if mixed["head"] == "skinny" else 16):
+            mixed = {k_: v_ for k_, v_ in mixed.items() if k_ != "head"}  # vocabulary size not a multiple the kernels take: cuBLAS
         if mixed:
             n_qkv = (H + 2 * Hkv) * D
             qkv_b = torch.empty((B, n_qkv), dtype=torch.bfloat16, device=dev)

@@ -804,3 +804,44 @@ print("wide ok")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "wide ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("choice", [{"o": "mma", "down": "mma"},
+                                    {"qkv": "skinny", "o": "skinny", "gate_up": "skinny", "down": "skinny", "head": "skinny"}])
+def test_decode_step_kernel_choices_agree_with_the_default_step(choice, monkeypatch):
+    """``SDAG_DECODE_GEMV`` (opt-in): the decode step of 3-8 prompts with its linear layers on ``llm_gemv``'s warp-MMA
+    form / on ``llm_skinny_linear`` (RMSNorm prologue, SwiGLU and residual epilogues fused, K split over a cluster)
+    against the default step (cuBLAS + stand-alone glue) on the same ragged batch: the first decode tokens equal, later
+    ones up to a bf16 near-tie flip (different GEMM orders), as between any two batch shapes of this engine."""
+    import sdag_b200.llama_runner as lr
+    import sdag_b200.sdag as sdag
+    from sdag_b200.generation import generate_batch_seq2seq
+
+    tok = synth.make_tokenizer()
+    tok.padding_side = "left"
+    model = _bf16_model(tok)
+    assert lr.get_runner(sdag.prepare_model(model)) is not None
+    prompts = ["Paris is the capital of", "Honey", "The highest mountain above sea level is called Mount Everest and it",
+               "Octopuses have three hearts"]
+    n_new = 16
+
+    def run():
+        seen = []
+        orig = _spy_decode(tok, seen)
+        try:
+            generate_batch_seq2seq(tok, model, prompts, max_tokens=n_new, temperature=0, top_p=1.0)
+        finally:
+            tok.decode = orig
+        return list(seen)
+
+    base = run()
+    launches0 = dict(lr._lib.launch_counts) if hasattr(lr._lib, "launch_counts") else None
+    monkeypatch.setattr(lr, "DECODE_GEMV", dict(choice))  # part of the decode-context key: a new graph is captured
+    mixed = run()
+    ctx = lr.get_runner(model)._last_ctx
+    assert ctx["graph"] is not None and ctx["step"].__name__ == "step_mixed"
+    del launches0
+    for b, (x, y) in enumerate(zip(base, mixed)):
+        d = next((i for i, (p, q) in enumerate(zip(x, y)) if p != q), min(len(x), len(y)))
+        assert d >= min(4, len(x)), (b, x, y)
+    assert sum(x == y for x, y in zip(base, mixed)) >= len(prompts) - 1, (base, mixed)
