@@ -238,7 +238,8 @@ llm_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else {
     // ======================= epilogue (warps 2.., both CTAs): TMEM -> bf16 rows =======================
-    static_assert(EW == 4 || (EW == 8 && EPI != LLM_GEMM_SWIGLU), "8 epilogue warps: plain / GELU / RoPE rows only");
+    static_assert(EW == 4 || (EW == 8 && EPI != LLM_GEMM_SWIGLU) || (EW == 16 && (EPI == LLM_GEMM_PLAIN || EPI == LLM_GEMM_GELU)),
+                  "8 epilogue warps: plain / GELU / RoPE rows; 16: plain / GELU rows");
     constexpr int CPW = (TNP / 32) / (EW / 4);  // 32-column chunks per warp
     const int c_lo = ((warp - 2) >> 2) * CPW;   // warps 2-5 take the first column half of their rows, warps 6-9 the second
     const int quarter = warp & 3;
@@ -627,6 +628,8 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_SWIGLU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     SDAG_CUDA_TRY(cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
+    SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_PLAIN, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
     SDAG_CUDA_TRY((cudaFuncSetAttribute(llm_gemm_kernel<LLM_GEMM_GELU, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)));
@@ -685,8 +688,14 @@ int run_gemm(const void* x, int64_t ldx, const void* weight, int64_t M, int N, i
     const char* e = getenv("SDAG_GEMM_EW");
     ew_env = e ? atoi(e) : 0;
   }
-  const bool ew8 = !wide && !swiglu && (ew_env ? ew_env == 8 : true);
-  if (ew8 && epi == LLM_GEMM_ROPE_EPI && p.bias)
+  const bool ew8 = !wide && !swiglu && (ew_env ? ew_env >= 8 : true);
+  // sixteen (two 32-column chunks per warp) for the biased plain / GELU rows of short main loops: experiment, SDAG_GEMM_EW=16
+  const bool ew16 = !wide && ew_env == 16 && p.bias && (epi == LLM_GEMM_PLAIN || epi == LLM_GEMM_GELU);
+  if (ew16 && epi == LLM_GEMM_GELU)
+    llm_gemm_kernel<LLM_GEMM_GELU, true, 16><<<grid, 576, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (ew16)
+    llm_gemm_kernel<LLM_GEMM_PLAIN, true, 16><<<grid, 576, SMEM_BYTES, st>>>(tmX, tmW, p);
+  else if (ew8 && epi == LLM_GEMM_ROPE_EPI && p.bias)
     llm_gemm_kernel<LLM_GEMM_ROPE_EPI, true, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
   else if (ew8 && epi == LLM_GEMM_ROPE_EPI)
     llm_gemm_kernel<LLM_GEMM_ROPE_EPI, false, 8><<<grid, 320, SMEM_BYTES, st>>>(tmX, tmW, p);
