@@ -59,17 +59,22 @@ __global__ void __launch_bounds__(THREADS, 1)
 decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __nv_bfloat16* __restrict__ q, long long sq_b, long long sq_h, float* __restrict__ partial,
                     int H, int Hkv, int kv_len_host, float scale_log2, const int32_t* __restrict__ kv_len_dev,
-                    int kv_len_dev_stride, __nv_bfloat16* __restrict__ merged_out, unsigned int* __restrict__ tickets) {
+                    int kv_len_dev_stride, __nv_bfloat16* __restrict__ merged_out, unsigned int* __restrict__ tickets,
+                    int early_tiles) {
   using S = DecodeSmem<D>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full[S::kStages], empty[S::kStages];
 
   const int split = blockIdx.x, nsplit = gridDim.x, hkv = blockIdx.y, b = blockIdx.z;
-  pdl_wait();     // launched as a programmatic dependent: q, the cache rows and the length come from preceding kernels
-  pdl_trigger();  // the merge kernel may be scheduled; it waits for this grid before reading the partial results
+  // Launched as a programmatic dependent.  What the kernel just before this one may still be writing is q and the cache row
+  // of the NEWEST token (row kv_len - 1: the q/k/v projection of this step); every other cache row and the length were
+  // written at least one step (several kernels) ago, and each kernel of the chain waits for its own predecessor before it
+  // lets its dependents start.  So the ring is filled with tiles that lie wholly below row kv_len - 1 BEFORE
+  // griddepcontrol.wait (early_tiles; the length is read past L1): the stream starts under the previous kernel's tail.
+  if (!early_tiles) pdl_wait();
   // device-side length: one value for the batch (stride 0) or one per prompt of a ragged batch (stride 1)
-  const int kv_len = kv_len_dev ? max(0, min(kv_len_dev[b * kv_len_dev_stride], kv_len_host)) : kv_len_host;
+  const int kv_len = kv_len_dev ? max(0, min(__ldcg(kv_len_dev + b * kv_len_dev_stride), kv_len_host)) : kv_len_host;
   const int G = H / Hkv;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_total = (kv_len + TILE_ROWS - 1) / TILE_ROWS;
@@ -92,7 +97,7 @@ decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   if (warp == CONSUMERS) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      for (int it = 0; it < n_tiles; ++it) {
+      auto issue = [&](int it) {
         const int s = it % S::kStages;
         if (it >= S::kStages) mbar_wait(&empty[s], ((it / S::kStages) - 1) & 1);
         uint8_t* stage = smem + s * S::kStageBytes;
@@ -101,12 +106,21 @@ decode_split_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         for (int dh = 0; dh < D / 64; ++dh) tma_load_4d(stage + dh * TILE_ROWS * 128, &tmK, &full[s], dh * 64, row0, hkv, b);
         for (int dh = 0; dh < D / 64; ++dh)
           tma_load_4d(stage + S::kTileBytes + dh * TILE_ROWS * 128, &tmV, &full[s], dh * 64, row0, hkv, b);
+      };
+      int it = 0;
+      if (early_tiles) {
+        for (; it < n_tiles && it < S::kStages && (t0 + it + 1) * TILE_ROWS <= kv_len - 1; ++it) issue(it);
+        pdl_wait();
       }
+      pdl_trigger();  // the merge kernel may be scheduled; it waits for this grid before reading the partial results
+      for (; it < n_tiles; ++it) issue(it);
     }
     return;
   }
 
   // ======================= consumers =======================
+  if (early_tiles) pdl_wait();  // q comes from the kernel just before this one
+  pdl_trigger();
   const int g = lane >> 2, qd = lane & 3;  // MMA row (query head within the group) / quad lane
   // A fragments of Q for every 16-wide slice of d: a0 = Q[g][16ks + 2qd .. +1], a2 = Q[g][16ks + 8 + 2qd .. +1]
   uint32_t qa[D / 16][2];
@@ -348,6 +362,11 @@ int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloa
   }
   // both kernels are programmatic dependents of their predecessor: launch latency hides behind the previous kernel's tail
   unsigned int* tickets = nullptr;
+  static int early_tiles = -1;
+  if (early_tiles < 0) {
+    const char* e = getenv("SDAG_DECODE_EARLY_TILES");  // 0: wait for the previous kernel before the first cache tile is requested
+    early_tiles = (e && !atoi(e)) ? 0 : 1;
+  }
   static int fused_merge = -1;
   if (fused_merge < 0) {
     const char* e = getenv("SDAG_DECODE_SPLIT_MERGE");  // 1: the last split CTA merges instead of decode_merge_kernel
@@ -356,7 +375,7 @@ int launch_decode(const CUtensorMap& tk, const CUtensorMap& tv, const __nv_bfloa
   if (fused_merge && B * Hkv <= MAX_TICKETS)
     SDAG_CUDA_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_decode_tickets));
   SDAG_CUDA_TRY(launch_pdl(decode_split_kernel<D>, dim3(nsplit, Hkv, B), dim3(THREADS), DecodeSmem<D>::kTotal, st, tk, tv, q,
-                           sq_b, sq_h, part, H, Hkv, kv_len, sl2, kv_len_dev, kv_len_dev_stride, out, tickets));
+                           sq_b, sq_h, part, H, Hkv, kv_len, sl2, kv_len_dev, kv_len_dev_stride, out, tickets, early_tiles));
   if (tickets != nullptr) return SDAG_OK;  // the last split CTA of every (b, hkv) merged in place
   return static_cast<int>(launch_pdl(decode_merge_kernel<D>, dim3(H, B), dim3(D), 0, st, static_cast<const float*>(part), out, H,
                                      Hkv, nsplit));
