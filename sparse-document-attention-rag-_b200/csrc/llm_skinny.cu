@@ -336,6 +336,16 @@ int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && *e) ? atoi(e) : dflt;
 }
+// bring-up knobs, read once per process
+struct SkinnyKnobs {
+  int no_mma, smem_kb, debug, sk, r, ks, stages;
+};
+const SkinnyKnobs& knobs() {
+  static const SkinnyKnobs k = {env_int("SDAG_SKINNY_NOMMA", 0), env_int("SDAG_SKINNY_SMEM_KB", 0), env_int("SDAG_SKINNY_DEBUG", 0),
+                                env_int("SDAG_SKINNY_SK", 0),    env_int("SDAG_SKINNY_R", 0),       env_int("SDAG_SKINNY_KS", 0),
+                                env_int("SDAG_SKINNY_STAGES", 0)};
+  return k;
+}
 
 // launch_pdl with a thread-block cluster of `cluster` CTAs along x
 template <typename... KArgs, typename... Args>
@@ -400,7 +410,7 @@ extern "C" int llm_skinny_linear(const void* x, int64_t ldx, const void* weight,
   p.norm = norm_weight ? 1 : 0;
   p.kblocks = K / 64;
   p.x_tile_bytes = static_cast<uint32_t>(p.RB) * 128u;
-  p.debug_no_mma = env_int("SDAG_SKINNY_NOMMA", 0);
+  p.debug_no_mma = knobs().no_mma;
 
   // Decomposition: SK CTAs (a cluster) share a row tile and split K; rows per tile R <= 128.  Model per choice: the stream
   // (bytes per CTA at the smaller of the HBM share and ~64 GB/s per SM) against the MMA time (~56 cycles per 128-row x 16-k
@@ -409,7 +419,7 @@ extern "C" int llm_skinny_linear(const void* x, int64_t ldx, const void* weight,
   // consecutive kernels of the step, so that the next layer's ring fills while this one drains); the large ones (gate/up,
   // LM head) a whole SM and a deeper ring.
   constexpr uint32_t SMEM_MAX = 224 * 1024;
-  const int forced_kb = env_int("SDAG_SKINNY_SMEM_KB", 0);
+  const int forced_kb = knobs().smem_kb;
   int cls = forced_kb > 0 ? (forced_kb <= 112 ? 0 : 1) : (static_cast<double>(N) * K * 2.0 < 150e6 ? 0 : 1);
   uint32_t SMEM_BUDGET = forced_kb > 0 ? static_cast<uint32_t>(forced_kb) * 1024u : (cls == 0 ? 110u * 1024u : SMEM_MAX);
   if (SMEM_BUDGET > SMEM_MAX) return SDAG_ERR_INVALID;
@@ -442,7 +452,7 @@ extern "C" int llm_skinny_linear(const void* x, int64_t ldx, const void* weight,
         (void)cudaGetLastError();
         n = 0;
       }
-      if (env_int("SDAG_SKINNY_DEBUG", 0))
+      if (knobs().debug)
         fprintf(stderr, "llm_skinny: cluster size %d, %u KB -> %d co-resident clusters (%s)\n", sk, SMEM_BUDGET / 1024u, n, cudaGetErrorString(e));
       max_clusters[dev][cls][sk] = n > 0 ? n : -1;
     }
@@ -450,7 +460,7 @@ extern "C" int llm_skinny_linear(const void* x, int64_t ldx, const void* weight,
   };
   int best_sk = 1, best_r = 8;
   double best_t = 1e30;
-  const int forced_sk = env_int("SDAG_SKINNY_SK", 0);
+  const int forced_sk = knobs().sk;
   for (int attempt = 0; attempt < 2 && best_t > 1e29; ++attempt) {
   if (attempt == 1) {  // nothing fits half an SM (a long K staged for the RMSNorm prologue): take a whole one
     if (cls == 1 || forced_kb > 0) break;
@@ -488,7 +498,7 @@ extern "C" int llm_skinny_linear(const void* x, int64_t ldx, const void* weight,
   if (best_t > 1e29) return SDAG_ERR_UNSUPPORTED;  // e.g. too many input rows x K to stage: normalise first (llm_rmsnorm)
   p.SK = best_sk;
   p.R = best_r;
-  const int forced_r = env_int("SDAG_SKINNY_R", 0);
+  const int forced_r = knobs().r;
   if (forced_r >= 8 && forced_r <= 128 && forced_r % 8 == 0) p.R = forced_r;
   p.n_tiles = (p.units + p.R - 1) / p.R;
   p.w_tile_bytes = static_cast<uint32_t>(p.R) * 128u;
@@ -517,11 +527,11 @@ extern "C" int llm_skinny_linear(const void* x, int64_t ldx, const void* weight,
       if (waste < best_waste) best_waste = waste, p.KS = ks;
     }
   }
-  const int forced_ks = env_int("SDAG_SKINNY_KS", 0);
+  const int forced_ks = knobs().ks;
   if (forced_ks >= 1 && forced_ks <= 8 && forced_ks <= slice_min) p.KS = forced_ks;
   p.stage_bytes = static_cast<uint32_t>(p.KS) * per_kb;
   p.stages = static_cast<int>(ring_budget / p.stage_bytes);
-  const int forced_s = env_int("SDAG_SKINNY_STAGES", 0);
+  const int forced_s = knobs().stages;
   if (forced_s > 0 && forced_s < p.stages) p.stages = forced_s;
   if (p.stages > SK_MAX_STAGES) p.stages = SK_MAX_STAGES;
   if (p.stages < 2) return SDAG_ERR_UNSUPPORTED;
@@ -548,7 +558,7 @@ extern "C" int llm_skinny_linear(const void* x, int64_t ldx, const void* weight,
     if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, x, dims, strides, box)) return SDAG_ERR_INVALID;
   }
   const int groups = clusters_for(p.SK);
-  if (env_int("SDAG_SKINNY_DEBUG", 0))
+  if (knobs().debug)
     fprintf(stderr, "llm_skinny: B=%d N=%d K=%d pair=%d norm=%d -> SK=%d R=%d tiles=%d KS=%d stages=%d stage=%u B smem=%zu groups=%d\n", B, N, K,
             p.parts == 2, p.norm, p.SK, p.R, p.n_tiles, p.KS, p.stages, p.stage_bytes, smem, groups);
   if (smem > SMEM_BUDGET || groups < 1 || (p.SK > 1 && p.n_tiles > groups)) return SDAG_ERR_UNSUPPORTED;

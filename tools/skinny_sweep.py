@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Bring-up: llm_skinny_linear streaming rate per layer shape under the SDAG_SKINNY_{TN,KS,STAGES,NOMMA} knobs (read per call)."""
+"""Bring-up: llm_skinny_linear streaming rate per layer shape under the SDAG_SKINNY_{SK,R,KS,STAGES,SMEM_KB,NOMMA} knobs (read once per process)."""
 import json
 import os
 import sys
