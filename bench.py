@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--topk", type=int, default=10)
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--balance-shards", action="store_true",
+                    help="dense top-k at N > 1: after timing equal row blocks, re-cut them by each GPU's measured search rate and time again")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hf", action="store_true", help="skip the same-GPU Hugging Face baseline")
     ap.add_argument("--no-config5", action="store_true")
@@ -439,47 +441,105 @@ def run_b200(args):
     # ---------------- dense top-k, config 3 ----------------
     if not args.no_secondary:
         N, d, Q, k = args.corpus_rows, 1024, args.queries, args.topk
-        rows = N // world
-        lo = rank * rows
-        n_local = rows if rank < world - 1 else N - lo
-        gen = torch.Generator(device=device).manual_seed(42 + rank)
-        x = torch.empty((n_local, d), dtype=torch.float32, device=device)
-        for r0 in range(0, n_local, 1 << 20):  # generate + normalise in 1M-row pieces
-            r1 = min(n_local, r0 + (1 << 20))
-            x[r0:r1].normal_(generator=gen)
-            x[r0:r1] /= x[r0:r1].norm(dim=1, keepdim=True)
-        index = ShardedFlatIPIndex(FlatIPIndex.from_device(x, id_offset=lo))
         qg = torch.Generator().manual_seed(7)
         xq_host = torch.randn(Q, d, generator=qg)
         xq_host = (xq_host / xq_host.norm(dim=1, keepdim=True)).pin_memory()
         xq_dev = xq_host.to(device)
-        # enough steps for the clock sampler (100 ms period) to see the timed region: >= 0.6 s of searches
-        search_index_probe = index.search_device(xq_dev, k)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        index.search_device(xq_dev, k)
-        p1.record()
-        torch.cuda.synchronize()
-        del search_index_probe
-        est_ms = max_over_ranks(max(p0.elapsed_time(p1), 0.05))
-        s_steps = int(max(3, min(args.steps, 10), min(200, -(-600.0 // est_ms))))
-
         timed_out = {}
 
-        def search_resident():
-            timed_out["s"], timed_out["i"] = index.search_device(xq_dev, k)
-            return timed_out["s"]
+        def build_shard(counts):
+            """This rank's contiguous block of rows (synthetic: unit Gaussian rows from a per-rank seed) as a sharded index."""
+            lo_ = int(sum(counts[:rank]))
+            n_ = int(counts[rank])
+            gen = torch.Generator(device=device).manual_seed(42 + rank)
+            x_ = torch.empty((n_, d), dtype=torch.float32, device=device)
+            for r0 in range(0, n_, 1 << 20):  # generate + normalise in 1M-row pieces
+                r1 = min(n_, r0 + (1 << 20))
+                x_[r0:r1].normal_(generator=gen)
+                x_[r0:r1] /= x_[r0:r1].norm(dim=1, keepdim=True)
+            return x_, lo_, n_, ShardedFlatIPIndex(FlatIPIndex.from_device(x_, id_offset=lo_))
 
-        def search_e2e():
-            s, i = index.search_device(xq_host.to(device, non_blocking=True), k)
-            return s.cpu(), i.cpu()
+        def time_search(index_):
+            # enough steps for the clock sampler (100 ms period) to see the timed region: >= 0.6 s of searches
+            index_.search_device(xq_dev, k)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            index_.search_device(xq_dev, k)
+            p1.record()
+            torch.cuda.synchronize()
+            est_ms = max_over_ranks(max(p0.elapsed_time(p1), 0.05))
+            steps_ = int(max(3, min(args.steps, 10), min(200, -(-600.0 // est_ms))))
 
-        ms_s, clocks_s, launches_s, _ = timed(search_resident, s_steps, args.warmup)
-        ms_se, _, _, _ = timed(search_e2e, s_steps, args.warmup)
+            def search_resident():
+                timed_out["s"], timed_out["i"] = index_.search_device(xq_dev, k)
+                return timed_out["s"]
+
+            def search_e2e():
+                s_, i_ = index_.search_device(xq_host.to(device, non_blocking=True), k)
+                return s_.cpu(), i_.cpu()
+
+            ms_, clocks_, launches_, _ = timed(search_resident, steps_, args.warmup)
+            ms_e_, _, _, _ = timed(search_e2e, steps_, args.warmup)
+            ms_pipe_ = None
+            if world > 1:
+                # throughput form: batch n's exchange (which waits for the slowest shard of batch n) runs on a side stream
+                # under batch n + 1's local search, so a step costs the mean shard time, not the slowest shard of every batch
+                def pipelined(n):
+                    prev = None
+                    for _ in range(n):
+                        h = index_.submit(xq_dev, k)
+                        if prev is not None:
+                            timed_out["s"], timed_out["i"] = index_.result(prev)
+                        prev = h
+                    timed_out["s"], timed_out["i"] = index_.result(prev)
+
+                pipelined(max(args.warmup, 2))
+                ms_pipe_, clocks_p_, launches_p_, _ = timed(lambda: pipelined(steps_), 1, 0)
+            # this rank's own search without the exchange (what the step waits for is the slowest rank's)
+            l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0.record()
+            for _ in range(steps_):
+                index_.local.search_device(xq_dev, k)
+            l1.record()
+            torch.cuda.synchronize()
+            local_ms_ = l0.elapsed_time(l1) / steps_
+            if world > 1:
+                t_all = [torch.zeros(1, device=device) for _ in range(world)]
+                dist.all_gather(t_all, torch.tensor([local_ms_], device=device))
+                local_all_ = [float(t) for t in t_all]
+            else:
+                local_all_ = [local_ms_]
+            return dict(ms=ms_, clocks=clocks_, launches=launches_, ms_e2e=ms_e_, steps=steps_, local_ms=local_all_,
+                        ms_pipelined=ms_pipe_, stats=index_.local.last_stats.cpu().tolist())
+
+        counts = [N // world] * world
+        counts[-1] = N - sum(counts[:-1])
+        x, lo, n_local, index = build_shard(counts)
+        res = time_search(index)
+        equal_shards = None
+        if world > 1 and args.balance_shards:
+            # GPUs of a node settle at different clocks under the power cap and every search step waits for the slowest
+            # shard: re-cut the row blocks in proportion to each GPU's measured search rate (multiples of 256 rows)
+            rate = [c / t for c, t in zip(counts, res["local_ms"])]
+            new_counts = [int(N * r / sum(rate)) // 256 * 256 for r in rate]
+            new_counts[-1] = N - sum(new_counts[:-1])
+            equal_shards = {"queries_per_s": Q * res["steps"] / (res["ms"] / 1000.0), "ms_per_step": res["ms"] / res["steps"],
+                            "queries_per_s_pipelined": Q * res["steps"] / (res["ms_pipelined"] / 1000.0),
+                            "rank_local_ms": [round(t, 3) for t in res["local_ms"]], "rows_per_rank": counts}
+            del index, x
+            torch.cuda.empty_cache()
+            counts = new_counts
+            x, lo, n_local, index = build_shard(counts)
+            res = time_search(index)
+        ms_s, clocks_s, launches_s, ms_se, s_steps, stats = res["ms"], res["clocks"], res["launches"], res["ms_e2e"], res["steps"], res["stats"]
+        lockstep = None
+        if res["ms_pipelined"] is not None and res["ms_pipelined"] < ms_s:
+            lockstep = {"queries_per_s": Q * s_steps / (ms_s / 1000.0), "ms_per_step": ms_s / s_steps,
+                        "note": "every batch's exchange completed before the next batch's local search is enqueued"}
+            ms_s = res["ms_pipelined"]
         qps = Q * s_steps / (ms_s / 1000.0)
-        flops = 2.0 * Q * n_local * d  # per GPU per batch (algorithmic; re-scoring and merge excluded)
+        flops = 2.0 * Q * (N / world) * d  # per GPU per batch (algorithmic; re-scoring and merge excluded)
         ach = flops / (ms_s / s_steps / 1000.0) / 1e12
-        stats = index.local.last_stats.cpu().tolist()
 
         # Full-size parity ON WHAT WAS TIMED: sampled rows of the output of the last timed Q-query search (the CTA-pair
         # kernel ip_gemm_filter_kernel_2cta whenever Q >= 256) against an fp32 brute force over the whole corpus in plain
@@ -535,7 +595,15 @@ def run_b200(args):
             "e2e": {"value": Q * s_steps / (ms_se / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": Q * d * 4,
                     "d2h_bytes_per_step": Q * k * 12, "api": "FlatIPIndex.search_device + host copies (faiss-shaped search)"},
             "gpu_launches": launches_s, "clocks": clocks_s, "parity_check": parity,
+            "rank_local_ms": [round(t, 3) for t in res["local_ms"]], "rows_per_rank": counts,
         }
+        if lockstep is not None:
+            line["secondary"]["lockstep"] = lockstep
+            line["secondary"]["config"]["pipelining"] = ("ShardedFlatIPIndex.submit / result: the exchange + merge of batch n on a side stream "
+                                                         "under the local search of batch n + 1 (one batch of look-ahead)")
+        if equal_shards is not None:
+            line["secondary"]["equal_shards"] = equal_shards
+            line["secondary"]["config"]["sharding"] = "row blocks cut in proportion to each GPU's measured search rate (equal blocks timed first: equal_shards)"
         del index, x
         torch.cuda.empty_cache()
 

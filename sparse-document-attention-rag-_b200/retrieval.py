@@ -259,28 +259,69 @@ class ShardedFlatIPIndex:
             self.ntotal = local.ntotal
 
     def search_device(self, xq: torch.Tensor, k: int):
+        s, i = self.local.search_device(xq, k)
+        return self._finish(s, i, k)
+
+    # -- pipelined form: the exchange of batch n runs on a side stream under the local search of batch n + 1 -------------------
+    def submit(self, xq: torch.Tensor, k: int):
+        """Start a search and return a handle for ``result``.  The local search is enqueued on the current stream; the
+        exchange + merge (which has to wait for the slowest shard of THIS batch) goes to a side stream, so the next
+        ``submit`` is not held back by it: a node's GPUs settle at different clocks under the power cap and a lock-step loop
+        pays the slowest shard of every batch, a pipelined one the mean.  The two receive areas of the peer-memory exchange
+        (alternating by call) are exactly what one batch of look-ahead needs; calls must be made in the same order on every
+        rank, and at most one handle should be outstanding when the next ``submit`` is issued."""
+        s, i = self.local.search_device(xq, k)
+        if self.world == 1 or self.exchange != "p2p" or self.merge_fn is not merge_topk_device:
+            return self._finish(s, i, k), None
+        if self._xchg is None:  # first call: set the symmetric buffer up synchronously (a collective on the host side)
+            out = self._search_exchange_p2p(s, i, k)
+            return (out if out is not None else self._finish(s, i, k)), None
+        dev = s.device
+        if getattr(self, "_xstream", None) is None:
+            self._xstream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self._xstream):
+            self._xstream.wait_event(ready)
+            out = self._search_exchange_p2p(s, i, k)
+            s.record_stream(self._xstream)
+            i.record_stream(self._xstream)
+            done = torch.cuda.Event()
+            done.record(self._xstream)
+        return out, done
+
+    def result(self, handle):
+        """``(scores, ids)`` of a ``submit``: the current stream waits for that batch's exchange."""
+        out, done = handle
+        if done is not None:
+            cur = torch.cuda.current_stream(out[0].device)
+            cur.wait_event(done)
+            out[0].record_stream(cur)
+            out[1].record_stream(cur)
+        return out
+
+    def _finish(self, s, i, k):
+        """Exchange + merge of local results on the current stream (the tail of ``search_device``)."""
         import torch.distributed as dist
 
-        s, i = self.local.search_device(xq, k)
         if self.world == 1:
             return s, i
         Q = s.shape[0]
-        if self.merge_fn is not merge_topk_device:  # injected checker (CPU / gloo tests): plain two-tensor exchange
+        if self.merge_fn is not merge_topk_device:
             gs = torch.empty((self.world * Q, k), dtype=s.dtype, device=s.device)
             gi = torch.empty((self.world * Q, k), dtype=i.dtype, device=i.device)
-            dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)  # rank-major concatenation
+            dist.all_gather_into_tensor(gs, s.contiguous(), group=self.group)
             dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
             return self.merge_fn(gs.view(self.world, Q, k), gi.view(self.world, Q, k), k)
         if self.exchange == "p2p":
             out = self._search_exchange_p2p(s, i, k)
             if out is not None:
                 return out
-        # one exchange: 12-byte {score, id} records, one all-gather over NVLink, merge straight from the gathered records
         lib = _lib.load()
-        st = _lib.stream_ptr(s.device)
         rec = torch.empty((Q, k, 3), dtype=torch.int32, device=s.device)
         _lib.count_launches(2)
-        _lib.check(lib.topk_pack(s.data_ptr(), i.data_ptr(), Q * k, rec.data_ptr(), st), "topk_pack")
+        _lib.check(lib.topk_pack(s.data_ptr(), i.data_ptr(), Q * k, rec.data_ptr(), _lib.stream_ptr(s.device)), "topk_pack")
         gathered = torch.empty((self.world, Q, k, 3), dtype=torch.int32, device=s.device)
         dist.all_gather_into_tensor(gathered, rec, group=self.group)
         out_s = torch.empty((Q, k), dtype=torch.float32, device=s.device)
