@@ -56,6 +56,17 @@ def _worker(rank, world, port, N, d, Q, k, out_dir):
         D, I = sharded.search(q, k)
         np.save(os.path.join(out_dir, f"D{rank}.npy"), D)
         np.save(os.path.join(out_dir, f"I{rank}.npy"), I)
+        # submit / result (the pipelined form): with an injected merge there is no peer-memory exchange to overlap, the
+        # handle must still carry the same merged result, two batches in flight in submission order
+        import torch
+
+        xq = torch.from_numpy(q)
+        h1 = sharded.submit(xq, k)
+        h2 = sharded.submit(xq[:5], k)
+        s1, i1 = sharded.result(h1)
+        s2, i2 = sharded.result(h2)
+        assert np.array_equal(i1.numpy(), I) and np.array_equal(i2.numpy(), I[:5])
+        np.testing.assert_allclose(s1.numpy(), D, rtol=0, atol=0)
         if rank == 0:
             full = FlatIPOracle(d)
             full.add(x)

@@ -41,6 +41,16 @@ def main():
         for rep in range(5):  # repeated calls: the peer-memory exchange alternates its receive areas by call parity
             s_sh, i_sh = sharded.search_device(xq, k)
             ok = ok and bool(torch.equal(i_sh, i_full)) and bool(torch.allclose(s_sh, s_full, rtol=0, atol=1e-6))
+        # pipelined form: two batches in flight (the second batch's local search is enqueued before the first exchange is awaited)
+        prev = None
+        for rep in range(6):
+            h = sharded.submit(xq, k)
+            if prev is not None:
+                s_p, i_p = sharded.result(prev)
+                ok = ok and bool(torch.equal(i_p, i_full)) and bool(torch.allclose(s_p, s_full, rtol=0, atol=1e-6))
+            prev = h
+        s_p, i_p = sharded.result(prev)
+        ok = ok and bool(torch.equal(i_p, i_full)) and bool(torch.allclose(s_p, s_full, rtol=0, atol=1e-6))
         # exchange step alone: time 50 back-to-back searches of a tiny local index (the exchange dominates)
         torch.cuda.synchronize()
         dist.barrier()
