@@ -1128,6 +1128,11 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
       const char* e = getenv("SDAG_IP_EARLY_RESCORE");
       early_env = (e && atoi(e)) ? 1 : 0;
     }
+    static long long fast_growth_rows = -1;  // SDAG_IP_FAST_GROWTH_ROWS: tuning knob for the epoch schedule
+    if (fast_growth_rows < 0) {
+      const char* e = getenv("SDAG_IP_FAST_GROWTH_ROWS");
+      fast_growth_rows = (e && atoll(e) > 0) ? atoll(e) : IP_FAST_GROWTH_ROWS;
+    }
     while (begin < N) {
       long long end = begin + span < N ? begin + span : N;
       const bool fork = early_env && !first && end == N;  // last epoch, and a tighten has already run
@@ -1162,7 +1167,7 @@ int ip_search(const float* xq, int Q, const float* corpus_f32, const void* corpu
       SDAG_CUDA_TRY(cudaGetLastError());
       first = false;
       begin = end;
-      span = begin < IP_FAST_GROWTH_ROWS ? 3 * begin : begin;
+      span = begin < fast_growth_rows ? 3 * begin : begin;
       ++epochs;
     }
     (void)epochs;

@@ -47,6 +47,9 @@ class Retriever(ABC):
         raise NotImplementedError
 
 
+_FAST_GROWTH_ROWS = int(os.environ.get("SDAG_IP_FAST_GROWTH_ROWS", "0")) or 65536  # mirrors ip_search.cu (launch accounting only)
+
+
 def _n_epochs(n_rows: int, cand_cap: int) -> int:
     """Number of (GEMM + tighten) epochs ip_search runs: the first cap/2 rows are dumped, then the swept prefix grows x4
     per epoch below 64 k rows and x2 above (ip_search.cu, IP_FAST_GROWTH_ROWS)."""
@@ -54,7 +57,7 @@ def _n_epochs(n_rows: int, cand_cap: int) -> int:
     done, n = 0, 0
     while done < n_rows:
         done = min(n_rows, done + span)
-        span = 3 * done if done < 65536 else done
+        span = 3 * done if done < _FAST_GROWTH_ROWS else done
         n += 1
     return n
 
